@@ -1,0 +1,311 @@
+// kernels.cu -- sm_100a kernels of the btl_bloomfilter k-mer hot path.
+//
+//   seq_kernel<OP,SPACED,POW2>   fused  stage -> classify/pack -> roll ntHash -> multi-hash -> filter op
+//                                (K1 bf_insert, K2 bf_contains, K3/K4 counting ops, K5 spaced seeds, K6 hash)
+//   cbf_list_kernel              residual rounds of the exact (reference-order) counting insert
+//   popcount_kernel (K8), merge_kernel (K7 local step), synth_*_kernel, random_probe_kernel
+//
+// Memory behaviour: the input is read once with coalesced 16-byte loads and lives in
+// shared memory as 2-bit codes; the filter traffic is one random 32-byte sector per hash (gather for
+// queries, RED.OR / byte update for inserts), so the kernels are bound by HBM random-sector rate.
+#include "tile_core.cuh"
+
+namespace btl {
+
+template<int OP, bool SPACED, bool POW2>
+__global__ void __launch_bounds__(kTPB) seq_kernel(const __grid_constant__ SeqParams P)
+{
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	const TileSmem sm = carve_smem(smem_raw, P.k, SPACED);
+	const int tid = threadIdx.x;
+	const uint64_t t0 = (uint64_t)blockIdx.x * kTile;
+
+	tile_phase_a(P, sm, t0, tid, kTPB);
+	__syncthreads();
+	tile_phase_b(P, sm, t0, tid, kTPB);
+	__syncthreads();
+	ThreadOut out = tile_phase_c<OP, SPACED, POW2>(P, sm, t0, tid);
+
+	// per-thread result words: 32 consecutive windows -> one coalesced 32-bit store per plane
+	uint64_t widx = (t0 >> 5) + tid;
+	if (widx < P.out_words) {
+		if (P.valid_bits)
+			P.valid_bits[widx] = out.validw;
+		if (P.hit_bits)
+			P.hit_bits[widx] = out.hitw;
+	}
+	if (P.stats) {
+		uint32_t nv = __popc(out.validw), nh = __popc(out.hitw);
+		nv = __reduce_add_sync(0xffffffffu, nv);
+		nh = __reduce_add_sync(0xffffffffu, nh);
+		uint32_t* red = reinterpret_cast<uint32_t*>(sm.scratch + 2);
+		if ((tid & 31) == 0) {
+			red[(tid >> 5) * 2] = nv;
+			red[(tid >> 5) * 2 + 1] = nh;
+		}
+		__syncthreads();
+		if (tid == 0) {
+			uint32_t sv = 0, sh = 0;
+			for (int w = 0; w < kTPB / 32; w++) {
+				sv += red[w * 2];
+				sh += red[w * 2 + 1];
+			}
+			if (sv)
+				atomicAdd((unsigned long long*)&P.stats[0], (unsigned long long)sv);
+			if (sh)
+				atomicAdd((unsigned long long*)&P.stats[1], (unsigned long long)sh);
+		}
+	}
+}
+
+size_t seq_kernel_smem_bytes(uint32_t k, bool spaced)
+{
+	return tile_smem_bytes(k, spaced);
+}
+
+template<int OP, bool SPACED, bool POW2>
+static cudaError_t launch_one(const SeqParams& P, cudaStream_t stream)
+{
+	size_t smem = tile_smem_bytes(P.k, SPACED);
+	auto kern = seq_kernel<OP, SPACED, POW2>;
+	if (smem > 48 * 1024) {
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess)
+			return e;
+	}
+	uint64_t tiles = (P.n_windows + kTile - 1) / kTile;
+	if (tiles == 0)
+		return cudaSuccess;
+	if (tiles > 0x7fffffffULL)
+		return cudaErrorInvalidValue;
+	kern<<<(unsigned)tiles, kTPB, smem, stream>>>(P);
+	return cudaGetLastError();
+}
+
+template<int OP>
+static cudaError_t launch_op(const SeqParams& P, cudaStream_t stream)
+{
+	bool spaced = P.n_seeds != 0, pow2 = P.fm.pow2 != 0;
+	if (spaced)
+		return pow2 ? launch_one<OP, true, true>(P, stream) : launch_one<OP, true, false>(P, stream);
+	return pow2 ? launch_one<OP, false, true>(P, stream) : launch_one<OP, false, false>(P, stream);
+}
+
+cudaError_t launch_seq(SeqOp op, const SeqParams& P, cudaStream_t stream)
+{
+	switch (op) {
+	case OP_HASH: return launch_op<OP_HASH>(P, stream);
+	case OP_BF_INSERT: return launch_op<OP_BF_INSERT>(P, stream);
+	case OP_BF_CONTAINS: return launch_op<OP_BF_CONTAINS>(P, stream);
+	case OP_CBF_MINCOUNT: return launch_op<OP_CBF_MINCOUNT>(P, stream);
+	case OP_CBF_INCALL: return launch_op<OP_CBF_INCALL>(P, stream);
+	case OP_CBF_TOUCH: return launch_op<OP_CBF_TOUCH>(P, stream);
+	case OP_CBF_COMMIT: return launch_op<OP_CBF_COMMIT>(P, stream);
+	case OP_CBF_CLEAR: return launch_op<OP_CBF_CLEAR>(P, stream);
+	case OP_BF_INSERT_CHECK: return launch_op<OP_BF_INSERT_CHECK>(P, stream);
+	}
+	return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------- exact counting insert, residual rounds
+template<bool POW2>
+__global__ void __launch_bounds__(128) cbf_list_kernel(int phase, const __grid_constant__ SeqParams P,
+                                                       const __grid_constant__ ListParams L)
+{
+	uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+	list_phase<POW2>(phase, P, L, item);
+}
+
+cudaError_t launch_cbf_list_phase(int phase, const SeqParams& P, const ListParams& L, cudaStream_t stream)
+{
+	if (L.max_items == 0)
+		return cudaSuccess;
+	unsigned grid = (L.max_items + 127) / 128;
+	if (P.fm.pow2)
+		cbf_list_kernel<true><<<grid, 128, 0, stream>>>(phase, P, L);
+	else
+		cbf_list_kernel<false><<<grid, 128, 0, stream>>>(phase, P, L);
+	return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- K8: popcount / count_nonzero / count_ge
+// mode 0: set bits, 1: non-zero bytes, 2: bytes >= threshold
+__global__ void __launch_bounds__(256) popcount_kernel(const uint8_t* __restrict__ data, uint64_t nbytes, int mode,
+                                                       unsigned threshold, unsigned long long* out)
+{
+	uint64_t nvec = nbytes / 16;
+	const uint4* v = reinterpret_cast<const uint4*>(data);
+	uint32_t thr4 = (threshold & 255u) * 0x01010101u;
+	unsigned long long acc = 0;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint4 x = __ldg(v + i);
+		if (mode == 0)
+			acc += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+		else if (mode == 1)
+			acc += (__popc(__vcmpne4(x.x, 0)) + __popc(__vcmpne4(x.y, 0)) + __popc(__vcmpne4(x.z, 0)) +
+			        __popc(__vcmpne4(x.w, 0))) >> 3;
+		else
+			acc += (__popc(__vcmpgeu4(x.x, thr4)) + __popc(__vcmpgeu4(x.y, thr4)) +
+			        __popc(__vcmpgeu4(x.z, thr4)) + __popc(__vcmpgeu4(x.w, thr4))) >> 3;
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		for (uint64_t b = nvec * 16; b < nbytes; b++) {
+			uint8_t c = data[b];
+			acc += mode == 0 ? __popc((unsigned)c) : mode == 1 ? (c != 0) : (c >= threshold);
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1)
+		acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	__shared__ unsigned long long red[8];
+	if ((threadIdx.x & 31) == 0)
+		red[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned long long s = 0;
+		for (int w = 0; w < 8; w++)
+			s += red[w];
+		if (s)
+			atomicAdd(out, s);
+	}
+}
+
+cudaError_t launch_popcount(const void* data, uint64_t nbytes, int mode, unsigned threshold,
+                            unsigned long long* d_out, cudaStream_t stream)
+{
+	uint64_t nvec = nbytes / 16;
+	uint64_t want = (nvec + 255) / 256;
+	unsigned grid = (unsigned)(want < 1 ? 1 : want > 148 * 16 ? 148 * 16 : want);
+	popcount_kernel<<<grid, 256, 0, stream>>>((const uint8_t*)data, nbytes, mode, threshold, d_out);
+	return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- K7 local step: dst |= src  /  dst = sat(dst + src)
+__global__ void __launch_bounds__(256) merge_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src,
+                                                    uint64_t nbytes, int sat_add)
+{
+	uint64_t nvec = nbytes / 16;
+	uint4* d = reinterpret_cast<uint4*>(dst);
+	const uint4* s = reinterpret_cast<const uint4*>(src);
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint4 a = d[i], b = s[i];
+		if (sat_add) {
+			a.x = __vaddus4(a.x, b.x); a.y = __vaddus4(a.y, b.y);
+			a.z = __vaddus4(a.z, b.z); a.w = __vaddus4(a.w, b.w);
+		} else {
+			a.x |= b.x; a.y |= b.y; a.z |= b.z; a.w |= b.w;
+		}
+		d[i] = a;
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		for (uint64_t b = nvec * 16; b < nbytes; b++) {
+			unsigned x = dst[b], y = src[b];
+			dst[b] = sat_add ? (uint8_t)(x + y > 255 ? 255 : x + y) : (uint8_t)(x | y);
+		}
+	}
+}
+
+cudaError_t launch_merge(void* dst, const void* src, uint64_t nbytes, int saturating_add, cudaStream_t stream)
+{
+	uint64_t nvec = nbytes / 16;
+	uint64_t want = (nvec + 255) / 256;
+	unsigned grid = (unsigned)(want < 1 ? 1 : want > 148 * 8 ? 148 * 8 : want);
+	merge_kernel<<<grid, 256, 0, stream>>>((uint8_t*)dst, (const uint8_t*)src, nbytes, saturating_add);
+	return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- synthetic inputs
+__global__ void __launch_bounds__(256) synth_genome_kernel(uint8_t* out, uint64_t start, uint64_t n, uint64_t seed)
+{
+	// one thread = 16 output bases (a 16-byte store when aligned)
+	uint64_t nchunks = (n + 15) / 16;
+	for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t o = c * 16;
+		uint8_t b[16];
+#pragma unroll
+		for (int j = 0; j < 16; j++)
+			b[j] = "ACGT"[synth_code(start + o + j, seed)];
+		if (o + 16 <= n && ((((uintptr_t)out) + o) & 15u) == 0) {
+			uint4 v;
+			v.x = b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24);
+			v.y = b[4] | (b[5] << 8) | (b[6] << 16) | ((uint32_t)b[7] << 24);
+			v.z = b[8] | (b[9] << 8) | (b[10] << 16) | ((uint32_t)b[11] << 24);
+			v.w = b[12] | (b[13] << 8) | (b[14] << 16) | ((uint32_t)b[15] << 24);
+			*reinterpret_cast<uint4*>(out + o) = v;
+		} else {
+			for (int j = 0; j < 16 && o + j < n; j++)
+				out[o + j] = b[j];
+		}
+	}
+}
+
+cudaError_t launch_synth_genome(uint8_t* out, uint64_t start, uint64_t n, uint64_t seed, cudaStream_t stream)
+{
+	if (n == 0)
+		return cudaSuccess;
+	uint64_t want = ((n + 15) / 16 + 255) / 256;
+	unsigned grid = (unsigned)(want > 148 * 32 ? 148 * 32 : want);
+	synth_genome_kernel<<<grid, 256, 0, stream>>>(out, start, n, seed);
+	return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) synth_reads_kernel(uint8_t* out, uint64_t first_read, uint64_t n_reads,
+                                                          unsigned read_len, uint64_t g_len, uint64_t gseed,
+                                                          uint64_t rseed)
+{
+	uint64_t total = n_reads * read_len;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t r = i / read_len;
+		unsigned j = (unsigned)(i - r * read_len);
+		uint64_t st = splitmix64(rseed + first_read + r) % (g_len - read_len);
+		out[i] = "ACGT"[synth_code(st + j, gseed)];
+	}
+}
+
+cudaError_t launch_synth_reads(uint8_t* out, uint64_t first_read, uint64_t n_reads, unsigned read_len,
+                               uint64_t g_len, uint64_t gseed, uint64_t rseed, cudaStream_t stream)
+{
+	uint64_t total = n_reads * read_len;
+	if (total == 0)
+		return cudaSuccess;
+	uint64_t want = (total + 255) / 256;
+	unsigned grid = (unsigned)(want > 148 * 64 ? 148 * 64 : want);
+	synth_reads_kernel<<<grid, 256, 0, stream>>>(out, first_read, n_reads, read_len, g_len, gseed, rseed);
+	return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- random-sector probe (roofline denominator)
+__global__ void __launch_bounds__(256) random_probe_kernel(uint32_t* arr, uint64_t n_words, uint64_t n_access, int mode,
+                                                           unsigned long long* sink)
+{
+	uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+	uint32_t acc = 0;
+	FastMod fm = make_fastmod(n_words);
+	for (uint64_t i = tid * 4; i < n_access; i += nthreads * 4) {
+		uint64_t r0 = splitmix64(i), r1 = splitmix64(i + 1), r2 = splitmix64(i + 2), r3 = splitmix64(i + 3);
+		uint64_t a0 = fm.pow2 ? fastmod<true>(r0, fm) : fastmod<false>(r0, fm);
+		uint64_t a1 = fm.pow2 ? fastmod<true>(r1, fm) : fastmod<false>(r1, fm);
+		uint64_t a2 = fm.pow2 ? fastmod<true>(r2, fm) : fastmod<false>(r2, fm);
+		uint64_t a3 = fm.pow2 ? fastmod<true>(r3, fm) : fastmod<false>(r3, fm);
+		if (mode == 0) {
+			uint32_t v0 = __ldg(arr + a0), v1 = __ldg(arr + a1), v2 = __ldg(arr + a2), v3 = __ldg(arr + a3);
+			acc += v0 + v1 + v2 + v3;
+		} else {
+			atomicOr(arr + a0, 1u << (r0 >> 59));
+			atomicOr(arr + a1, 1u << (r1 >> 59));
+			atomicOr(arr + a2, 1u << (r2 >> 59));
+			atomicOr(arr + a3, 1u << (r3 >> 59));
+		}
+	}
+	if (mode == 0 && acc == 0x9e3779b9u)
+		atomicAdd(sink, 1ull);
+}
+
+cudaError_t launch_random_probe(uint32_t* arr, uint64_t n_words, uint64_t n_access, int mode,
+                                unsigned long long* d_sink, cudaStream_t stream)
+{
+	random_probe_kernel<<<148 * 8, 256, 0, stream>>>(arr, n_words, n_access, mode, d_sink);
+	return cudaGetLastError();
+}
+
+} // namespace btl

@@ -1,0 +1,99 @@
+// kernels.cuh -- launch interface between the C ABI (capi.cu) and the sm_100a kernels (kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nthash_dev.cuh"
+
+namespace btl {
+
+constexpr int kMaxHash = 64;  // hashes per k-mer (hash_num, or n_seeds*h2)
+constexpr int kMaxSeeds = 16; // spaced seeds
+constexpr int kTPB = 128;     // threads per CTA of the sequence kernels
+constexpr int kWPT = 32;      // consecutive windows rolled by one thread
+constexpr int kTile = kTPB * kWPT; // windows per tile (4096)
+
+enum SeqOp {
+	OP_HASH = 0,         // emit raw hashes / strands / valid bits
+	OP_BF_INSERT = 1,    // BloomFilter::insert
+	OP_BF_CONTAINS = 2,  // BloomFilter::contains
+	OP_CBF_MINCOUNT = 3, // CountingBloomFilter::minCount (+ contains via threshold)
+	OP_CBF_INCALL = 4,   // CountingBloomFilter::incrementAll
+	OP_CBF_TOUCH = 5,    // exact incrementMin, phase 1: mark reservation bits
+	OP_CBF_COMMIT = 6,   // exact incrementMin, phase 2: commit uncontended k-mers, defer the rest
+	OP_CBF_CLEAR = 7,    // exact incrementMin, phase 3: clear the reservation bits this batch set
+	OP_BF_INSERT_CHECK = 8 // BloomFilter::insertAndCheck (atomic fetch-or; exact when k-mers are distinct)
+};
+
+struct SeqParams
+{
+	// input batch (device pointers)
+	const uint8_t* bases;    // chunk of the flat base stream
+	uint64_t n_bases;        // bytes readable at `bases`
+	uint64_t base0;          // flat position of bases[0] in the whole batch (for offsets lookup)
+	uint64_t n_windows;      // windows [0, n_windows) of this chunk are processed by this launch
+	const uint64_t* offsets; // n_seqs + 1 flat sequence offsets of the whole batch
+	uint64_t n_seqs;
+	// hashing
+	uint32_t k, h;           // k-mer size, hashes per k-mer
+	uint32_t n_seeds, h2;    // spaced seeds: h == n_seeds*h2
+	const uint64_t* st_tab;  // spaced: TF[k][8] then TR[k][8]
+	const uint16_t* st_dc;   // spaced: concatenated don't-care positions
+	uint32_t st_dc_off[kMaxSeeds + 1];
+	uint64_t mult[kMaxHash]; // mult[i] = i ^ k*multiSeed (i >= 1)
+	uint64_t g_f[16], g_fk[16], g_r[16], g_rk[16]; // seed tables by base class; *k = R^k applied
+	// filter
+	void* filter;
+	FastMod fm;
+	uint32_t threshold;
+	// exact counting insert: reservation bit tables (touched / contended), 2^resv_log2 bits each
+	uint32_t* resv_touched;
+	uint32_t* resv_contended;
+	uint32_t resv_log2;
+	uint32_t* pending;       // deferred window list (chunk-local window indices)
+	uint32_t* pending_count;
+	// outputs (chunk-local indexing by window)
+	uint32_t* hit_bits;
+	uint32_t* valid_bits;
+	uint64_t out_words;      // uint32 words available in hit_bits / valid_bits
+	uint8_t* counts;
+	uint64_t* hashes;
+	uint8_t* strands;
+	uint64_t* stats; // [0] += valid k-mers, [1] += hits
+	// knobs
+	uint32_t force_generic;
+	uint32_t query_mode;
+};
+
+size_t seq_kernel_smem_bytes(uint32_t k, bool spaced);
+// launches seq_kernel<op> for P on stream; returns cudaGetLastError()
+cudaError_t launch_seq(SeqOp op, const SeqParams& P, cudaStream_t stream);
+
+// exact incrementMin on a compacted list of deferred windows (P.pending / P.pending_count)
+struct ListParams
+{
+	const uint32_t* list_in;
+	const uint32_t* count_in;
+	uint32_t* list_out;
+	uint32_t* count_out;
+	uint32_t* resv_idx; // 2^resv_idx_log2 uint32 entries for index reservation
+	uint32_t resv_idx_log2;
+	uint32_t epoch;     // high byte of the reservation word (smaller wins)
+	uint32_t max_items;
+};
+cudaError_t launch_cbf_list_phase(int phase, const SeqParams& P, const ListParams& L,
+                                  cudaStream_t stream);
+
+cudaError_t launch_popcount(const void* data, uint64_t nbytes, int mode, unsigned threshold,
+                            unsigned long long* d_out, cudaStream_t stream);
+cudaError_t launch_merge(void* dst, const void* src, uint64_t nbytes, int saturating_add,
+                         cudaStream_t stream);
+cudaError_t launch_synth_genome(uint8_t* out, uint64_t start, uint64_t n, uint64_t seed,
+                                cudaStream_t stream);
+cudaError_t launch_synth_reads(uint8_t* out, uint64_t first_read, uint64_t n_reads,
+                               unsigned read_len, uint64_t g_len, uint64_t gseed, uint64_t rseed,
+                               cudaStream_t stream);
+cudaError_t launch_random_probe(uint32_t* arr, uint64_t n_words, uint64_t n_access, int mode,
+                                unsigned long long* d_sink, cudaStream_t stream);
+
+} // namespace btl

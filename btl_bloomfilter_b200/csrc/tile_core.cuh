@@ -1,0 +1,646 @@
+// tile_core.cuh -- the body of the fused sequence kernels, written as per-thread phase functions.
+//
+// One CTA (kTPB threads) processes one tile of kTile consecutive window start positions of the flat
+// base stream:
+//   phase A  stage the tile's ASCII bytes (+ k-1 halo) into shared memory with 16-byte loads,
+//            find the first sequence boundary of the tile (binary search in the offsets array)
+//   phase B  classify the bytes (seedTab semantics) in place, pack them into 2-bit codes + an
+//            invalid-bit plane, mark sequence starts in a start-bit plane
+//   phase C  every thread rolls the canonical ntHash over its kWPT consecutive windows: O(k) seeding
+//            once, then one split-rotate step per window from register-resident 2-bit streams; each
+//            valid window is extended to its h hashes and handed to the fused filter operation
+//            (atomicOr bit set / word gather + test / counter gather + min / ...).
+// The phases are separated by __syncthreads() in kernels.cu.  The functions are host+device and take
+// the thread index as an argument so that tests/emu/ can run the very same source on the CPU
+// (test infrastructure; the product only ever runs them inside the CUDA kernels).
+//
+// Reference semantics reproduced (upstream paths): vendor/ntHashIterator.hpp:59-86 (which windows
+// are visited), vendor/nthash.hpp:667-692,581-590 (NTMC64), :820-878 (NTMSM64),
+// BloomFilter.hpp:185-194,252-262, CountingBloomFilter.hpp:53-64,134-183,190-196.
+#pragma once
+#include "kernels.cuh"
+
+namespace btl {
+
+// ---------------------------------------------------------------- memory-operation shims
+#if defined(__CUDA_ARCH__)
+BTL_HD uint32_t mem_atomic_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
+BTL_HD void mem_red_or(uint32_t* p, uint32_t v) { atomicOr(p, v); } // result unused -> RED.OR
+BTL_HD uint32_t mem_atomic_cas(uint32_t* p, uint32_t c, uint32_t v) { return atomicCAS(p, c, v); }
+BTL_HD void mem_add64(uint64_t* p, uint64_t v) { atomicAdd((unsigned long long*)p, (unsigned long long)v); }
+BTL_HD uint32_t mem_atomic_inc(uint32_t* p) { return atomicAdd(p, 1u); }
+BTL_HD uint64_t mem_atomic_min64(uint64_t* p, uint64_t v)
+{
+	return atomicMin((unsigned long long*)p, (unsigned long long)v);
+}
+BTL_HD uint32_t ld_ro(const uint32_t* p) { return __ldg(p); }      // read-only filter gathers
+BTL_HD uint8_t ld_ro(const uint8_t* p) { return __ldg(p); }
+BTL_HD uint8_t ld_cg(const uint8_t* p) { return __ldcg(p); }        // L2-coherent counter reads
+BTL_HD uint32_t ld_cg(const uint32_t* p) { return __ldcg(p); }
+BTL_HD uint64_t ld_cg(const uint64_t* p) { return __ldcg((const unsigned long long*)p); }
+#else
+BTL_HD uint32_t mem_atomic_or(uint32_t* p, uint32_t v) { return __sync_fetch_and_or(p, v); }
+BTL_HD void mem_red_or(uint32_t* p, uint32_t v) { __sync_fetch_and_or(p, v); }
+BTL_HD uint32_t mem_atomic_cas(uint32_t* p, uint32_t c, uint32_t v) { return __sync_val_compare_and_swap(p, c, v); }
+BTL_HD void mem_add64(uint64_t* p, uint64_t v) { __sync_fetch_and_add(p, v); }
+BTL_HD uint32_t mem_atomic_inc(uint32_t* p) { return __sync_fetch_and_add(p, 1u); }
+BTL_HD uint64_t mem_atomic_min64(uint64_t* p, uint64_t v)
+{
+	uint64_t old = *p;
+	if (v < old)
+		*p = v;
+	return old;
+}
+BTL_HD uint32_t ld_ro(const uint32_t* p) { return *p; }
+BTL_HD uint8_t ld_ro(const uint8_t* p) { return *p; }
+BTL_HD uint8_t ld_cg(const uint8_t* p) { return *(const volatile uint8_t*)p; }
+BTL_HD uint32_t ld_cg(const uint32_t* p) { return *(const volatile uint32_t*)p; }
+BTL_HD uint64_t ld_cg(const uint64_t* p) { return *(const volatile uint64_t*)p; }
+#endif
+
+BTL_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) // (hi:lo >> sh) low word, sh in [0,31]
+{
+#if defined(__CUDA_ARCH__)
+	return __funnelshift_r(lo, hi, sh);
+#else
+	return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+
+// ---------------------------------------------------------------- shared-memory carve-up
+struct TileSmem
+{
+	uint8_t* tile;     // nb bytes: ASCII, then base classes in place
+	uint32_t* codes;   // 2-bit codes, 16 bases per word
+	uint32_t* badw;    // invalid-bit plane, 32 bases per word
+	uint32_t* startw;  // sequence-start plane, 32 bases per word
+	uint64_t* gtab;    // g_f[16] g_fk[16] g_r[16] g_rk[16]
+	uint64_t* sttab;   // spaced: TF[k][8], TR[k][8]
+	uint8_t* lut;      // byte -> class
+	uint64_t* scratch; // [0] first sequence index of the tile, [1] exotic flag, [2..] reductions
+	uint32_t nb;       // staged bytes (multiple of 32)
+};
+
+BTL_HD uint32_t tile_bytes(uint32_t k)
+{
+	return ((uint32_t)kTile + k - 1 + 31u) / 32u * 32u + 32u;
+}
+
+BTL_HD size_t tile_smem_bytes(uint32_t k, bool spaced)
+{
+	uint32_t nb = tile_bytes(k);
+	size_t s = nb;                       // tile
+	s += (nb / 16 + 4) * 4;              // codes
+	s += (nb / 32 + 4) * 4 * 2;          // badw, startw
+	s += 64 * 8;                         // gtab
+	s += spaced ? (size_t)k * 16 * 8 : 0; // sttab
+	s += 256;                            // lut
+	s += 16 * 8;                         // scratch
+	return (s + 15) / 16 * 16;
+}
+
+BTL_HD TileSmem carve_smem(uint8_t* raw, uint32_t k, bool spaced)
+{
+	TileSmem sm;
+	sm.nb = tile_bytes(k);
+	uint8_t* p = raw;
+	sm.gtab = (uint64_t*)p;    p += 64 * 8;
+	sm.scratch = (uint64_t*)p; p += 16 * 8;
+	sm.sttab = (uint64_t*)p;   p += spaced ? (size_t)k * 16 * 8 : 0;
+	sm.tile = p;               p += sm.nb; // nb is a multiple of 32 -> keeps 16-byte alignment
+	sm.codes = (uint32_t*)p;   p += (sm.nb / 16 + 4) * 4;
+	sm.badw = (uint32_t*)p;    p += (sm.nb / 32 + 4) * 4;
+	sm.startw = (uint32_t*)p;  p += (sm.nb / 32 + 4) * 4;
+	sm.lut = p;
+	return sm;
+}
+
+// ---------------------------------------------------------------- phase A: stage the tile
+BTL_HD void tile_phase_a(const SeqParams& P, const TileSmem& sm, uint64_t t0, int tid, int ntid)
+{
+	// tables
+	for (int i = tid; i < 64; i += ntid)
+		sm.gtab[i] = i < 16 ? P.g_f[i] : i < 32 ? P.g_fk[i - 16] : i < 48 ? P.g_r[i - 32] : P.g_rk[i - 48];
+	for (int i = tid; i < 256; i += ntid)
+		sm.lut[i] = base_class((unsigned)i);
+	if (P.n_seeds)
+		for (uint32_t i = tid; i < P.k * 16; i += ntid)
+			sm.sttab[i] = P.st_tab[i];
+	for (uint32_t i = tid; i < sm.nb / 32 + 4; i += ntid)
+		sm.startw[i] = 0;
+	if (tid == 0)
+		sm.scratch[1] = 0;
+
+	// ASCII bytes [t0, t0+nb) of the chunk, zero (= invalid) beyond its end
+	const uint8_t* src = P.bases + t0;
+	uint64_t avail = P.n_bases > t0 ? P.n_bases - t0 : 0;
+	bool aligned = (((uintptr_t)src) & 15u) == 0;
+	uint32_t nvec = sm.nb / 16;
+	for (uint32_t v = tid; v < nvec; v += ntid) {
+		uint64_t off = (uint64_t)v * 16;
+		uint4 val;
+		if (aligned && off + 16 <= avail) {
+			val = *reinterpret_cast<const uint4*>(src + off);
+		} else {
+			uint32_t w[4] = { 0, 0, 0, 0 };
+			for (int b = 0; b < 16; b++)
+				if (off + b < avail)
+					w[b >> 2] |= (uint32_t)src[off + b] << (8 * (b & 3));
+			val.x = w[0]; val.y = w[1]; val.z = w[2]; val.w = w[3];
+		}
+		*reinterpret_cast<uint4*>(sm.tile + off) = val;
+	}
+
+	// first sequence offset >= flat start of the tile (lower bound over offsets[0..n_seqs])
+	if (tid == 0) {
+		uint64_t gstart = P.base0 + t0;
+		uint64_t lo = 0, hi = P.n_seqs + 1;
+		while (lo < hi) {
+			uint64_t mid = (lo + hi) >> 1;
+			if (P.offsets[mid] < gstart)
+				lo = mid + 1;
+			else
+				hi = mid;
+		}
+		sm.scratch[0] = lo;
+	}
+}
+
+// ---------------------------------------------------------------- phase B: classify + pack
+BTL_HD void tile_phase_b(const SeqParams& P, const TileSmem& sm, uint64_t t0, int tid, int ntid)
+{
+	uint32_t ngroups = sm.nb / 32;
+	uint32_t* tile32 = reinterpret_cast<uint32_t*>(sm.tile);
+	bool exotic = false;
+	for (uint32_t g = tid; g < ngroups; g += ntid) {
+		uint32_t clo = 0, chi = 0, bad = 0;
+#pragma unroll
+		for (int w = 0; w < 8; w++) {
+			uint32_t x = tile32[g * 8 + w];
+			uint32_t y = 0;
+#pragma unroll
+			for (int b = 0; b < 4; b++) {
+				uint32_t cls = sm.lut[(x >> (8 * b)) & 255u];
+				y |= cls << (8 * b);
+				int idx = w * 4 + b; // base index within the group
+				if (idx < 16)
+					clo |= (cls & 3u) << (2 * idx);
+				else
+					chi |= (cls & 3u) << (2 * (idx - 16));
+				bad |= ((cls >> 3) & 1u) << idx;
+				exotic |= (cls & kClsSelf) != 0;
+			}
+			tile32[g * 8 + w] = y;
+		}
+		sm.codes[2 * g] = clo;
+		sm.codes[2 * g + 1] = chi;
+		sm.badw[g] = bad;
+	}
+	if (tid < 4) { // padding words read by the register streams
+		sm.codes[2 * ngroups + tid] = 0;
+		sm.badw[ngroups + tid] = 0xffffffffu;
+	}
+	if (exotic)
+		sm.scratch[1] = 1;
+
+	// sequence starts inside [gstart, gstart + nb)
+	uint64_t gstart = P.base0 + t0, gend = gstart + sm.nb;
+	for (uint64_t i = sm.scratch[0] + (uint64_t)tid; i <= P.n_seqs; i += (uint64_t)ntid) {
+		uint64_t o = P.offsets[i];
+		if (o >= gend)
+			break;
+		uint32_t rel = (uint32_t)(o - gstart);
+#if defined(__CUDA_ARCH__)
+		atomicOr(&sm.startw[rel >> 5], 1u << (rel & 31));
+#else
+		sm.startw[rel >> 5] |= 1u << (rel & 31);
+#endif
+	}
+}
+
+// ---------------------------------------------------------------- per-window hash expansion
+// Calls fn(i, hash_i, strand) for the h hashes of one valid window in reference order; stops early
+// when fn returns false.  w = tile-local window index (spaced seeds re-read the window's classes).
+template<bool SPACED, class Fn>
+BTL_HD void for_each_hash(const SeqParams& P, const TileSmem& sm, uint32_t w, uint64_t F, uint64_t RC, Fn&& fn)
+{
+	if (!SPACED) {
+		bool st = RC < F;
+		uint64_t b = st ? RC : F;
+		if (!fn(0u, b, st))
+			return;
+		for (uint32_t i = 1; i < P.h; i++)
+			if (!fn(i, multi_mix(b, P.mult[i]), st))
+				return;
+	} else {
+		const uint64_t* TF = sm.sttab;
+		const uint64_t* TR = sm.sttab + (size_t)P.k * 8;
+		for (uint32_t j = 0; j < P.n_seeds; j++) {
+			uint64_t fs = F, rs = RC;
+			for (uint32_t t = P.st_dc_off[j]; t < P.st_dc_off[j + 1]; t++) {
+				uint32_t pos = P.st_dc[t];
+				uint32_t c = sm.tile[w + pos] & 7u;
+				fs ^= TF[pos * 8 + c];
+				rs ^= TR[pos * 8 + c];
+			}
+			bool st = rs < fs;
+			uint64_t b = st ? rs : fs;
+			if (!fn(j * P.h2, b, st))
+				return;
+			for (uint32_t j2 = 1; j2 < P.h2; j2++)
+				if (!fn(j * P.h2 + j2, multi_mix(b, P.mult[j2]), st))
+					return;
+		}
+	}
+}
+
+// all h probes of a contiguous-ntHash BloomFilter query issued before any is consumed
+template<int H, bool POW2>
+BTL_HD bool bf_test_unrolled(const SeqParams& P, uint64_t b)
+{
+	const uint32_t* words = (const uint32_t*)P.filter;
+	uint32_t acc = 1;
+	uint32_t bit[H];
+#pragma unroll
+	for (int i = 0; i < H; i++) {
+		uint64_t hv = i ? multi_mix(b, P.mult[i]) : b;
+		uint64_t n = fastmod<POW2>(hv, P.fm);
+		bit[i] = ld_ro(words + (n >> 5)) >> (uint32_t)(n & 31);
+	}
+#pragma unroll
+	for (int i = 0; i < H; i++)
+		acc &= bit[i];
+	return acc & 1u;
+}
+
+template<int H, bool POW2>
+BTL_HD uint32_t cbf_min_unrolled(const SeqParams& P, uint64_t b)
+{
+	const uint8_t* cnt = (const uint8_t*)P.filter;
+	uint32_t v[H];
+#pragma unroll
+	for (int i = 0; i < H; i++) {
+		uint64_t hv = i ? multi_mix(b, P.mult[i]) : b;
+		v[i] = ld_ro(cnt + fastmod<POW2>(hv, P.fm));
+	}
+	uint32_t mn = 255;
+#pragma unroll
+	for (int i = 0; i < H; i++)
+		mn = v[i] < mn ? v[i] : mn;
+	return mn;
+}
+
+// saturating ++ of one 8-bit counter by CAS on its aligned 32-bit word (CountingBloomFilter.hpp:164-183)
+BTL_HD void counter_sat_inc(uint8_t* cnt, uint64_t n)
+{
+	uint32_t* word = reinterpret_cast<uint32_t*>(cnt + (n & ~(uint64_t)3));
+	uint32_t sh = (uint32_t)(n & 3) * 8;
+	uint32_t old = ld_cg(word);
+	for (;;) {
+		if (((old >> sh) & 255u) == 255u)
+			return;
+		uint32_t seen = mem_atomic_cas(word, old, old + (1u << sh));
+		if (seen == old)
+			return;
+		old = seen;
+	}
+}
+
+// exact incrementMin of one k-mer that owns all its slots (CountingBloomFilter.hpp:134-162)
+template<bool SPACED, bool POW2>
+BTL_HD void cbf_commit_one(const SeqParams& P, const TileSmem& sm, uint32_t w, uint64_t F, uint64_t RC)
+{
+	uint8_t* cnt = (uint8_t*)P.filter;
+	uint32_t mn = 255;
+	for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t, uint64_t hv, bool) {
+		uint32_t v = ld_cg(cnt + fastmod<POW2>(hv, P.fm));
+		mn = v < mn ? v : mn;
+		return true;
+	});
+	if (mn == 255)
+		return;
+	for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t, uint64_t hv, bool) {
+		uint64_t n = fastmod<POW2>(hv, P.fm);
+		if (ld_cg(cnt + n) == mn)
+			*(volatile uint8_t*)(cnt + n) = (uint8_t)(mn + 1);
+		return true;
+	});
+}
+
+// ---------------------------------------------------------------- the fused per-window operation
+struct ThreadOut
+{
+	uint32_t validw, hitw; // bit s = window p0+s
+};
+
+template<int OP, bool SPACED, bool POW2>
+BTL_HD void window_op(const SeqParams& P, const TileSmem& sm, uint64_t t0, uint32_t w, uint32_t s,
+                      uint64_t F, uint64_t RC, ThreadOut& out)
+{
+	out.validw |= 1u << s;
+	if (OP == OP_HASH) {
+		uint64_t gw = t0 + w;
+		for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t i, uint64_t hv, bool st) {
+			if (P.hashes)
+				P.hashes[gw * P.h + i] = hv;
+			if (P.strands)
+				P.strands[gw * P.h + i] = SPACED ? (uint8_t)st : 0;
+			return true;
+		});
+	} else if (OP == OP_BF_INSERT) {
+		uint32_t* words = (uint32_t*)P.filter;
+		for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t, uint64_t hv, bool) {
+			uint64_t n = fastmod<POW2>(hv, P.fm);
+			mem_red_or(words + (n >> 5), 1u << (uint32_t)(n & 31));
+			return true;
+		});
+	} else if (OP == OP_BF_INSERT_CHECK) {
+		uint32_t* words = (uint32_t*)P.filter;
+		bool found = true;
+		for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t, uint64_t hv, bool) {
+			uint64_t n = fastmod<POW2>(hv, P.fm);
+			uint32_t bit = 1u << (uint32_t)(n & 31);
+			found &= (mem_atomic_or(words + (n >> 5), bit) & bit) != 0;
+			return true;
+		});
+		if (found)
+			out.hitw |= 1u << s;
+	} else if (OP == OP_BF_CONTAINS) {
+		bool hit;
+		bool done = false;
+		if (!SPACED && P.query_mode == 0) {
+			uint64_t b = RC < F ? RC : F;
+			done = true;
+			switch (P.h) {
+			case 1: hit = bf_test_unrolled<1, POW2>(P, b); break;
+			case 2: hit = bf_test_unrolled<2, POW2>(P, b); break;
+			case 3: hit = bf_test_unrolled<3, POW2>(P, b); break;
+			case 4: hit = bf_test_unrolled<4, POW2>(P, b); break;
+			case 5: hit = bf_test_unrolled<5, POW2>(P, b); break;
+			case 6: hit = bf_test_unrolled<6, POW2>(P, b); break;
+			case 7: hit = bf_test_unrolled<7, POW2>(P, b); break;
+			case 8: hit = bf_test_unrolled<8, POW2>(P, b); break;
+			default: done = false; hit = false; break;
+			}
+		}
+		if (!done) {
+			const uint32_t* words = (const uint32_t*)P.filter;
+			hit = true;
+			for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t, uint64_t hv, bool) {
+				uint64_t n = fastmod<POW2>(hv, P.fm);
+				hit = (ld_ro(words + (n >> 5)) >> (uint32_t)(n & 31)) & 1u;
+				return hit; // early exit on the first miss, BloomFilter.hpp:257-259
+			});
+		}
+		if (hit)
+			out.hitw |= 1u << s;
+	} else if (OP == OP_CBF_MINCOUNT) {
+		uint32_t mn = 255;
+		bool done = false;
+		if (!SPACED) {
+			uint64_t b = RC < F ? RC : F;
+			done = true;
+			switch (P.h) {
+			case 1: mn = cbf_min_unrolled<1, POW2>(P, b); break;
+			case 2: mn = cbf_min_unrolled<2, POW2>(P, b); break;
+			case 3: mn = cbf_min_unrolled<3, POW2>(P, b); break;
+			case 4: mn = cbf_min_unrolled<4, POW2>(P, b); break;
+			case 5: mn = cbf_min_unrolled<5, POW2>(P, b); break;
+			case 6: mn = cbf_min_unrolled<6, POW2>(P, b); break;
+			case 7: mn = cbf_min_unrolled<7, POW2>(P, b); break;
+			case 8: mn = cbf_min_unrolled<8, POW2>(P, b); break;
+			default: done = false; break;
+			}
+		}
+		if (!done) {
+			const uint8_t* cnt = (const uint8_t*)P.filter;
+			for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t, uint64_t hv, bool) {
+				uint32_t v = ld_ro(cnt + fastmod<POW2>(hv, P.fm));
+				mn = v < mn ? v : mn;
+				return true;
+			});
+		}
+		if (P.counts)
+			P.counts[t0 + w] = (uint8_t)mn;
+		if (mn >= P.threshold) // CountingBloomFilter.hpp:190-196
+			out.hitw |= 1u << s;
+	} else if (OP == OP_CBF_INCALL) {
+		uint8_t* cnt = (uint8_t*)P.filter;
+		for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t, uint64_t hv, bool) {
+			counter_sat_inc(cnt, fastmod<POW2>(hv, P.fm));
+			return true;
+		});
+	} else if (OP == OP_CBF_TOUCH) {
+		uint32_t mask = (1u << P.resv_log2) - 1u;
+		for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t, uint64_t hv, bool) {
+			uint32_t e = (uint32_t)fastmod<POW2>(hv, P.fm) & mask;
+			uint32_t bit = 1u << (e & 31);
+			if (mem_atomic_or(P.resv_touched + (e >> 5), bit) & bit)
+				mem_red_or(P.resv_contended + (e >> 5), bit);
+			return true;
+		});
+	} else if (OP == OP_CBF_COMMIT) {
+		uint32_t mask = (1u << P.resv_log2) - 1u;
+		bool contended = false;
+		for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t, uint64_t hv, bool) {
+			uint32_t e = (uint32_t)fastmod<POW2>(hv, P.fm) & mask;
+			contended |= (ld_cg(P.resv_contended + (e >> 5)) >> (e & 31)) & 1u;
+			return true;
+		});
+		if (!contended) {
+			cbf_commit_one<SPACED, POW2>(P, sm, w, F, RC);
+		} else {
+			uint32_t slot = mem_atomic_inc(P.pending_count);
+			P.pending[slot] = (uint32_t)(t0 + w);
+			out.hitw |= 1u << s; // counts deferred k-mers in stats[1]
+		}
+	} else if (OP == OP_CBF_CLEAR) {
+		uint32_t mask = (1u << P.resv_log2) - 1u;
+		for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t, uint64_t hv, bool) {
+			uint32_t e = (uint32_t)fastmod<POW2>(hv, P.fm) & mask;
+			P.resv_touched[e >> 5] = 0;
+			P.resv_contended[e >> 5] = 0;
+			return true;
+		});
+	}
+}
+
+// ---------------------------------------------------------------- phase C: roll + operate
+template<int OP, bool SPACED, bool POW2>
+BTL_HD ThreadOut tile_phase_c(const SeqParams& P, const TileSmem& sm, uint64_t t0, int tid)
+{
+	ThreadOut out;
+	out.validw = 0;
+	out.hitw = 0;
+	uint64_t nwin64 = P.n_windows > t0 ? P.n_windows - t0 : 0;
+	uint32_t nwin = nwin64 > (uint64_t)kTile ? (uint32_t)kTile : (uint32_t)nwin64;
+	uint32_t p0 = (uint32_t)tid * kWPT;
+	if (p0 >= nwin)
+		return out;
+	const uint32_t k = P.k;
+	const uint64_t* Gf = sm.gtab;
+	const uint64_t* Gfk = sm.gtab + 16;
+	const uint64_t* Gr = sm.gtab + 32;
+	const uint64_t* Grk = sm.gtab + 48;
+	uint64_t F = 0, RC = 0;
+	uint32_t g = 0; // hashable bases of the current sequence ending at the newest base
+	uint32_t q1 = p0 + k - 1; // first incoming base
+	bool generic = P.force_generic || sm.scratch[1] != 0;
+
+	if (generic) {
+		// byte-class path: exact for every byte value (self-complementary raw bytes included)
+		for (uint32_t i = 0; i + 1 < k; i++) {
+			uint32_t qa = p0 + i, qb = p0 + k - 2 - i;
+			uint32_t ca = sm.tile[qa], cb = sm.tile[qb];
+			F = srol(F) ^ Gf[ca];
+			RC = srol(RC) ^ Gr[cb];
+			bool st = (sm.startw[qa >> 5] >> (qa & 31)) & 1u;
+			g = (ca & kClsBad) ? 0u : (st ? 1u : g + 1u);
+		}
+		RC = srol(RC);
+		for (uint32_t s = 0; s < (uint32_t)kWPT; s++) {
+			uint32_t q = q1 + s;
+			uint32_t cin = sm.tile[q];
+			F = srol(F) ^ Gf[cin];
+			RC ^= Grk[cin];
+			if (s > 0) {
+				uint32_t cout = sm.tile[p0 + s - 1];
+				F ^= Gfk[cout];
+				RC ^= Gr[cout];
+			}
+			RC = sror(RC);
+			bool st = (sm.startw[q >> 5] >> (q & 31)) & 1u;
+			g = (cin & kClsBad) ? 0u : (st ? 1u : g + 1u);
+			if (g >= k && p0 + s < nwin)
+				window_op<OP, SPACED, POW2>(P, sm, t0, p0 + s, s, F, RC, out);
+		}
+		return out;
+	}
+
+	// 2-bit packed path
+	for (uint32_t i = 0; i + 1 < k; i++) {
+		uint32_t qa = p0 + i, qb = p0 + k - 2 - i;
+		uint32_t ca = (sm.codes[qa >> 4] >> (2 * (qa & 15))) & 3u;
+		uint32_t cb = (sm.codes[qb >> 4] >> (2 * (qb & 15))) & 3u;
+		F = srol(F) ^ Gf[ca];
+		RC = srol(RC) ^ Gr[cb];
+		bool bad = (sm.badw[qa >> 5] >> (qa & 31)) & 1u;
+		bool st = (sm.startw[qa >> 5] >> (qa & 31)) & 1u;
+		g = bad ? 0u : (st ? 1u : g + 1u);
+	}
+	RC = srol(RC);
+	// register streams: 32 incoming bases from q1 (unaligned), 32 outgoing bases from p0 (aligned)
+	uint32_t a = q1 >> 4, sh2 = 2 * (q1 & 15);
+	uint32_t in_lo = funnel_r(sm.codes[a], sm.codes[a + 1], sh2);
+	uint32_t in_hi = funnel_r(sm.codes[a + 1], sm.codes[a + 2], sh2);
+	uint32_t bw = q1 >> 5, sh1 = q1 & 31;
+	uint32_t in_bad = funnel_r(sm.badw[bw], sm.badw[bw + 1], sh1);
+	uint32_t in_start = funnel_r(sm.startw[bw], sm.startw[bw + 1], sh1);
+	uint64_t in_codes = ((uint64_t)in_hi << 32) | in_lo;
+	uint64_t out_codes = ((uint64_t)sm.codes[(p0 >> 4) + 1] << 32) | sm.codes[p0 >> 4];
+#pragma unroll 4
+	for (uint32_t s = 0; s < (uint32_t)kWPT; s++) {
+		uint32_t cin = (uint32_t)in_codes & 3u;
+		in_codes >>= 2;
+		F = srol(F) ^ Gf[cin];
+		RC ^= Grk[cin];
+		if (s > 0) {
+			uint32_t cout = (uint32_t)out_codes & 3u;
+			out_codes >>= 2;
+			F ^= Gfk[cout];
+			RC ^= Gr[cout];
+		}
+		RC = sror(RC);
+		g = ((in_bad >> s) & 1u) ? 0u : (((in_start >> s) & 1u) ? 1u : g + 1u);
+		if (g >= k && p0 + s < nwin)
+			window_op<OP, SPACED, POW2>(P, sm, t0, p0 + s, s, F, RC, out);
+	}
+	return out;
+}
+
+// ---------------------------------------------------------------- deferred-list phases (exact counting insert)
+// One thread = one deferred window; hashes are re-derived directly from the bases (O(k)).
+template<bool POW2, class Fn>
+BTL_HD void list_for_each_hash(const SeqParams& P, uint32_t w, Fn&& fn)
+{
+	const uint8_t* s = P.bases + w;
+	const uint32_t k = P.k;
+	uint64_t F = 0, RC = 0;
+	for (uint32_t i = 0; i < k; i++) {
+		F = srol(F) ^ class_fseed(base_class(s[i]));
+		RC = srol(RC) ^ class_rseed(base_class(s[k - 1 - i]));
+	}
+	if (P.n_seeds == 0) {
+		uint64_t b = RC < F ? RC : F;
+		if (!fn(fastmod<POW2>(b, P.fm)))
+			return;
+		for (uint32_t i = 1; i < P.h; i++)
+			if (!fn(fastmod<POW2>(multi_mix(b, P.mult[i]), P.fm)))
+				return;
+	} else {
+		const uint64_t* TF = P.st_tab;
+		const uint64_t* TR = P.st_tab + (size_t)k * 8;
+		for (uint32_t j = 0; j < P.n_seeds; j++) {
+			uint64_t fs = F, rs = RC;
+			for (uint32_t t = P.st_dc_off[j]; t < P.st_dc_off[j + 1]; t++) {
+				uint32_t pos = P.st_dc[t];
+				uint32_t c = base_class(s[pos]) & 7u;
+				fs ^= TF[pos * 8 + c];
+				rs ^= TR[pos * 8 + c];
+			}
+			uint64_t b = rs < fs ? rs : fs;
+			if (!fn(fastmod<POW2>(b, P.fm)))
+				return;
+			for (uint32_t j2 = 1; j2 < P.h2; j2++)
+				if (!fn(fastmod<POW2>(multi_mix(b, P.mult[j2]), P.fm)))
+					return;
+		}
+	}
+}
+
+// phase 0: reserve every slot with (epoch, window index); the smallest value wins, i.e. the newest
+// round and, within it, the earliest k-mer in reference order.
+// phase 1: a k-mer holding all its reservations commits; the others go to list_out.
+template<bool POW2>
+BTL_HD void list_phase(int phase, const SeqParams& P, const ListParams& L, uint32_t item)
+{
+	uint32_t n = *L.count_in;
+	if (item >= n)
+		return;
+	uint32_t w = L.list_in[item];
+	uint64_t* R = reinterpret_cast<uint64_t*>(L.resv_idx);
+	uint64_t emask = ((uint64_t)1 << L.resv_idx_log2) - 1;
+	uint64_t tag = ((uint64_t)(0xffffffffu - L.epoch) << 32) | w;
+	if (phase == 0) {
+		list_for_each_hash<POW2>(P, w, [&](uint64_t slot) {
+			mem_atomic_min64(R + (slot & emask), tag);
+			return true;
+		});
+	} else {
+		bool own = true;
+		list_for_each_hash<POW2>(P, w, [&](uint64_t slot) {
+			own = ld_cg(R + (slot & emask)) == tag;
+			return own;
+		});
+		if (own) {
+			uint8_t* cnt = (uint8_t*)P.filter;
+			uint32_t mn = 255;
+			list_for_each_hash<POW2>(P, w, [&](uint64_t slot) {
+				uint32_t v = ld_cg(cnt + slot);
+				mn = v < mn ? v : mn;
+				return true;
+			});
+			if (mn != 255)
+				list_for_each_hash<POW2>(P, w, [&](uint64_t slot) {
+					if (ld_cg(cnt + slot) == mn)
+						*(volatile uint8_t*)(cnt + slot) = (uint8_t)(mn + 1);
+					return true;
+				});
+		} else {
+			uint32_t o = mem_atomic_inc(L.count_out);
+			L.list_out[o] = w;
+		}
+	}
+}
+
+} // namespace btl

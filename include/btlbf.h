@@ -1,0 +1,164 @@
+/*
+ * btlbf.h -- C ABI of libbtlbf_cuda.so: the B200 (sm_100a) k-mer insert/query hot path of
+ * bcgsc/btl_bloomfilter (canonical ntHash / spaced-seed ntHash fused with BloomFilter and
+ * CountingBloomFilter<uint8_t> insert/contains).
+ *
+ * Plain pointers and sizes only; every call returns an int status (BTLBF_OK == 0) and leaves a
+ * message for btlbf_last_error() on failure.  Nothing here exits the process or throws.  There is
+ * NO CPU fallback: every entry point fails with BTLBF_ERR_CUDA when no sm_100-class device is usable.
+ *
+ * Reference interfaces replaced (paths relative to the upstream tree):
+ *   - the per-k-mer loop  ntHashIterator itr(seq,h,k); while(itr!=itr.end()){ bloom.insert(*itr); ++itr; }
+ *     README.md:30-43, BloomFilterUtil.h:10-17 (insertSeq), Tests/AdHoc/ParallelFilter.cpp:78-122
+ *       -> btlbf_insert_seqs / btlbf_insert_seqs_dev
+ *   - the query twin (bloom.contains(*itr)), README.md:46-57, BloomFilter.hpp:252-262,
+ *     CountingBloomFilter.hpp:190-196            -> btlbf_contains_seqs / _dev
+ *   - CountingBloomFilter<uint8_t>::minCount, CountingBloomFilter.hpp:53-64 -> btlbf_mincount_seqs
+ *   - CountingBloomFilter<uint8_t>::incrementAll, :164-183                   -> btlbf_increment_all_seqs
+ *   - BloomFilter::insertAndCheck, BloomFilter.hpp:200-214                   -> btlbf_insert_and_check_seqs
+ *   - ntHashIterator::operator* / stHashIterator::operator*, strandArray()
+ *     (vendor/ntHashIterator.hpp:93-96, vendor/stHashIterator.hpp:94-104)    -> btlbf_hash_seqs
+ *   - BloomFilter::getPop (BloomFilter.hpp:316-323), CountingBloomFilter::popCount /
+ *     filtered_popcount (CountingBloomFilter.hpp:216-242)                    -> btlbf_filter_popcount / _count_ge
+ *   - the raw filter array m_filter (BloomFilter.hpp:436, CountingBloomFilter.hpp:102) that
+ *     storeFilter/loadFilter write/read after the TOML header               -> btlbf_filter_upload / _download
+ *
+ * Batch convention (shared with the test oracle):
+ *   bases   : all sequences concatenated without separators (any byte values; validity follows the
+ *             reference's seedTab: A C G T U a c g t u and raw bytes 1 3 4 5 7 hash, all else breaks k-mers)
+ *   offsets : n_seqs+1 monotone offsets, offsets[0]==0, offsets[n_seqs]==n_bases
+ *   window p: the k-mer whose first base is flat position p.  Per-window outputs are indexed by p:
+ *             bit p of a little-endian bit array (byte p/8, mask 1<<(p%8)) of ceil(n_bases/32)*4 bytes,
+ *             or element p of a per-window array.  Invalid windows (non-hashable byte inside, crossing
+ *             a sequence end, sequence shorter than k) have valid=0, hit=0, count=0, hashes=0.
+ *   The reference's iterator visits exactly the valid windows of each sequence in ascending p.
+ */
+#ifndef BTLBF_H
+#define BTLBF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BTLBF_VERSION 100
+
+enum {
+	BTLBF_OK = 0,
+	BTLBF_ERR_ARG = 1,     /* invalid argument (size not multiple of 8, k == 0, bad seeds, ...) */
+	BTLBF_ERR_CUDA = 2,    /* CUDA runtime / device error, or no usable device */
+	BTLBF_ERR_NOMEM = 3,   /* host or device allocation failed */
+	BTLBF_ERR_STATE = 4    /* handle used in a way its kind does not support */
+};
+
+enum {
+	BTLBF_BLOOM = 0,       /* BloomFilter: size = number of bits (multiple of 8), BloomFilter.hpp:389-399 */
+	BTLBF_COUNTING8 = 1    /* CountingBloomFilter<uint8_t>: size = number of 8-bit counters */
+};
+
+typedef struct btlbf_ctx btlbf_ctx;       /* one per GPU: streams, staging buffers, constants */
+typedef struct btlbf_filter btlbf_filter; /* one filter resident in that GPU's HBM */
+
+const char *btlbf_last_error(void); /* thread-local, never NULL */
+int btlbf_version(void);
+int btlbf_device_count(int *count);
+
+/* ---- context ---- */
+int btlbf_ctx_create(int device, btlbf_ctx **ctx);
+int btlbf_ctx_destroy(btlbf_ctx *ctx);
+/* Run all kernels of this context on a caller-owned cudaStream_t (e.g. torch's current stream);
+ * NULL restores the context's own stream. */
+int btlbf_ctx_set_stream(btlbf_ctx *ctx, void *cuda_stream);
+int btlbf_ctx_sync(btlbf_ctx *ctx);
+/* number of kernels this context has launched so far (for accounting / tests) */
+int btlbf_ctx_launch_count(btlbf_ctx *ctx, uint64_t *count);
+/* tuning / debugging knobs: "force_generic" (1: byte-LUT hashing path for every tile),
+ * "query_mode" (0: all probes in flight, 1: early-exit probing), "chunk_bases", "cbf_batch" */
+int btlbf_ctx_set_option(btlbf_ctx *ctx, const char *key, int64_t value);
+
+/* ---- filters ---- */
+/* size: bits (BTLBF_BLOOM, multiple of 8) or counters (BTLBF_COUNTING8); zero-initialised like
+ * BloomFilter::initSize / CountingBloomFilter's ctor.  threshold is CountingBloomFilter's
+ * m_countThreshold (ignored for BTLBF_BLOOM). */
+int btlbf_filter_create(btlbf_ctx *ctx, int kind, uint64_t size, unsigned hash_num,
+                        unsigned kmer_size, unsigned threshold, btlbf_filter **filter);
+/* Same, but over caller-owned device memory (e.g. a torch uint8 tensor) of >= round_up(bytes,16)
+ * bytes, 16-byte aligned; the memory is used as is (not cleared). */
+int btlbf_filter_wrap(btlbf_ctx *ctx, int kind, uint64_t size, unsigned hash_num,
+                      unsigned kmer_size, unsigned threshold, void *device_ptr,
+                      uint64_t capacity_bytes, btlbf_filter **filter);
+int btlbf_filter_destroy(btlbf_filter *f);
+int btlbf_filter_clear(btlbf_filter *f);
+int btlbf_filter_info(btlbf_filter *f, int *kind, uint64_t *size, uint64_t *size_bytes,
+                      unsigned *hash_num, unsigned *kmer_size, unsigned *threshold);
+int btlbf_filter_set_threshold(btlbf_filter *f, unsigned threshold);
+/* the raw array exactly as the reference keeps it in host memory / writes it to the file body */
+int btlbf_filter_upload(btlbf_filter *f, const void *host, uint64_t nbytes);
+int btlbf_filter_download(btlbf_filter *f, void *host, uint64_t nbytes);
+int btlbf_filter_device_ptr(btlbf_filter *f, void **device_ptr, uint64_t *nbytes);
+/* BLOOM: number of set bits (getPop); COUNTING8: number of non-zero counters (popCount) */
+int btlbf_filter_popcount(btlbf_filter *f, uint64_t *count);
+/* COUNTING8: number of counters >= threshold (filtered_popcount with an explicit threshold) */
+int btlbf_filter_count_ge(btlbf_filter *f, unsigned threshold, uint64_t *count);
+/* Spaced-seed mode (stHashIterator): n_seeds strings of exactly kmer_size chars, '1' = care,
+ * anything else = don't care; h2 hashes per seed; requires hash_num == n_seeds*h2.
+ * n_seeds == 0 returns the filter to contiguous ntHash mode. */
+int btlbf_filter_set_seeds(btlbf_filter *f, const char *const *seeds, unsigned n_seeds, unsigned h2);
+/* this |= other (BLOOM) or saturating this += other (COUNTING8); src is a device pointer to a raw
+ * array of the same size (a peer GPU's mapped memory is fine): the local step of the multi-GPU merge */
+int btlbf_filter_merge_from_device(btlbf_filter *f, const void *src_device, uint64_t nbytes);
+
+/* ---- batched sequence operations, HOST buffers (copies are inside the call) ---- */
+/* All outputs may be NULL when not wanted.  n_kmers = number of valid windows processed. */
+int btlbf_insert_seqs(btlbf_filter *f, const char *bases, const uint64_t *offsets, uint64_t n_seqs,
+                      uint64_t *n_kmers);
+int btlbf_contains_seqs(btlbf_filter *f, const char *bases, const uint64_t *offsets,
+                        uint64_t n_seqs, uint8_t *hit_bits, uint8_t *valid_bits, uint64_t *n_kmers,
+                        uint64_t *n_hits);
+int btlbf_insert_and_check_seqs(btlbf_filter *f, const char *bases, const uint64_t *offsets,
+                                uint64_t n_seqs, uint8_t *found_bits, uint8_t *valid_bits,
+                                uint64_t *n_kmers);
+int btlbf_mincount_seqs(btlbf_filter *f, const char *bases, const uint64_t *offsets,
+                        uint64_t n_seqs, uint8_t *counts, uint8_t *valid_bits, uint64_t *n_kmers);
+int btlbf_increment_all_seqs(btlbf_filter *f, const char *bases, const uint64_t *offsets,
+                             uint64_t n_seqs, uint64_t *n_kmers);
+/* raw iterator output: hashes[p*H + i]; strands[p*H + i] (spaced seeds only, else zero).
+ * seeds == NULL / n_seeds == 0: ntHashIterator with H = hash_num;
+ * else stHashIterator with H = n_seeds*h2 (hash_num is ignored). */
+int btlbf_hash_seqs(btlbf_ctx *ctx, unsigned hash_num, unsigned kmer_size, const char *const *seeds,
+                    unsigned n_seeds, unsigned h2, const char *bases, const uint64_t *offsets,
+                    uint64_t n_seqs, uint64_t *hashes, uint8_t *strands, uint8_t *valid_bits,
+                    uint64_t *n_kmers);
+
+/* ---- the same operations on DEVICE-resident batches (asynchronous on the context's stream) ---- */
+/* d_bases: n_bases bytes, 16-byte aligned; d_offsets: n_seqs+1 uint64; d_hit_bits / d_valid_bits:
+ * ceil(n_bases/32) uint32 words; d_stats: 2 uint64 slots that are INCREMENTED by {n_kmers, n_hits}
+ * (may be NULL).  Call btlbf_ctx_sync (or synchronise the stream) before reading results. */
+int btlbf_insert_seqs_dev(btlbf_filter *f, const void *d_bases, uint64_t n_bases,
+                          const uint64_t *d_offsets, uint64_t n_seqs, uint64_t *d_stats);
+int btlbf_contains_seqs_dev(btlbf_filter *f, const void *d_bases, uint64_t n_bases,
+                            const uint64_t *d_offsets, uint64_t n_seqs, uint32_t *d_hit_bits,
+                            uint32_t *d_valid_bits, uint64_t *d_stats);
+int btlbf_mincount_seqs_dev(btlbf_filter *f, const void *d_bases, uint64_t n_bases,
+                            const uint64_t *d_offsets, uint64_t n_seqs, uint8_t *d_counts,
+                            uint32_t *d_valid_bits, uint64_t *d_stats);
+
+/* ---- synthetic inputs generated in HBM (bench / tests; replayable by the oracle) ---- */
+/* base(i) = "ACGT"[(splitmix64(seed ^ (i>>5)) >> 2*(i&31)) & 3] for i in [start, start+n) */
+int btlbf_synth_genome_dev(btlbf_ctx *ctx, void *d_out, uint64_t start, uint64_t n, uint64_t seed);
+/* read r = genome[s .. s+read_len) with s = splitmix64(read_seed + r) % (g_len - read_len) */
+int btlbf_synth_reads_dev(btlbf_ctx *ctx, void *d_out, uint64_t first_read, uint64_t n_reads,
+                          unsigned read_len, uint64_t g_len, uint64_t genome_seed,
+                          uint64_t read_seed);
+/* random-sector microbenchmark that establishes the measured roofline denominator:
+ * mode 0: one 4-byte load per access, mode 1: one atomicOr per access, over a device array of
+ * `bytes` bytes at pseudo-random 4-byte-aligned addresses; elapsed_ms from CUDA events. */
+int btlbf_random_access_probe(btlbf_ctx *ctx, void *d_array, uint64_t bytes, uint64_t n_access,
+                              int mode, float *elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BTLBF_H */
