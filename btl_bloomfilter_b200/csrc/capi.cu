@@ -1,0 +1,1381 @@
+// capi.cu -- the C ABI of libbtlbf_cuda.so (include/btlbf.h): handles, device memory, host<->device
+// pipelines and kernel orchestration.  No CPU implementation of the hot path lives here: every batched
+// operation is a launch of the sm_100a kernels in kernels.cu.
+#include "../../include/btlbf.h"
+#include "kernels.cuh"
+#include "host_params.hpp"
+
+#include <cerrno>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace btl;
+
+// ---------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof g_err, fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+#define CU(call)                                                                                   \
+	do {                                                                                           \
+		cudaError_t e_ = (call);                                                                   \
+		if (e_ != cudaSuccess)                                                                     \
+			return fail(e_ == cudaErrorMemoryAllocation ? BTLBF_ERR_NOMEM : BTLBF_ERR_CUDA,       \
+			            "%s failed: %s", #call, cudaGetErrorString(e_));                           \
+	} while (0)
+#define TRY(call)                                                                                   \
+	do {                                                                                           \
+		int rc_ = (call);                                                                          \
+		if (rc_ != BTLBF_OK)                                                                       \
+			return rc_;                                                                            \
+	} while (0)
+
+// ---------------------------------------------------------------- handles
+namespace {
+
+struct DevBuf
+{
+	void* p = nullptr;
+	size_t cap = 0;
+};
+
+struct Slot // one stage of the host-buffer pipeline (H2D copy | kernel | D2H copy)
+{
+	DevBuf bases, hit, valid, counts, hashes, strands;
+	cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_d2h = nullptr;
+	bool used = false;
+};
+
+struct HashCfg // everything the kernels need to turn a window into its hashes
+{
+	uint32_t k = 0, h = 0, n_seeds = 0, h2 = 0;
+	uint64_t* d_st_tab = nullptr;
+	uint16_t* d_st_dc = nullptr;
+	SeqParams proto;
+};
+
+} // namespace
+
+struct btlbf_ctx
+{
+	int device = 0;
+	cudaStream_t own = nullptr, active = nullptr, copy_in = nullptr, copy_out = nullptr;
+	uint64_t launches = 0;
+	unsigned long long* d_scalars = nullptr; // 16 device words: [0..1] stats, [2] popcount, [4..7] list counters
+	unsigned long long* h_scalars = nullptr; // pinned mirror
+	int64_t force_generic = 0, query_mode = 0;
+	int64_t chunk_bases = (int64_t)32 << 20; // windows per pipeline stage of the host-buffer calls
+	int64_t cbf_batch = (int64_t)1 << 20;    // windows per batch of the ordered (exact) updates
+	int64_t resv_log2 = 28, list_log2 = 22;
+	int64_t drain_threshold = 4096;
+	Slot slot[2];
+	DevBuf offsets;
+};
+
+struct btlbf_filter
+{
+	btlbf_ctx* ctx = nullptr;
+	int kind = BTLBF_BLOOM;
+	uint64_t size = 0, bytes = 0, cap = 0;
+	unsigned threshold = 1;
+	uint8_t* d_data = nullptr;
+	bool owned = false;
+	HashCfg hc;
+	// ordered-update state (lazy)
+	uint32_t* d_touched = nullptr;
+	uint32_t* d_contended = nullptr;
+	uint32_t resv_log2 = 0;
+	uint32_t* d_pending[2] = { nullptr, nullptr };
+	uint32_t pending_cap = 0;
+	uint64_t* d_list_resv = nullptr;
+	uint32_t list_log2 = 0;
+	uint32_t epoch = 0;
+	uint64_t deferred_total = 0, rounds_total = 0;
+};
+
+// ---------------------------------------------------------------- small helpers
+static int use(btlbf_ctx* ctx)
+{
+	if (!ctx)
+		return fail(BTLBF_ERR_ARG, "null context");
+	CU(cudaSetDevice(ctx->device));
+	return BTLBF_OK;
+}
+
+static int ensure(DevBuf& b, size_t bytes)
+{
+	if (bytes <= b.cap)
+		return BTLBF_OK;
+	if (b.p)
+		CU(cudaFree(b.p));
+	b.p = nullptr;
+	b.cap = 0;
+	size_t want = (bytes + 255) / 256 * 256;
+	CU(cudaMalloc(&b.p, want));
+	b.cap = want;
+	return BTLBF_OK;
+}
+
+static void release(DevBuf& b)
+{
+	if (b.p)
+		cudaFree(b.p);
+	b.p = nullptr;
+	b.cap = 0;
+}
+
+static int launch(btlbf_ctx* ctx, SeqOp op, const SeqParams& P, cudaStream_t s)
+{
+	if (P.n_windows == 0)
+		return BTLBF_OK;
+	cudaError_t e = launch_seq(op, P, s);
+	if (e != cudaSuccess)
+		return fail(BTLBF_ERR_CUDA, "kernel launch (op %d) failed: %s", (int)op, cudaGetErrorString(e));
+	ctx->launches++;
+	return BTLBF_OK;
+}
+
+static void hashcfg_free(HashCfg& hc)
+{
+	if (hc.d_st_tab)
+		cudaFree(hc.d_st_tab);
+	if (hc.d_st_dc)
+		cudaFree(hc.d_st_dc);
+	hc.d_st_tab = nullptr;
+	hc.d_st_dc = nullptr;
+}
+
+// Fills hc.proto with the launch-invariant hashing constants (host_params.hpp) and uploads the
+// spaced-seed tables.
+static int hashcfg_init(HashCfg& hc, unsigned k, unsigned h, const char* const* seeds, unsigned n_seeds,
+                        unsigned h2)
+{
+	hashcfg_free(hc);
+	HostSeedTables t;
+	std::string err = build_hash_proto(hc.proto, t, k, h, seeds, n_seeds, h2);
+	if (!err.empty())
+		return fail(BTLBF_ERR_ARG, "%s", err.c_str());
+	hc.k = hc.proto.k;
+	hc.h = hc.proto.h;
+	hc.n_seeds = hc.proto.n_seeds;
+	hc.h2 = hc.proto.h2;
+	if (hc.n_seeds) {
+		CU(cudaMalloc(&hc.d_st_tab, t.tab.size() * 8));
+		CU(cudaMemcpy(hc.d_st_tab, t.tab.data(), t.tab.size() * 8, cudaMemcpyHostToDevice));
+		CU(cudaMalloc(&hc.d_st_dc, (t.dc.size() + 1) * 2));
+		if (!t.dc.empty())
+			CU(cudaMemcpy(hc.d_st_dc, t.dc.data(), t.dc.size() * 2, cudaMemcpyHostToDevice));
+		hc.proto.st_tab = hc.d_st_tab;
+		hc.proto.st_dc = hc.d_st_dc;
+	}
+	return BTLBF_OK;
+}
+
+static SeqParams filter_params(btlbf_filter* f)
+{
+	SeqParams P = f->hc.proto;
+	P.filter = f->d_data;
+	P.fm = make_fastmod(f->size);
+	P.threshold = f->threshold;
+	P.force_generic = (uint32_t)f->ctx->force_generic;
+	P.query_mode = (uint32_t)f->ctx->query_mode;
+	return P;
+}
+
+// ---------------------------------------------------------------- misc entry points
+extern "C" const char* btlbf_last_error(void)
+{
+	return g_err;
+}
+
+extern "C" int btlbf_version(void)
+{
+	return BTLBF_VERSION;
+}
+
+extern "C" int btlbf_device_count(int* count)
+{
+	if (!count)
+		return fail(BTLBF_ERR_ARG, "null argument");
+	*count = 0;
+	CU(cudaGetDeviceCount(count));
+	return BTLBF_OK;
+}
+
+// ---------------------------------------------------------------- context
+extern "C" int btlbf_ctx_create(int device, btlbf_ctx** out)
+{
+	if (!out)
+		return fail(BTLBF_ERR_ARG, "null argument");
+	*out = nullptr;
+	int n = 0;
+	CU(cudaGetDeviceCount(&n));
+	if (device < 0 || device >= n)
+		return fail(BTLBF_ERR_CUDA, "device %d not available (%d CUDA devices); there is no CPU fallback", device, n);
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10)
+		return fail(BTLBF_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+		            prop.major, prop.minor);
+	CU(cudaSetDevice(device));
+	btlbf_ctx* ctx = new (std::nothrow) btlbf_ctx();
+	if (!ctx)
+		return fail(BTLBF_ERR_NOMEM, "out of host memory");
+	ctx->device = device;
+	cudaError_t e = cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking);
+	if (e == cudaSuccess)
+		e = cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking);
+	if (e == cudaSuccess)
+		e = cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking);
+	if (e == cudaSuccess)
+		e = cudaMalloc(&ctx->d_scalars, 16 * sizeof(unsigned long long));
+	if (e == cudaSuccess)
+		e = cudaMemset(ctx->d_scalars, 0, 16 * sizeof(unsigned long long));
+	if (e == cudaSuccess)
+		e = cudaHostAlloc(&ctx->h_scalars, 16 * sizeof(unsigned long long), cudaHostAllocDefault);
+	for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+		e = cudaEventCreateWithFlags(&ctx->slot[i].ev_h2d, cudaEventDisableTiming);
+		if (e == cudaSuccess)
+			e = cudaEventCreateWithFlags(&ctx->slot[i].ev_kernel, cudaEventDisableTiming);
+		if (e == cudaSuccess)
+			e = cudaEventCreateWithFlags(&ctx->slot[i].ev_d2h, cudaEventDisableTiming);
+	}
+	if (e != cudaSuccess) {
+		btlbf_ctx_destroy(ctx);
+		return fail(BTLBF_ERR_CUDA, "context creation failed: %s", cudaGetErrorString(e));
+	}
+	ctx->active = ctx->own;
+	*out = ctx;
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_ctx_destroy(btlbf_ctx* ctx)
+{
+	if (!ctx)
+		return BTLBF_OK;
+	cudaSetDevice(ctx->device);
+	cudaDeviceSynchronize();
+	for (int i = 0; i < 2; i++) {
+		Slot& s = ctx->slot[i];
+		release(s.bases); release(s.hit); release(s.valid); release(s.counts); release(s.hashes); release(s.strands);
+		if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+		if (s.ev_kernel) cudaEventDestroy(s.ev_kernel);
+		if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
+	}
+	release(ctx->offsets);
+	if (ctx->d_scalars) cudaFree(ctx->d_scalars);
+	if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+	if (ctx->own) cudaStreamDestroy(ctx->own);
+	if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+	if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+	delete ctx;
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_ctx_set_stream(btlbf_ctx* ctx, void* cuda_stream)
+{
+	TRY(use(ctx));
+	ctx->active = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own;
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_ctx_sync(btlbf_ctx* ctx)
+{
+	TRY(use(ctx));
+	CU(cudaStreamSynchronize(ctx->active));
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_ctx_launch_count(btlbf_ctx* ctx, uint64_t* count)
+{
+	if (!ctx || !count)
+		return fail(BTLBF_ERR_ARG, "null argument");
+	*count = ctx->launches;
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_ctx_set_option(btlbf_ctx* ctx, const char* key, int64_t value)
+{
+	if (!ctx || !key)
+		return fail(BTLBF_ERR_ARG, "null argument");
+	std::string k(key);
+	if (k == "force_generic")
+		ctx->force_generic = value != 0;
+	else if (k == "query_mode")
+		ctx->query_mode = value != 0;
+	else if (k == "chunk_bases") {
+		if (value < kTile || value > ((int64_t)1 << 31))
+			return fail(BTLBF_ERR_ARG, "chunk_bases out of range");
+		ctx->chunk_bases = value / kTile * kTile;
+	} else if (k == "cbf_batch") {
+		if (value < kTile || value > ((int64_t)1 << 30))
+			return fail(BTLBF_ERR_ARG, "cbf_batch out of range");
+		ctx->cbf_batch = value / kTile * kTile;
+	} else if (k == "resv_log2") {
+		if (value < 10 || value > 32)
+			return fail(BTLBF_ERR_ARG, "resv_log2 out of range");
+		ctx->resv_log2 = value;
+	} else if (k == "list_log2") {
+		if (value < 6 || value > 28)
+			return fail(BTLBF_ERR_ARG, "list_log2 out of range");
+		ctx->list_log2 = value;
+	} else if (k == "drain_threshold") {
+		if (value < 0)
+			return fail(BTLBF_ERR_ARG, "drain_threshold out of range");
+		ctx->drain_threshold = value;
+	} else
+		return fail(BTLBF_ERR_ARG, "unknown option '%s'", key);
+	return BTLBF_OK;
+}
+
+// ---------------------------------------------------------------- filters
+static int filter_make(btlbf_ctx* ctx, int kind, uint64_t size, unsigned h, unsigned k, unsigned threshold,
+                       void* wrap_ptr, uint64_t wrap_cap, btlbf_filter** out)
+{
+	if (!out)
+		return fail(BTLBF_ERR_ARG, "null argument");
+	*out = nullptr;
+	TRY(use(ctx));
+	if (kind != BTLBF_BLOOM && kind != BTLBF_COUNTING8)
+		return fail(BTLBF_ERR_ARG, "unknown filter kind %d", kind);
+	if (size == 0)
+		return fail(BTLBF_ERR_ARG, "filter size must be > 0");
+	if (kind == BTLBF_BLOOM && size % 8 != 0) // BloomFilter.hpp:389-394
+		return fail(BTLBF_ERR_ARG, "Filter Size \"%llu\" is not a multiple of 8", (unsigned long long)size);
+	btlbf_filter* f = new (std::nothrow) btlbf_filter();
+	if (!f)
+		return fail(BTLBF_ERR_NOMEM, "out of host memory");
+	f->ctx = ctx;
+	f->kind = kind;
+	f->size = size;
+	f->bytes = kind == BTLBF_BLOOM ? size / 8 : size;
+	f->threshold = threshold;
+	int rc = hashcfg_init(f->hc, k, h, nullptr, 0, 0);
+	if (rc != BTLBF_OK) {
+		delete f;
+		return rc;
+	}
+	uint64_t need = (f->bytes + 15) / 16 * 16;
+	if (wrap_ptr) {
+		if (wrap_cap < need || ((uintptr_t)wrap_ptr & 15u)) {
+			delete f;
+			return fail(BTLBF_ERR_ARG, "wrapped memory must be 16-byte aligned and hold %llu bytes",
+			            (unsigned long long)need);
+		}
+		f->d_data = (uint8_t*)wrap_ptr;
+		f->cap = wrap_cap;
+		f->owned = false;
+	} else {
+		cudaError_t e = cudaMalloc(&f->d_data, need);
+		if (e == cudaSuccess)
+			e = cudaMemsetAsync(f->d_data, 0, need, ctx->active);
+		if (e != cudaSuccess) {
+			delete f;
+			return fail(e == cudaErrorMemoryAllocation ? BTLBF_ERR_NOMEM : BTLBF_ERR_CUDA,
+			            "allocating a %llu-byte filter failed: %s", (unsigned long long)need, cudaGetErrorString(e));
+		}
+		f->cap = need;
+		f->owned = true;
+	}
+	*out = f;
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_filter_create(btlbf_ctx* ctx, int kind, uint64_t size, unsigned hash_num, unsigned kmer_size,
+                                   unsigned threshold, btlbf_filter** filter)
+{
+	return filter_make(ctx, kind, size, hash_num, kmer_size, threshold, nullptr, 0, filter);
+}
+
+extern "C" int btlbf_filter_wrap(btlbf_ctx* ctx, int kind, uint64_t size, unsigned hash_num, unsigned kmer_size,
+                                 unsigned threshold, void* device_ptr, uint64_t capacity_bytes, btlbf_filter** filter)
+{
+	if (!device_ptr)
+		return fail(BTLBF_ERR_ARG, "null device pointer");
+	return filter_make(ctx, kind, size, hash_num, kmer_size, threshold, device_ptr, capacity_bytes, filter);
+}
+
+extern "C" int btlbf_filter_destroy(btlbf_filter* f)
+{
+	if (!f)
+		return BTLBF_OK;
+	cudaSetDevice(f->ctx->device);
+	cudaStreamSynchronize(f->ctx->active);
+	if (f->owned && f->d_data)
+		cudaFree(f->d_data);
+	hashcfg_free(f->hc);
+	if (f->d_touched) cudaFree(f->d_touched);
+	if (f->d_contended) cudaFree(f->d_contended);
+	if (f->d_pending[0]) cudaFree(f->d_pending[0]);
+	if (f->d_pending[1]) cudaFree(f->d_pending[1]);
+	if (f->d_list_resv) cudaFree(f->d_list_resv);
+	delete f;
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_filter_clear(btlbf_filter* f)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	TRY(use(f->ctx));
+	CU(cudaMemsetAsync(f->d_data, 0, (f->bytes + 15) / 16 * 16, f->ctx->active));
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_filter_info(btlbf_filter* f, int* kind, uint64_t* size, uint64_t* size_bytes, unsigned* hash_num,
+                                 unsigned* kmer_size, unsigned* threshold)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	if (kind) *kind = f->kind;
+	if (size) *size = f->size;
+	if (size_bytes) *size_bytes = f->bytes;
+	if (hash_num) *hash_num = f->hc.h;
+	if (kmer_size) *kmer_size = f->hc.k;
+	if (threshold) *threshold = f->threshold;
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_filter_set_threshold(btlbf_filter* f, unsigned threshold)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	f->threshold = threshold;
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_filter_upload(btlbf_filter* f, const void* host, uint64_t nbytes)
+{
+	if (!f || (!host && nbytes))
+		return fail(BTLBF_ERR_ARG, "null argument");
+	if (nbytes != f->bytes)
+		return fail(BTLBF_ERR_ARG, "upload of %llu bytes into a %llu-byte filter", (unsigned long long)nbytes,
+		            (unsigned long long)f->bytes);
+	TRY(use(f->ctx));
+	CU(cudaMemcpyAsync(f->d_data, host, nbytes, cudaMemcpyHostToDevice, f->ctx->active));
+	uint64_t pad = (f->bytes + 15) / 16 * 16 - f->bytes;
+	if (pad)
+		CU(cudaMemsetAsync(f->d_data + f->bytes, 0, pad, f->ctx->active));
+	CU(cudaStreamSynchronize(f->ctx->active));
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_filter_download(btlbf_filter* f, void* host, uint64_t nbytes)
+{
+	if (!f || (!host && nbytes))
+		return fail(BTLBF_ERR_ARG, "null argument");
+	if (nbytes != f->bytes)
+		return fail(BTLBF_ERR_ARG, "download of %llu bytes from a %llu-byte filter", (unsigned long long)nbytes,
+		            (unsigned long long)f->bytes);
+	TRY(use(f->ctx));
+	CU(cudaMemcpyAsync(host, f->d_data, nbytes, cudaMemcpyDeviceToHost, f->ctx->active));
+	CU(cudaStreamSynchronize(f->ctx->active));
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_filter_device_ptr(btlbf_filter* f, void** device_ptr, uint64_t* nbytes)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	if (device_ptr) *device_ptr = f->d_data;
+	if (nbytes) *nbytes = f->bytes;
+	return BTLBF_OK;
+}
+
+static int reduce_count(btlbf_filter* f, int mode, unsigned threshold, uint64_t* count)
+{
+	if (!f || !count)
+		return fail(BTLBF_ERR_ARG, "null argument");
+	btlbf_ctx* ctx = f->ctx;
+	TRY(use(ctx));
+	CU(cudaMemsetAsync(ctx->d_scalars + 2, 0, 8, ctx->active));
+	cudaError_t e = launch_popcount(f->d_data, f->bytes, mode, threshold, ctx->d_scalars + 2, ctx->active);
+	if (e != cudaSuccess)
+		return fail(BTLBF_ERR_CUDA, "popcount launch failed: %s", cudaGetErrorString(e));
+	ctx->launches++;
+	CU(cudaMemcpyAsync(ctx->h_scalars + 2, ctx->d_scalars + 2, 8, cudaMemcpyDeviceToHost, ctx->active));
+	CU(cudaStreamSynchronize(ctx->active));
+	*count = ctx->h_scalars[2];
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_filter_popcount(btlbf_filter* f, uint64_t* count)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	return reduce_count(f, f->kind == BTLBF_BLOOM ? 0 : 1, 0, count);
+}
+
+extern "C" int btlbf_filter_count_ge(btlbf_filter* f, unsigned threshold, uint64_t* count)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	if (f->kind != BTLBF_COUNTING8)
+		return fail(BTLBF_ERR_STATE, "count_ge needs a counting filter");
+	if (threshold > 255) {
+		if (count) *count = 0;
+		return count ? BTLBF_OK : fail(BTLBF_ERR_ARG, "null argument");
+	}
+	if (threshold == 0) {
+		if (count) *count = f->size;
+		return count ? BTLBF_OK : fail(BTLBF_ERR_ARG, "null argument");
+	}
+	return reduce_count(f, 2, threshold, count);
+}
+
+extern "C" int btlbf_filter_set_seeds(btlbf_filter* f, const char* const* seeds, unsigned n_seeds, unsigned h2)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	TRY(use(f->ctx));
+	CU(cudaStreamSynchronize(f->ctx->active));
+	unsigned k = f->hc.k, h = f->hc.h;
+	if (n_seeds == 0)
+		return hashcfg_init(f->hc, k, h, nullptr, 0, 0);
+	if ((uint64_t)n_seeds * h2 != h)
+		return fail(BTLBF_ERR_ARG, "spaced seeds need hash_num == n_seeds*h2 (%u != %u*%u)", h, n_seeds, h2);
+	HashCfg tmp;
+	int rc = hashcfg_init(tmp, k, h, seeds, n_seeds, h2);
+	if (rc != BTLBF_OK) {
+		hashcfg_free(tmp);
+		return rc;
+	}
+	hashcfg_free(f->hc);
+	f->hc = tmp;
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_filter_merge_from_device(btlbf_filter* f, const void* src_device, uint64_t nbytes)
+{
+	if (!f || !src_device)
+		return fail(BTLBF_ERR_ARG, "null argument");
+	if (nbytes != f->bytes)
+		return fail(BTLBF_ERR_ARG, "merge of %llu bytes into a %llu-byte filter", (unsigned long long)nbytes,
+		            (unsigned long long)f->bytes);
+	if ((uintptr_t)src_device & 15u)
+		return fail(BTLBF_ERR_ARG, "merge source must be 16-byte aligned");
+	TRY(use(f->ctx));
+	cudaError_t e = launch_merge(f->d_data, src_device, nbytes, f->kind == BTLBF_COUNTING8, f->ctx->active);
+	if (e != cudaSuccess)
+		return fail(BTLBF_ERR_CUDA, "merge launch failed: %s", cudaGetErrorString(e));
+	f->ctx->launches++;
+	return BTLBF_OK;
+}
+
+// ---------------------------------------------------------------- ordered (exact) updates
+static int ordered_state(btlbf_filter* f, uint32_t batch)
+{
+	btlbf_ctx* ctx = f->ctx;
+	uint32_t want_log2 = (uint32_t)ctx->resv_log2;
+	if (f->d_touched && f->resv_log2 != want_log2) {
+		CU(cudaFree(f->d_touched));
+		CU(cudaFree(f->d_contended));
+		f->d_touched = f->d_contended = nullptr;
+	}
+	if (!f->d_touched) {
+		size_t bytes = (((size_t)1 << want_log2) + 7) / 8;
+		bytes = bytes < 4 ? 4 : bytes;
+		CU(cudaMalloc(&f->d_touched, bytes));
+		CU(cudaMalloc(&f->d_contended, bytes));
+		CU(cudaMemsetAsync(f->d_touched, 0, bytes, ctx->active));
+		CU(cudaMemsetAsync(f->d_contended, 0, bytes, ctx->active));
+		f->resv_log2 = want_log2;
+	}
+	if (f->pending_cap < batch) {
+		for (int i = 0; i < 2; i++) {
+			if (f->d_pending[i])
+				CU(cudaFree(f->d_pending[i]));
+			f->d_pending[i] = nullptr;
+			CU(cudaMalloc(&f->d_pending[i], (size_t)batch * 4));
+		}
+		f->pending_cap = batch;
+	}
+	uint32_t want_list = (uint32_t)ctx->list_log2;
+	if (f->d_list_resv && f->list_log2 != want_list) {
+		CU(cudaFree(f->d_list_resv));
+		f->d_list_resv = nullptr;
+	}
+	if (!f->d_list_resv) {
+		size_t bytes = ((size_t)1 << want_list) * 8;
+		CU(cudaMalloc(&f->d_list_resv, bytes));
+		CU(cudaMemsetAsync(f->d_list_resv, 0xff, bytes, ctx->active));
+		f->list_log2 = want_list;
+		f->epoch = 0;
+	}
+	return BTLBF_OK;
+}
+
+// Applies an order-dependent update (kind 0: incrementMin, 1: insertAndCheck) to the windows of a
+// device-resident chunk so that the result equals the reference's single-threaded, read-order,
+// position-order loop.  P describes the whole chunk (outputs included).
+static int ordered_apply(btlbf_filter* f, const SeqParams& chunk, int kind, cudaStream_t s)
+{
+	btlbf_ctx* ctx = f->ctx;
+	uint64_t batch = (uint64_t)ctx->cbf_batch;
+	TRY(ordered_state(f, (uint32_t)batch));
+	uint32_t* d_cnt = reinterpret_cast<uint32_t*>(ctx->d_scalars + 4); // [0],[1]: list counters, [2]: rounds
+	volatile uint32_t* h_cnt = reinterpret_cast<volatile uint32_t*>(ctx->h_scalars + 4);
+	for (uint64_t b0 = 0; b0 < chunk.n_windows; b0 += batch) {
+		SeqParams P = chunk;
+		uint64_t bw = chunk.n_windows - b0 < batch ? chunk.n_windows - b0 : batch;
+		P.bases = chunk.bases + b0;
+		P.n_bases = chunk.n_bases > b0 ? chunk.n_bases - b0 : 0;
+		P.base0 = chunk.base0 + b0;
+		P.n_windows = bw;
+		if (chunk.hit_bits) P.hit_bits = chunk.hit_bits + (b0 >> 5);
+		if (chunk.valid_bits) P.valid_bits = chunk.valid_bits + (b0 >> 5);
+		P.out_words = chunk.out_words > (b0 >> 5) ? chunk.out_words - (b0 >> 5) : 0;
+		P.resv_touched = f->d_touched;
+		P.resv_contended = f->d_contended;
+		P.resv_log2 = f->resv_log2;
+		P.pending = f->d_pending[0];
+		P.pending_count = d_cnt;
+		CU(cudaMemsetAsync(d_cnt, 0, 16, s));
+		// pass 1 carries no outputs; pass 2 writes valid/hit words and the k-mer statistics
+		SeqParams T = P;
+		T.hit_bits = T.valid_bits = nullptr;
+		T.stats = nullptr;
+		TRY(launch(ctx, OP_RESV_TOUCH, T, s));
+		TRY(launch(ctx, kind == 0 ? OP_CBF_COMMIT : OP_BFCHK_COMMIT, P, s));
+		TRY(launch(ctx, OP_RESV_CLEAR, T, s));
+		CU(cudaMemcpyAsync((void*)h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
+		CU(cudaStreamSynchronize(s));
+		uint32_t n = h_cnt[0];
+		f->deferred_total += n;
+		int cur = 0;
+		while (n > 0) {
+			ListParams L;
+			memset(&L, 0, sizeof L);
+			L.list_in = f->d_pending[cur];
+			L.count_in = d_cnt + cur;
+			L.list_out = f->d_pending[1 - cur];
+			L.count_out = d_cnt + (1 - cur);
+			L.resv = f->d_list_resv;
+			L.resv_log2 = f->list_log2;
+			L.kind = (uint32_t)kind;
+			L.max_items = n;
+			if (f->epoch > 0xfff00000u) { // re-arm the reservation table long before the epoch wraps
+				CU(cudaMemsetAsync(f->d_list_resv, 0xff, ((size_t)1 << f->list_log2) * 8, s));
+				f->epoch = 0;
+			}
+			L.epoch = ++f->epoch;
+			if ((int64_t)n > ctx->drain_threshold) {
+				CU(cudaMemsetAsync(d_cnt + (1 - cur), 0, 4, s));
+				cudaError_t e = launch_list_round(0, P, L, s);
+				if (e == cudaSuccess)
+					e = launch_list_round(1, P, L, s);
+				if (e != cudaSuccess)
+					return fail(BTLBF_ERR_CUDA, "list round launch failed: %s", cudaGetErrorString(e));
+				ctx->launches += 2;
+				f->rounds_total++;
+				CU(cudaMemcpyAsync((void*)(h_cnt + (1 - cur)), d_cnt + (1 - cur), 4, cudaMemcpyDeviceToHost, s));
+				CU(cudaStreamSynchronize(s));
+				n = h_cnt[1 - cur];
+				cur = 1 - cur;
+			} else {
+				L.rounds_out = d_cnt + 2;
+				cudaError_t e = launch_list_drain(P, L, s);
+				if (e != cudaSuccess)
+					return fail(BTLBF_ERR_CUDA, "list drain launch failed: %s", cudaGetErrorString(e));
+				ctx->launches++;
+				f->epoch += n + 1; // the drain kernel runs at most n rounds, one epoch each
+				f->rounds_total += 1;
+				n = 0;
+			}
+		}
+	}
+	return BTLBF_OK;
+}
+
+// ---------------------------------------------------------------- operations on a device-resident chunk
+enum PublicOp { PUB_INSERT, PUB_CONTAINS, PUB_INSERT_CHECK, PUB_MINCOUNT, PUB_INCALL, PUB_HASH };
+
+struct ChunkIO
+{
+	const uint8_t* d_bases = nullptr;
+	uint64_t n_bases = 0;   // bytes readable at d_bases
+	uint64_t base0 = 0;     // flat position of d_bases[0]
+	uint64_t n_windows = 0; // windows of this chunk
+	const uint64_t* d_offsets = nullptr;
+	uint64_t n_seqs = 0;
+	uint32_t* d_hit = nullptr;
+	uint32_t* d_valid = nullptr;
+	uint8_t* d_counts = nullptr;
+	uint64_t* d_hashes = nullptr;
+	uint8_t* d_strands = nullptr;
+	uint64_t* d_stats = nullptr;
+};
+
+static void fill_io(SeqParams& P, const ChunkIO& io)
+{
+	P.bases = io.d_bases;
+	P.n_bases = io.n_bases;
+	P.base0 = io.base0;
+	P.n_windows = io.n_windows;
+	P.offsets = io.d_offsets;
+	P.n_seqs = io.n_seqs;
+	P.hit_bits = io.d_hit;
+	P.valid_bits = io.d_valid;
+	P.out_words = (io.n_windows + 31) / 32;
+	P.counts = io.d_counts;
+	P.hashes = io.d_hashes;
+	P.strands = io.d_strands;
+	P.stats = io.d_stats;
+}
+
+static int filter_op_dev(btlbf_filter* f, PublicOp op, const ChunkIO& io, cudaStream_t s)
+{
+	SeqParams P = filter_params(f);
+	fill_io(P, io);
+	btlbf_ctx* ctx = f->ctx;
+	switch (op) {
+	case PUB_INSERT:
+		if (f->kind == BTLBF_BLOOM)
+			return launch(ctx, OP_BF_INSERT, P, s);
+		return ordered_apply(f, P, 0, s);
+	case PUB_CONTAINS:
+		return launch(ctx, f->kind == BTLBF_BLOOM ? OP_BF_CONTAINS : OP_CBF_MINCOUNT, P, s);
+	case PUB_INSERT_CHECK:
+		return ordered_apply(f, P, f->kind == BTLBF_BLOOM ? 1 : 0, s);
+	case PUB_MINCOUNT:
+		if (f->kind != BTLBF_COUNTING8)
+			return fail(BTLBF_ERR_STATE, "mincount_seqs needs a counting filter");
+		return launch(ctx, OP_CBF_MINCOUNT, P, s);
+	case PUB_INCALL:
+		if (f->kind != BTLBF_COUNTING8)
+			return fail(BTLBF_ERR_STATE, "increment_all_seqs needs a counting filter");
+		return launch(ctx, OP_CBF_INCALL, P, s);
+	default:
+		return fail(BTLBF_ERR_ARG, "bad operation");
+	}
+}
+
+static int check_dev_args(btlbf_filter* f, const void* d_bases, uint64_t n_bases, const uint64_t* d_offsets)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	if (n_bases && (!d_bases || !d_offsets))
+		return fail(BTLBF_ERR_ARG, "null device batch");
+	if ((uintptr_t)d_bases & 15u)
+		return fail(BTLBF_ERR_ARG, "device bases must be 16-byte aligned");
+	return use(f->ctx);
+}
+
+extern "C" int btlbf_insert_seqs_dev(btlbf_filter* f, const void* d_bases, uint64_t n_bases, const uint64_t* d_offsets,
+                                     uint64_t n_seqs, uint64_t* d_stats)
+{
+	TRY(check_dev_args(f, d_bases, n_bases, d_offsets));
+	ChunkIO io;
+	io.d_bases = (const uint8_t*)d_bases;
+	io.n_bases = io.n_windows = n_bases;
+	io.d_offsets = d_offsets;
+	io.n_seqs = n_seqs;
+	io.d_stats = d_stats;
+	return filter_op_dev(f, PUB_INSERT, io, f->ctx->active);
+}
+
+extern "C" int btlbf_contains_seqs_dev(btlbf_filter* f, const void* d_bases, uint64_t n_bases,
+                                       const uint64_t* d_offsets, uint64_t n_seqs, uint32_t* d_hit_bits,
+                                       uint32_t* d_valid_bits, uint64_t* d_stats)
+{
+	TRY(check_dev_args(f, d_bases, n_bases, d_offsets));
+	ChunkIO io;
+	io.d_bases = (const uint8_t*)d_bases;
+	io.n_bases = io.n_windows = n_bases;
+	io.d_offsets = d_offsets;
+	io.n_seqs = n_seqs;
+	io.d_hit = d_hit_bits;
+	io.d_valid = d_valid_bits;
+	io.d_stats = d_stats;
+	return filter_op_dev(f, PUB_CONTAINS, io, f->ctx->active);
+}
+
+extern "C" int btlbf_mincount_seqs_dev(btlbf_filter* f, const void* d_bases, uint64_t n_bases,
+                                       const uint64_t* d_offsets, uint64_t n_seqs, uint8_t* d_counts,
+                                       uint32_t* d_valid_bits, uint64_t* d_stats)
+{
+	TRY(check_dev_args(f, d_bases, n_bases, d_offsets));
+	ChunkIO io;
+	io.d_bases = (const uint8_t*)d_bases;
+	io.n_bases = io.n_windows = n_bases;
+	io.d_offsets = d_offsets;
+	io.n_seqs = n_seqs;
+	io.d_counts = d_counts;
+	io.d_valid = d_valid_bits;
+	io.d_stats = d_stats;
+	if (d_counts)
+		CU(cudaMemsetAsync(d_counts, 0, n_bases, f->ctx->active));
+	return filter_op_dev(f, PUB_MINCOUNT, io, f->ctx->active);
+}
+
+// ---------------------------------------------------------------- host-buffer pipeline
+struct HostIO
+{
+	const char* bases = nullptr;
+	const uint64_t* offsets = nullptr;
+	uint64_t n_seqs = 0;
+	uint8_t* hit_bits = nullptr;   // ceil(n/32)*4 bytes each
+	uint8_t* valid_bits = nullptr;
+	uint8_t* counts = nullptr;     // n bytes
+	uint64_t* hashes = nullptr;    // n*H
+	uint8_t* strands = nullptr;    // n*H
+	uint64_t* n_kmers = nullptr;
+	uint64_t* n_hits = nullptr;
+};
+
+// Streams the flat batch through the GPU in chunks of ctx->chunk_bases windows: chunk i+1 is copied
+// in (copy_in stream) and chunk i-1's results are copied out (copy_out stream) while chunk i runs.
+static int host_pipeline(btlbf_ctx* ctx, btlbf_filter* f, const HashCfg* hash_only, PublicOp op, const HostIO& h)
+{
+	TRY(use(ctx));
+	if (h.n_seqs && !h.offsets)
+		return fail(BTLBF_ERR_ARG, "null offsets");
+	if (h.n_kmers) *h.n_kmers = 0;
+	if (h.n_hits) *h.n_hits = 0;
+	uint64_t n_bases = h.n_seqs ? h.offsets[h.n_seqs] : 0;
+	if (h.n_seqs && h.offsets[0] != 0)
+		return fail(BTLBF_ERR_ARG, "offsets[0] must be 0");
+	if (n_bases && !h.bases)
+		return fail(BTLBF_ERR_ARG, "null bases");
+	if (n_bases == 0)
+		return BTLBF_OK;
+	for (uint64_t i = 0; i < h.n_seqs; i++)
+		if (h.offsets[i] > h.offsets[i + 1])
+			return fail(BTLBF_ERR_ARG, "offsets must be non-decreasing (sequence %llu)", (unsigned long long)i);
+	const HashCfg& hc = hash_only ? *hash_only : f->hc;
+	const uint32_t k = hc.k, H = hc.h;
+	cudaStream_t s = ctx->active;
+
+	uint64_t chunk = (uint64_t)ctx->chunk_bases;
+	if (op == PUB_HASH) { // keep the per-chunk hash buffer around 256 MiB
+		uint64_t lim = ((uint64_t)256 << 20) / ((uint64_t)H * 9);
+		lim = lim / kTile * kTile;
+		if (lim < (uint64_t)kTile) lim = kTile;
+		if (chunk > lim) chunk = lim;
+	}
+	if (chunk > n_bases)
+		chunk = (n_bases + kTile - 1) / kTile * kTile;
+
+	TRY(ensure(ctx->offsets, (h.n_seqs + 1) * 8));
+	CU(cudaMemcpyAsync(ctx->offsets.p, h.offsets, (h.n_seqs + 1) * 8, cudaMemcpyHostToDevice, s));
+	CU(cudaMemsetAsync(ctx->d_scalars, 0, 16, s));
+	CU(cudaEventRecord(ctx->slot[0].ev_d2h, s)); // orders the copy streams after the setup above
+	CU(cudaStreamWaitEvent(ctx->copy_in, ctx->slot[0].ev_d2h, 0));
+	ctx->slot[0].used = ctx->slot[1].used = false;
+
+	const bool want_hit = h.hit_bits != nullptr, want_valid = h.valid_bits != nullptr;
+	const bool need_hit_dev = want_hit || op == PUB_INSERT_CHECK; // list rounds OR into hit words
+	auto run_chunks = [&]() -> int {
+		uint64_t idx = 0;
+		for (uint64_t c0 = 0; c0 < n_bases; c0 += chunk, idx++) {
+			Slot& sl = ctx->slot[idx & 1];
+			uint64_t cw = n_bases - c0 < chunk ? n_bases - c0 : chunk;
+			uint64_t cb = n_bases - c0 < cw + k - 1 ? n_bases - c0 : cw + k - 1; // chunk + halo
+			uint64_t words = (cw + 31) / 32;
+			TRY(ensure(sl.bases, (size_t)chunk + k + 64));
+			if (need_hit_dev) TRY(ensure(sl.hit, (size_t)(chunk / 32 + 1) * 4));
+			if (want_valid) TRY(ensure(sl.valid, (size_t)(chunk / 32 + 1) * 4));
+			if (h.counts) TRY(ensure(sl.counts, (size_t)chunk));
+			if (h.hashes) TRY(ensure(sl.hashes, (size_t)chunk * H * 8));
+			if (h.strands) TRY(ensure(sl.strands, (size_t)chunk * H));
+			// the slot is free once its previous results have left the device
+			if (sl.used)
+				CU(cudaStreamWaitEvent(ctx->copy_in, sl.ev_d2h, 0));
+			CU(cudaMemcpyAsync(sl.bases.p, h.bases + c0, cb, cudaMemcpyHostToDevice, ctx->copy_in));
+			CU(cudaEventRecord(sl.ev_h2d, ctx->copy_in));
+			CU(cudaStreamWaitEvent(s, sl.ev_h2d, 0));
+			if (sl.used)
+				CU(cudaStreamWaitEvent(s, sl.ev_d2h, 0));
+			ChunkIO io;
+			io.d_bases = (const uint8_t*)sl.bases.p;
+			io.n_bases = cb;
+			io.base0 = c0;
+			io.n_windows = cw;
+			io.d_offsets = (const uint64_t*)ctx->offsets.p;
+			io.n_seqs = h.n_seqs;
+			io.d_hit = need_hit_dev ? (uint32_t*)sl.hit.p : nullptr;
+			io.d_valid = want_valid ? (uint32_t*)sl.valid.p : nullptr;
+			io.d_counts = h.counts ? (uint8_t*)sl.counts.p : nullptr;
+			io.d_hashes = h.hashes ? (uint64_t*)sl.hashes.p : nullptr;
+			io.d_strands = h.strands ? (uint8_t*)sl.strands.p : nullptr;
+			io.d_stats = (uint64_t*)ctx->d_scalars;
+			if (io.d_counts) CU(cudaMemsetAsync(io.d_counts, 0, cw, s));
+			if (io.d_hashes) CU(cudaMemsetAsync(io.d_hashes, 0, cw * H * 8, s));
+			if (io.d_strands) CU(cudaMemsetAsync(io.d_strands, 0, cw * H, s));
+			if (op == PUB_HASH) {
+				SeqParams P = hc.proto;
+				P.fm = make_fastmod(1);
+				P.force_generic = (uint32_t)ctx->force_generic;
+				fill_io(P, io);
+				TRY(launch(ctx, OP_HASH, P, s));
+			} else {
+				TRY(filter_op_dev(f, op, io, s));
+			}
+			CU(cudaEventRecord(sl.ev_kernel, s));
+			CU(cudaStreamWaitEvent(ctx->copy_out, sl.ev_kernel, 0));
+			if (want_hit)
+				CU(cudaMemcpyAsync(h.hit_bits + (c0 >> 3), sl.hit.p, words * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
+			if (want_valid)
+				CU(cudaMemcpyAsync(h.valid_bits + (c0 >> 3), sl.valid.p, words * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
+			if (h.counts)
+				CU(cudaMemcpyAsync(h.counts + c0, sl.counts.p, cw, cudaMemcpyDeviceToHost, ctx->copy_out));
+			if (h.hashes)
+				CU(cudaMemcpyAsync(h.hashes + c0 * H, sl.hashes.p, cw * H * 8, cudaMemcpyDeviceToHost, ctx->copy_out));
+			if (h.strands)
+				CU(cudaMemcpyAsync(h.strands + c0 * H, sl.strands.p, cw * H, cudaMemcpyDeviceToHost, ctx->copy_out));
+			CU(cudaEventRecord(sl.ev_d2h, ctx->copy_out));
+			sl.used = true;
+		}
+		return BTLBF_OK;
+	};
+	int rc = run_chunks();
+	// drain: everything queued on the three streams must finish before the caller reads its buffers
+	cudaError_t e1 = cudaStreamSynchronize(ctx->copy_in);
+	cudaError_t e2 = cudaStreamSynchronize(s);
+	cudaError_t e3 = cudaStreamSynchronize(ctx->copy_out);
+	if (rc != BTLBF_OK)
+		return rc;
+	CU(e1);
+	CU(e2);
+	CU(e3);
+	CU(cudaMemcpy(ctx->h_scalars, ctx->d_scalars, 16, cudaMemcpyDeviceToHost));
+	if (h.n_kmers) *h.n_kmers = ctx->h_scalars[0];
+	if (h.n_hits) *h.n_hits = ctx->h_scalars[1];
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_insert_seqs(btlbf_filter* f, const char* bases, const uint64_t* offsets, uint64_t n_seqs,
+                                 uint64_t* n_kmers)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	HostIO h;
+	h.bases = bases; h.offsets = offsets; h.n_seqs = n_seqs; h.n_kmers = n_kmers;
+	return host_pipeline(f->ctx, f, nullptr, PUB_INSERT, h);
+}
+
+extern "C" int btlbf_contains_seqs(btlbf_filter* f, const char* bases, const uint64_t* offsets, uint64_t n_seqs,
+                                   uint8_t* hit_bits, uint8_t* valid_bits, uint64_t* n_kmers, uint64_t* n_hits)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	HostIO h;
+	h.bases = bases; h.offsets = offsets; h.n_seqs = n_seqs; h.hit_bits = hit_bits; h.valid_bits = valid_bits;
+	h.n_kmers = n_kmers; h.n_hits = n_hits;
+	return host_pipeline(f->ctx, f, nullptr, PUB_CONTAINS, h);
+}
+
+extern "C" int btlbf_insert_and_check_seqs(btlbf_filter* f, const char* bases, const uint64_t* offsets,
+                                           uint64_t n_seqs, uint8_t* found_bits, uint8_t* valid_bits,
+                                           uint64_t* n_kmers)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	HostIO h;
+	h.bases = bases; h.offsets = offsets; h.n_seqs = n_seqs; h.hit_bits = found_bits; h.valid_bits = valid_bits;
+	h.n_kmers = n_kmers;
+	return host_pipeline(f->ctx, f, nullptr, PUB_INSERT_CHECK, h);
+}
+
+extern "C" int btlbf_mincount_seqs(btlbf_filter* f, const char* bases, const uint64_t* offsets, uint64_t n_seqs,
+                                   uint8_t* counts, uint8_t* valid_bits, uint64_t* n_kmers)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	if (f->kind != BTLBF_COUNTING8)
+		return fail(BTLBF_ERR_STATE, "mincount_seqs needs a counting filter");
+	HostIO h;
+	h.bases = bases; h.offsets = offsets; h.n_seqs = n_seqs; h.counts = counts; h.valid_bits = valid_bits;
+	h.n_kmers = n_kmers;
+	return host_pipeline(f->ctx, f, nullptr, PUB_MINCOUNT, h);
+}
+
+extern "C" int btlbf_increment_all_seqs(btlbf_filter* f, const char* bases, const uint64_t* offsets, uint64_t n_seqs,
+                                        uint64_t* n_kmers)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	if (f->kind != BTLBF_COUNTING8)
+		return fail(BTLBF_ERR_STATE, "increment_all_seqs needs a counting filter");
+	HostIO h;
+	h.bases = bases; h.offsets = offsets; h.n_seqs = n_seqs; h.n_kmers = n_kmers;
+	return host_pipeline(f->ctx, f, nullptr, PUB_INCALL, h);
+}
+
+extern "C" int btlbf_hash_seqs(btlbf_ctx* ctx, unsigned hash_num, unsigned kmer_size, const char* const* seeds,
+                               unsigned n_seeds, unsigned h2, const char* bases, const uint64_t* offsets,
+                               uint64_t n_seqs, uint64_t* hashes, uint8_t* strands, uint8_t* valid_bits,
+                               uint64_t* n_kmers)
+{
+	TRY(use(ctx));
+	HashCfg hc;
+	int rc = hashcfg_init(hc, kmer_size, hash_num, n_seeds ? seeds : nullptr, n_seeds, h2);
+	if (rc == BTLBF_OK) {
+		HostIO h;
+		h.bases = bases; h.offsets = offsets; h.n_seqs = n_seqs; h.hashes = hashes; h.strands = strands;
+		h.valid_bits = valid_bits; h.n_kmers = n_kmers;
+		rc = host_pipeline(ctx, nullptr, &hc, PUB_HASH, h);
+	}
+	hashcfg_free(hc);
+	return rc;
+}
+
+// ---------------------------------------------------------------- ordered-update statistics (tests / tuning)
+extern "C" int btlbf_filter_ordered_stats(btlbf_filter* f, uint64_t* deferred, uint64_t* rounds)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	if (deferred) *deferred = f->deferred_total;
+	if (rounds) *rounds = f->rounds_total;
+	return BTLBF_OK;
+}
+
+// ---------------------------------------------------------------- synthetic inputs, probe
+extern "C" int btlbf_synth_genome_dev(btlbf_ctx* ctx, void* d_out, uint64_t start, uint64_t n, uint64_t seed)
+{
+	TRY(use(ctx));
+	if (n && !d_out)
+		return fail(BTLBF_ERR_ARG, "null output");
+	cudaError_t e = launch_synth_genome((uint8_t*)d_out, start, n, seed, ctx->active);
+	if (e != cudaSuccess)
+		return fail(BTLBF_ERR_CUDA, "synth_genome launch failed: %s", cudaGetErrorString(e));
+	ctx->launches++;
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_synth_reads_dev(btlbf_ctx* ctx, void* d_out, uint64_t first_read, uint64_t n_reads,
+                                     unsigned read_len, uint64_t g_len, uint64_t genome_seed, uint64_t read_seed)
+{
+	TRY(use(ctx));
+	if (n_reads && !d_out)
+		return fail(BTLBF_ERR_ARG, "null output");
+	if (read_len == 0 || g_len <= read_len)
+		return fail(BTLBF_ERR_ARG, "need 0 < read_len < g_len");
+	cudaError_t e = launch_synth_reads((uint8_t*)d_out, first_read, n_reads, read_len, g_len, genome_seed, read_seed,
+	                                   ctx->active);
+	if (e != cudaSuccess)
+		return fail(BTLBF_ERR_CUDA, "synth_reads launch failed: %s", cudaGetErrorString(e));
+	ctx->launches++;
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_random_access_probe(btlbf_ctx* ctx, void* d_array, uint64_t bytes, uint64_t n_access, int mode,
+                                         float* elapsed_ms)
+{
+	TRY(use(ctx));
+	if (!d_array || bytes < 4 || !elapsed_ms || (mode != 0 && mode != 1))
+		return fail(BTLBF_ERR_ARG, "bad probe arguments");
+	cudaEvent_t a, b;
+	CU(cudaEventCreate(&a));
+	CU(cudaEventCreate(&b));
+	CU(cudaEventRecord(a, ctx->active));
+	cudaError_t e = launch_random_probe((uint32_t*)d_array, bytes / 4, n_access, mode, ctx->d_scalars + 3, ctx->active);
+	if (e != cudaSuccess)
+		return fail(BTLBF_ERR_CUDA, "probe launch failed: %s", cudaGetErrorString(e));
+	ctx->launches++;
+	CU(cudaEventRecord(b, ctx->active));
+	CU(cudaEventSynchronize(b));
+	CU(cudaEventElapsedTime(elapsed_ms, a, b));
+	cudaEventDestroy(a);
+	cudaEventDestroy(b);
+	return BTLBF_OK;
+}
+
+// ---------------------------------------------------------------- legacy per-k-mer interface (precomputed hashes)
+static int hashes_op(btlbf_filter* f, int op, const uint64_t* hashes, uint64_t n, uint8_t* out)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	if (n == 0)
+		return BTLBF_OK;
+	if (!hashes)
+		return fail(BTLBF_ERR_ARG, "null hashes");
+	btlbf_ctx* ctx = f->ctx;
+	TRY(use(ctx));
+	cudaStream_t s = ctx->active;
+	Slot& sl = ctx->slot[0];
+	uint32_t h = f->hc.h;
+	TRY(ensure(sl.hashes, n * h * 8));
+	TRY(ensure(sl.counts, n));
+	CU(cudaMemcpyAsync(sl.hashes.p, hashes, n * h * 8, cudaMemcpyHostToDevice, s));
+	cudaError_t e = launch_hashes_op(op, f->d_data, make_fastmod(f->size), h, f->threshold,
+	                                 (const uint64_t*)sl.hashes.p, n, (uint8_t*)sl.counts.p, s);
+	if (e != cudaSuccess)
+		return fail(BTLBF_ERR_CUDA, "hashes kernel launch failed: %s", cudaGetErrorString(e));
+	ctx->launches++;
+	if (out)
+		CU(cudaMemcpyAsync(out, sl.counts.p, n, cudaMemcpyDeviceToHost, s));
+	CU(cudaStreamSynchronize(s));
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_insert_hashes(btlbf_filter* f, const uint64_t* hashes, uint64_t n_kmers, uint8_t* found)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	if (f->kind == BTLBF_BLOOM)
+		return hashes_op(f, found ? 5 : 0, hashes, n_kmers, found);
+	return hashes_op(f, 3, hashes, n_kmers, found);
+}
+
+extern "C" int btlbf_contains_hashes(btlbf_filter* f, const uint64_t* hashes, uint64_t n_kmers, uint8_t* hit)
+{
+	if (!f || (!hit && n_kmers))
+		return fail(BTLBF_ERR_ARG, "null argument");
+	if (f->kind == BTLBF_BLOOM)
+		return hashes_op(f, 1, hashes, n_kmers, hit);
+	TRY(hashes_op(f, 2, hashes, n_kmers, hit));
+	for (uint64_t i = 0; i < n_kmers; i++)
+		hit[i] = hit[i] >= f->threshold; // CountingBloomFilter.hpp:190-196
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_mincount_hashes(btlbf_filter* f, const uint64_t* hashes, uint64_t n_kmers, uint8_t* counts)
+{
+	if (!f || (!counts && n_kmers))
+		return fail(BTLBF_ERR_ARG, "null argument");
+	if (f->kind != BTLBF_COUNTING8)
+		return fail(BTLBF_ERR_STATE, "mincount_hashes needs a counting filter");
+	return hashes_op(f, 2, hashes, n_kmers, counts);
+}
+
+extern "C" int btlbf_increment_all_hashes(btlbf_filter* f, const uint64_t* hashes, uint64_t n_kmers)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	if (f->kind != BTLBF_COUNTING8)
+		return fail(BTLBF_ERR_STATE, "increment_all_hashes needs a counting filter");
+	return hashes_op(f, 4, hashes, n_kmers, nullptr);
+}
+
+// ---------------------------------------------------------------- file layout (BTLBloomFilter_v1 / BTLCountingBloomFilter_v1)
+// The reference writes the header through cpptoml (BloomFilter.hpp:264-288, CountingBloomFilter.hpp:
+// 344-367): one table, tab-indented "key = value" lines in the iteration order of the
+// std::unordered_map that cpptoml keeps the keys in (libstdc++), doubles with showpoint and 17
+// significant digits (cpptoml.h:3477-3494), then "[HeaderEnd]\n" and the raw array.
+static std::string toml_double(double v)
+{
+	char tmp[64];
+	snprintf(tmp, sizeof tmp, "%#.17g", v);
+	std::string s(tmp);
+	size_t p;
+	if ((p = s.find("e-0")) != std::string::npos) s.erase(p + 2, 1);
+	else if ((p = s.find("e+0")) != std::string::npos) s.erase(p + 2, 1);
+	else if ((p = s.find("e0")) != std::string::npos) s.erase(p + 1, 1);
+	return s;
+}
+
+static std::string format_header(int kind, uint64_t size, uint64_t size_bytes, unsigned h, unsigned k, double dFPR,
+                                 uint64_t nEntry, uint64_t tEntry)
+{
+	char buf[640];
+	if (kind == BTLBF_BLOOM)
+		snprintf(buf, sizeof buf,
+		         "[BTLBloomFilter_v1]\n\tnEntry = %llu\n\tdFPR = %s\n\tEntry = %llu\n\tBloomFilterSizeInBytes = %llu\n"
+		         "\tBloomFilterSize = %llu\n\tHashNum = %u\n\tKmerSize = %u\n[HeaderEnd]\n",
+		         (unsigned long long)nEntry, toml_double(dFPR).c_str(), (unsigned long long)tEntry,
+		         (unsigned long long)size_bytes, (unsigned long long)size, h, k);
+	else
+		snprintf(buf, sizeof buf,
+		         "[BTLCountingBloomFilter_v1]\n\tBloomFilterSize = %llu\n\tHashNum = %u\n\tKmerSize = %u\n"
+		         "\tBloomFilterSizeInBytes = %llu\n\tBitsPerCounter = 8\n[HeaderEnd]\n",
+		         (unsigned long long)size, h, k, (unsigned long long)size_bytes);
+	return buf;
+}
+
+extern "C" int btlbf_format_header(int kind, uint64_t size, uint64_t size_bytes, unsigned hash_num, unsigned kmer_size,
+                                   double dFPR, uint64_t nEntry, uint64_t tEntry, char* buf, size_t cap, size_t* len)
+{
+	if (kind != BTLBF_BLOOM && kind != BTLBF_COUNTING8)
+		return fail(BTLBF_ERR_ARG, "unknown filter kind %d", kind);
+	std::string hdr = format_header(kind, size, size_bytes, hash_num, kmer_size, dFPR, nEntry, tEntry);
+	if (len) *len = hdr.size();
+	if (buf) {
+		if (cap < hdr.size() + 1)
+			return fail(BTLBF_ERR_ARG, "header buffer too small");
+		memcpy(buf, hdr.c_str(), hdr.size() + 1);
+	}
+	return BTLBF_OK;
+}
+
+struct ParsedHeader
+{
+	uint64_t size = 0, size_bytes = 0, nEntry = 0, tEntry = 0;
+	unsigned h = 0, k = 0, bits_per_counter = 8;
+	double dFPR = 0;
+	unsigned seen = 0; // bit per key
+	size_t body_offset = 0;
+};
+
+// Mirrors loadHeader (BloomFilter.hpp:116-166, CountingBloomFilter.hpp:283-329): first line must be
+// "[magic]", lines are collected up to "[HeaderEnd]", and every key the reference dereferences must exist.
+static int parse_header(FILE* fp, int kind, ParsedHeader& H)
+{
+	const char* magic = kind == BTLBF_BLOOM ? "[BTLBloomFilter_v1]" : "[BTLCountingBloomFilter_v1]";
+	std::string line;
+	auto getline = [&](std::string& out) -> bool {
+		out.clear();
+		int c;
+		bool any = false;
+		while ((c = fgetc(fp)) != EOF) {
+			any = true;
+			if (c == '\n')
+				return true;
+			out.push_back((char)c);
+		}
+		return any;
+	};
+	if (!getline(line) || line != magic)
+		return fail(BTLBF_ERR_ARG, "magic string does not match (likely version mismatch): '%.80s' vs '%s'",
+		            line.c_str(), magic);
+	bool end = false;
+	while (getline(line)) {
+		if (line == "[HeaderEnd]") {
+			end = true;
+			break;
+		}
+		size_t eq = line.find('=');
+		if (eq == std::string::npos)
+			continue;
+		auto trim = [](std::string s) {
+			size_t a = s.find_first_not_of(" \t\r"), b = s.find_last_not_of(" \t\r");
+			return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+		};
+		std::string key = trim(line.substr(0, eq)), val = trim(line.substr(eq + 1));
+		size_t hash = val.find('#');
+		if (hash != std::string::npos)
+			val = trim(val.substr(0, hash));
+		std::string digits;
+		for (char c : val)
+			if (c != '_')
+				digits.push_back(c);
+		if (key == "BloomFilterSize") { H.size = strtoull(digits.c_str(), nullptr, 10); H.seen |= 1; }
+		else if (key == "HashNum") { H.h = (unsigned)strtoull(digits.c_str(), nullptr, 10); H.seen |= 2; }
+		else if (key == "KmerSize") { H.k = (unsigned)strtoull(digits.c_str(), nullptr, 10); H.seen |= 4; }
+		else if (key == "BloomFilterSizeInBytes") { H.size_bytes = strtoull(digits.c_str(), nullptr, 10); H.seen |= 8; }
+		else if (key == "dFPR") { H.dFPR = strtod(digits.c_str(), nullptr); H.seen |= 16; }
+		else if (key == "nEntry") { H.nEntry = strtoull(digits.c_str(), nullptr, 10); H.seen |= 32; }
+		else if (key == "Entry") { H.tEntry = strtoull(digits.c_str(), nullptr, 10); H.seen |= 64; }
+		else if (key == "BitsPerCounter") { H.bits_per_counter = (unsigned)strtoull(digits.c_str(), nullptr, 10); H.seen |= 128; }
+	}
+	if (!end)
+		return fail(BTLBF_ERR_ARG, "pre-built bloom filter does not have the correct header end.");
+	unsigned need = kind == BTLBF_BLOOM ? (1 | 2 | 4 | 8 | 16 | 32 | 64) : (1 | 2 | 4 | 8 | 128);
+	if ((H.seen & need) != need)
+		return fail(BTLBF_ERR_ARG, "filter header lacks a required key (mask %#x of %#x present)", H.seen & need, need);
+	H.body_offset = (size_t)ftell(fp);
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_filter_store(btlbf_filter* f, const char* path, double dFPR, uint64_t nEntry, uint64_t tEntry)
+{
+	if (!f || !path)
+		return fail(BTLBF_ERR_ARG, "null argument");
+	btlbf_ctx* ctx = f->ctx;
+	TRY(use(ctx));
+	FILE* fp = fopen(path, "wb");
+	if (!fp)
+		return fail(BTLBF_ERR_ARG, "error: `%s': %s", path, strerror(errno));
+	std::string hdr = format_header(f->kind, f->size, f->bytes, f->hc.h, f->hc.k, dFPR, nEntry, tEntry);
+	bool ok = fwrite(hdr.data(), 1, hdr.size(), fp) == hdr.size();
+	// stream the array through a pinned bounce buffer
+	const size_t CH = (size_t)64 << 20;
+	void* bounce = nullptr;
+	size_t bsz = f->bytes < CH ? (size_t)f->bytes : CH;
+	cudaError_t e = cudaHostAlloc(&bounce, bsz ? bsz : 1, cudaHostAllocDefault);
+	for (uint64_t off = 0; ok && e == cudaSuccess && off < f->bytes; off += CH) {
+		size_t n = f->bytes - off < CH ? (size_t)(f->bytes - off) : CH;
+		e = cudaMemcpyAsync(bounce, f->d_data + off, n, cudaMemcpyDeviceToHost, ctx->active);
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(ctx->active);
+		if (e == cudaSuccess)
+			ok = fwrite(bounce, 1, n, fp) == n;
+	}
+	if (bounce)
+		cudaFreeHost(bounce);
+	ok = ok && fflush(fp) == 0;
+	int saved = errno;
+	fclose(fp);
+	if (e != cudaSuccess)
+		return fail(BTLBF_ERR_CUDA, "reading the filter back failed: %s", cudaGetErrorString(e));
+	if (!ok)
+		return fail(BTLBF_ERR_ARG, "error: `%s': %s", path, strerror(saved));
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_filter_load(btlbf_ctx* ctx, const char* path, int kind, unsigned threshold, btlbf_filter** out,
+                                 double* dFPR, uint64_t* nEntry, uint64_t* tEntry)
+{
+	if (!ctx || !path || !out)
+		return fail(BTLBF_ERR_ARG, "null argument");
+	*out = nullptr;
+	TRY(use(ctx));
+	if (kind != BTLBF_BLOOM && kind != BTLBF_COUNTING8)
+		return fail(BTLBF_ERR_ARG, "unknown filter kind %d", kind);
+	FILE* fp = fopen(path, "rb");
+	if (!fp)
+		return fail(BTLBF_ERR_ARG, "error: `%s': %s", path, strerror(errno));
+	ParsedHeader H;
+	int rc = parse_header(fp, kind, H);
+	if (rc != BTLBF_OK) {
+		fclose(fp);
+		return rc;
+	}
+	// BloomFilter: the array is BloomFilterSize/8 bytes (initSize, :389-399) and BloomFilterSizeInBytes
+	// bytes are read into it; CountingBloomFilter<uint8_t>: BloomFilterSizeInBytes counters are read
+	// and indexed modulo BloomFilterSize (:268-281).
+	uint64_t size = H.size, body = H.size_bytes;
+	if (kind == BTLBF_BLOOM && (size % 8 != 0 || body != size / 8)) {
+		fclose(fp);
+		return fail(BTLBF_ERR_ARG, "inconsistent header: BloomFilterSize %llu, BloomFilterSizeInBytes %llu",
+		            (unsigned long long)size, (unsigned long long)body);
+	}
+	if (kind == BTLBF_COUNTING8 && (H.bits_per_counter != 8 || body != size)) {
+		fclose(fp);
+		return fail(BTLBF_ERR_ARG, "only 8-bit counting filters are supported (BitsPerCounter %u, size %llu, bytes %llu)",
+		            H.bits_per_counter, (unsigned long long)size, (unsigned long long)body);
+	}
+	btlbf_filter* f = nullptr;
+	rc = filter_make(ctx, kind, size, H.h, H.k, threshold, nullptr, 0, &f);
+	if (rc != BTLBF_OK) {
+		fclose(fp);
+		return rc;
+	}
+	const size_t CH = (size_t)64 << 20;
+	void* bounce = nullptr;
+	cudaError_t e = cudaHostAlloc(&bounce, body < CH ? (size_t)(body ? body : 1) : CH, cudaHostAllocDefault);
+	bool ok = true;
+	for (uint64_t off = 0; ok && e == cudaSuccess && off < body; off += CH) {
+		size_t n = body - off < CH ? (size_t)(body - off) : CH;
+		ok = fread(bounce, 1, n, fp) == n;
+		if (ok)
+			e = cudaMemcpyAsync(f->d_data + off, bounce, n, cudaMemcpyHostToDevice, ctx->active);
+		if (ok && e == cudaSuccess)
+			e = cudaStreamSynchronize(ctx->active);
+	}
+	if (bounce)
+		cudaFreeHost(bounce);
+	fclose(fp);
+	if (e != cudaSuccess || !ok) {
+		btlbf_filter_destroy(f);
+		if (!ok)
+			return fail(BTLBF_ERR_ARG, "error: `%s': file shorter than its header says", path);
+		return fail(BTLBF_ERR_CUDA, "uploading the filter failed: %s", cudaGetErrorString(e));
+	}
+	if (dFPR) *dFPR = H.dFPR;
+	if (nEntry) *nEntry = H.nEntry;
+	if (tEntry) *tEntry = H.tEntry;
+	*out = f;
+	return BTLBF_OK;
+}

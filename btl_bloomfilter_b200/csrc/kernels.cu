@@ -99,32 +99,190 @@ cudaError_t launch_seq(SeqOp op, const SeqParams& P, cudaStream_t stream)
 	case OP_BF_CONTAINS: return launch_op<OP_BF_CONTAINS>(P, stream);
 	case OP_CBF_MINCOUNT: return launch_op<OP_CBF_MINCOUNT>(P, stream);
 	case OP_CBF_INCALL: return launch_op<OP_CBF_INCALL>(P, stream);
-	case OP_CBF_TOUCH: return launch_op<OP_CBF_TOUCH>(P, stream);
+	case OP_RESV_TOUCH: return launch_op<OP_RESV_TOUCH>(P, stream);
 	case OP_CBF_COMMIT: return launch_op<OP_CBF_COMMIT>(P, stream);
-	case OP_CBF_CLEAR: return launch_op<OP_CBF_CLEAR>(P, stream);
-	case OP_BF_INSERT_CHECK: return launch_op<OP_BF_INSERT_CHECK>(P, stream);
+	case OP_RESV_CLEAR: return launch_op<OP_RESV_CLEAR>(P, stream);
+	case OP_BFCHK_COMMIT: return launch_op<OP_BFCHK_COMMIT>(P, stream);
 	}
 	return cudaErrorInvalidValue;
 }
 
-// ---------------------------------------------------------------- exact counting insert, residual rounds
-template<bool POW2>
-__global__ void __launch_bounds__(128) cbf_list_kernel(int phase, const __grid_constant__ SeqParams P,
-                                                       const __grid_constant__ ListParams L)
+// ---------------------------------------------------------------- ordered updates, residual rounds
+template<bool POW2, int KIND>
+__global__ void __launch_bounds__(128) list_round_kernel(int phase, const __grid_constant__ SeqParams P,
+                                                         const __grid_constant__ ListParams L)
 {
 	uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
-	list_phase<POW2>(phase, P, L, item);
+	if (item >= *L.count_in)
+		return;
+	uint32_t w = L.list_in[item];
+	uint64_t emask = ((uint64_t)1 << L.resv_log2) - 1;
+	if (phase == 0)
+		list_round_reserve<POW2>(P, L.resv, emask, L.epoch, w);
+	else if (!list_round_commit<POW2, KIND>(P, L.resv, emask, L.epoch, w))
+		L.list_out[atomicAdd(L.count_out, 1u)] = w;
 }
 
-cudaError_t launch_cbf_list_phase(int phase, const SeqParams& P, const ListParams& L, cudaStream_t stream)
+cudaError_t launch_list_round(int phase, const SeqParams& P, const ListParams& L, cudaStream_t stream)
 {
 	if (L.max_items == 0)
 		return cudaSuccess;
 	unsigned grid = (L.max_items + 127) / 128;
-	if (P.fm.pow2)
-		cbf_list_kernel<true><<<grid, 128, 0, stream>>>(phase, P, L);
+	if (P.fm.pow2) {
+		if (L.kind == 0)
+			list_round_kernel<true, 0><<<grid, 128, 0, stream>>>(phase, P, L);
+		else
+			list_round_kernel<true, 1><<<grid, 128, 0, stream>>>(phase, P, L);
+	} else {
+		if (L.kind == 0)
+			list_round_kernel<false, 0><<<grid, 128, 0, stream>>>(phase, P, L);
+		else
+			list_round_kernel<false, 1><<<grid, 128, 0, stream>>>(phase, P, L);
+	}
+	return cudaGetLastError();
+}
+
+constexpr int kDrainThreads = 1024;
+
+template<bool POW2, int KIND>
+__global__ void __launch_bounds__(kDrainThreads) list_drain_kernel(const __grid_constant__ SeqParams P,
+                                                                    const __grid_constant__ ListParams L)
+{
+	__shared__ uint32_t s_out;
+	const uint32_t* in = L.list_in;
+	uint32_t* out = L.list_out;
+	uint32_t* other = const_cast<uint32_t*>(L.list_in);
+	uint32_t n = *L.count_in;
+	uint32_t epoch = L.epoch, rounds = 0;
+	uint64_t emask = ((uint64_t)1 << L.resv_log2) - 1;
+	while (n > 0) {
+		if (threadIdx.x == 0)
+			s_out = 0;
+		for (uint32_t i = threadIdx.x; i < n; i += kDrainThreads)
+			list_round_reserve<POW2>(P, L.resv, emask, epoch, in[i]);
+		__syncthreads();
+		for (uint32_t i = threadIdx.x; i < n; i += kDrainThreads) {
+			uint32_t w = in[i];
+			if (!list_round_commit<POW2, KIND>(P, L.resv, emask, epoch, w))
+				out[atomicAdd(&s_out, 1u)] = w;
+		}
+		__syncthreads();
+		n = s_out;
+		const uint32_t* t = out;
+		out = other;
+		in = t;
+		other = const_cast<uint32_t*>(t);
+		epoch++;
+		rounds++;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) {
+		*L.count_out = 0;
+		if (L.rounds_out)
+			*L.rounds_out = rounds;
+	}
+}
+
+cudaError_t launch_list_drain(const SeqParams& P, const ListParams& L, cudaStream_t stream)
+{
+	if (P.fm.pow2) {
+		if (L.kind == 0)
+			list_drain_kernel<true, 0><<<1, kDrainThreads, 0, stream>>>(P, L);
+		else
+			list_drain_kernel<true, 1><<<1, kDrainThreads, 0, stream>>>(P, L);
+	} else {
+		if (L.kind == 0)
+			list_drain_kernel<false, 0><<<1, kDrainThreads, 0, stream>>>(P, L);
+		else
+			list_drain_kernel<false, 1><<<1, kDrainThreads, 0, stream>>>(P, L);
+	}
+	return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- precomputed-hash (legacy per-k-mer) interface
+__global__ void __launch_bounds__(128) hashes_kernel(int op, void* filter, FastMod fm, uint32_t h, uint32_t threshold,
+                                                     const uint64_t* __restrict__ hashes, uint64_t n, uint8_t* out)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	const uint64_t* hv = hashes + i * h;
+	if (op == 0) {
+		uint32_t* words = (uint32_t*)filter;
+		for (uint32_t j = 0; j < h; j++) {
+			uint64_t b = fm.pow2 ? fastmod<true>(hv[j], fm) : fastmod<false>(hv[j], fm);
+			atomicOr(words + (b >> 5), 1u << (uint32_t)(b & 31));
+		}
+	} else if (op == 1) {
+		const uint32_t* words = (const uint32_t*)filter;
+		uint32_t hit = 1;
+		for (uint32_t j = 0; j < h && hit; j++) {
+			uint64_t b = fm.pow2 ? fastmod<true>(hv[j], fm) : fastmod<false>(hv[j], fm);
+			hit = (__ldcg(words + (b >> 5)) >> (uint32_t)(b & 31)) & 1u;
+		}
+		out[i] = (uint8_t)hit;
+	} else if (op == 2) {
+		const uint8_t* cnt = (const uint8_t*)filter;
+		uint32_t mn = 255;
+		for (uint32_t j = 0; j < h; j++) {
+			uint32_t v = __ldcg(cnt + (fm.pow2 ? fastmod<true>(hv[j], fm) : fastmod<false>(hv[j], fm)));
+			mn = v < mn ? v : mn;
+		}
+		out[i] = (uint8_t)mn;
+	} else if (op == 4) {
+		for (uint32_t j = 0; j < h; j++)
+			counter_sat_inc((uint8_t*)filter, fm.pow2 ? fastmod<true>(hv[j], fm) : fastmod<false>(hv[j], fm));
+	}
+}
+
+__global__ void hashes_serial_kernel(int op, void* filter, FastMod fm, uint32_t h, uint32_t threshold,
+                                     const uint64_t* __restrict__ hashes, uint64_t n, uint8_t* out)
+{
+	if (blockIdx.x != 0 || threadIdx.x != 0)
+		return;
+	for (uint64_t i = 0; i < n; i++) {
+		const uint64_t* hv = hashes + i * h;
+		if (op == 3) {
+			volatile uint8_t* cnt = (volatile uint8_t*)filter;
+			uint32_t mn = 255;
+			for (uint32_t j = 0; j < h; j++) {
+				uint32_t v = cnt[fm.pow2 ? fastmod<true>(hv[j], fm) : fastmod<false>(hv[j], fm)];
+				mn = v < mn ? v : mn;
+			}
+			if (out)
+				out[i] = mn >= threshold;
+			if (mn == 255)
+				continue;
+			for (uint32_t j = 0; j < h; j++) {
+				uint64_t p = fm.pow2 ? fastmod<true>(hv[j], fm) : fastmod<false>(hv[j], fm);
+				if (cnt[p] == mn)
+					cnt[p] = (uint8_t)(mn + 1);
+			}
+		} else {
+			volatile uint32_t* words = (volatile uint32_t*)filter;
+			uint32_t found = 1;
+			for (uint32_t j = 0; j < h; j++) {
+				uint64_t b = fm.pow2 ? fastmod<true>(hv[j], fm) : fastmod<false>(hv[j], fm);
+				uint32_t bit = 1u << (uint32_t)(b & 31);
+				uint32_t old = words[b >> 5];
+				found &= (old & bit) != 0;
+				words[b >> 5] = old | bit;
+			}
+			if (out)
+				out[i] = (uint8_t)found;
+		}
+	}
+}
+
+cudaError_t launch_hashes_op(int op, void* filter, FastMod fm, uint32_t h, uint32_t threshold,
+                             const uint64_t* d_hashes, uint64_t n, uint8_t* d_out, cudaStream_t stream)
+{
+	if (n == 0)
+		return cudaSuccess;
+	if (op == 3 || op == 5)
+		hashes_serial_kernel<<<1, 32, 0, stream>>>(op, filter, fm, h, threshold, d_hashes, n, d_out);
 	else
-		cbf_list_kernel<false><<<grid, 128, 0, stream>>>(phase, P, L);
+		hashes_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(op, filter, fm, h, threshold, d_hashes, n, d_out);
 	return cudaGetLastError();
 }
 

@@ -19,10 +19,11 @@ enum SeqOp {
 	OP_BF_CONTAINS = 2,  // BloomFilter::contains
 	OP_CBF_MINCOUNT = 3, // CountingBloomFilter::minCount (+ contains via threshold)
 	OP_CBF_INCALL = 4,   // CountingBloomFilter::incrementAll
-	OP_CBF_TOUCH = 5,    // exact incrementMin, phase 1: mark reservation bits
-	OP_CBF_COMMIT = 6,   // exact incrementMin, phase 2: commit uncontended k-mers, defer the rest
-	OP_CBF_CLEAR = 7,    // exact incrementMin, phase 3: clear the reservation bits this batch set
-	OP_BF_INSERT_CHECK = 8 // BloomFilter::insertAndCheck (atomic fetch-or; exact when k-mers are distinct)
+	// order-dependent updates (incrementMin, insertAndCheck) reproduced exactly, three passes per batch:
+	OP_RESV_TOUCH = 5,   // pass 1: mark reservation bits, detect contended slots
+	OP_CBF_COMMIT = 6,   // pass 2 (incrementMin): commit uncontended k-mers, defer the rest
+	OP_RESV_CLEAR = 7,   // pass 3: clear the reservation bits this batch set
+	OP_BFCHK_COMMIT = 8  // pass 2 (insertAndCheck)
 };
 
 struct SeqParams
@@ -69,21 +70,32 @@ size_t seq_kernel_smem_bytes(uint32_t k, bool spaced);
 // launches seq_kernel<op> for P on stream; returns cudaGetLastError()
 cudaError_t launch_seq(SeqOp op, const SeqParams& P, cudaStream_t stream);
 
-// exact incrementMin on a compacted list of deferred windows (P.pending / P.pending_count)
+// residual rounds of the ordered updates on the compacted list of deferred windows
 struct ListParams
 {
 	const uint32_t* list_in;
 	const uint32_t* count_in;
 	uint32_t* list_out;
-	uint32_t* count_out;
-	uint32_t* resv_idx; // 2^resv_idx_log2 uint32 entries for index reservation
-	uint32_t resv_idx_log2;
-	uint32_t epoch;     // high byte of the reservation word (smaller wins)
-	uint32_t max_items;
+	uint32_t* count_out;  // must be zero before a commit round
+	uint64_t* resv;       // 2^resv_log2 reservation words, initialised to all-ones
+	uint32_t resv_log2;
+	uint32_t epoch;       // strictly increasing across rounds
+	uint32_t max_items;   // upper bound of *count_in (sizes the grid)
+	uint32_t kind;        // 0: incrementMin, 1: insertAndCheck
+	uint32_t* rounds_out; // serial kernel: number of rounds it ran
 };
-cudaError_t launch_cbf_list_phase(int phase, const SeqParams& P, const ListParams& L,
-                                  cudaStream_t stream);
+// phase 0: reserve, phase 1: commit or re-queue (one grid-wide launch each)
+cudaError_t launch_list_round(int phase, const SeqParams& P, const ListParams& L, cudaStream_t stream);
+// one CTA loops reserve/commit rounds until the list is empty (short lists, long dependency chains)
+cudaError_t launch_list_drain(const SeqParams& P, const ListParams& L, cudaStream_t stream);
 
+// Legacy per-k-mer interface of the reference classes (caller supplies the h hash values of each k-mer,
+// BloomFilter.hpp:185-262, CountingBloomFilter.hpp:53-64,134-214): hashes = n x h values.
+// op 0: BF insert, 1: BF contains -> out[i], 2: CBF minCount -> out[i], 3: CBF incrementMin (+ out[i] =
+// minCount >= threshold beforehand, i.e. insertAndCheck), 4: CBF incrementAll, 5: BF insertAndCheck -> out[i].
+// Ops 3 and 5 are order-dependent and run the n k-mers one after the other in a single thread.
+cudaError_t launch_hashes_op(int op, void* filter, FastMod fm, uint32_t h, uint32_t threshold,
+                             const uint64_t* d_hashes, uint64_t n, uint8_t* d_out, cudaStream_t stream);
 cudaError_t launch_popcount(const void* data, uint64_t nbytes, int mode, unsigned threshold,
                             unsigned long long* d_out, cudaStream_t stream);
 cudaError_t launch_merge(void* dst, const void* src, uint64_t nbytes, int saturating_add,

@@ -307,8 +307,10 @@ BTL_HD void counter_sat_inc(uint8_t* cnt, uint64_t n)
 }
 
 // exact incrementMin of one k-mer that owns all its slots (CountingBloomFilter.hpp:134-162)
+// returns the minimum BEFORE the update (CountingBloomFilter::insertAndCheck, :206-214, reports
+// minCount >= threshold of that value)
 template<bool SPACED, bool POW2>
-BTL_HD void cbf_commit_one(const SeqParams& P, const TileSmem& sm, uint32_t w, uint64_t F, uint64_t RC)
+BTL_HD uint32_t cbf_commit_one(const SeqParams& P, const TileSmem& sm, uint32_t w, uint64_t F, uint64_t RC)
 {
 	uint8_t* cnt = (uint8_t*)P.filter;
 	uint32_t mn = 255;
@@ -318,13 +320,29 @@ BTL_HD void cbf_commit_one(const SeqParams& P, const TileSmem& sm, uint32_t w, u
 		return true;
 	});
 	if (mn == 255)
-		return;
+		return mn;
 	for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t, uint64_t hv, bool) {
 		uint64_t n = fastmod<POW2>(hv, P.fm);
 		if (ld_cg(cnt + n) == mn)
 			*(volatile uint8_t*)(cnt + n) = (uint8_t)(mn + 1);
 		return true;
 	});
+	return mn;
+}
+
+// insertAndCheck of one k-mer that owns all its bits (BloomFilter.hpp:200-214): true when every bit was set
+template<bool SPACED, bool POW2>
+BTL_HD bool bfchk_commit_one(const SeqParams& P, const TileSmem& sm, uint32_t w, uint64_t F, uint64_t RC)
+{
+	uint32_t* words = (uint32_t*)P.filter;
+	bool found = true;
+	for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t, uint64_t hv, bool) {
+		uint64_t n = fastmod<POW2>(hv, P.fm);
+		uint32_t bit = 1u << (uint32_t)(n & 31);
+		found &= (mem_atomic_or(words + (n >> 5), bit) & bit) != 0;
+		return true;
+	});
+	return found;
 }
 
 // ---------------------------------------------------------------- the fused per-window operation
@@ -354,17 +372,6 @@ BTL_HD void window_op(const SeqParams& P, const TileSmem& sm, uint64_t t0, uint3
 			mem_red_or(words + (n >> 5), 1u << (uint32_t)(n & 31));
 			return true;
 		});
-	} else if (OP == OP_BF_INSERT_CHECK) {
-		uint32_t* words = (uint32_t*)P.filter;
-		bool found = true;
-		for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t, uint64_t hv, bool) {
-			uint64_t n = fastmod<POW2>(hv, P.fm);
-			uint32_t bit = 1u << (uint32_t)(n & 31);
-			found &= (mem_atomic_or(words + (n >> 5), bit) & bit) != 0;
-			return true;
-		});
-		if (found)
-			out.hitw |= 1u << s;
 	} else if (OP == OP_BF_CONTAINS) {
 		bool hit;
 		bool done = false;
@@ -430,7 +437,8 @@ BTL_HD void window_op(const SeqParams& P, const TileSmem& sm, uint64_t t0, uint3
 			counter_sat_inc(cnt, fastmod<POW2>(hv, P.fm));
 			return true;
 		});
-	} else if (OP == OP_CBF_TOUCH) {
+	} else if (OP == OP_RESV_TOUCH) {
+		// ordered updates, pass 1: mark every (hashed) slot; a slot marked twice is contended
 		uint32_t mask = (1u << P.resv_log2) - 1u;
 		for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t, uint64_t hv, bool) {
 			uint32_t e = (uint32_t)fastmod<POW2>(hv, P.fm) & mask;
@@ -439,7 +447,10 @@ BTL_HD void window_op(const SeqParams& P, const TileSmem& sm, uint64_t t0, uint3
 				mem_red_or(P.resv_contended + (e >> 5), bit);
 			return true;
 		});
-	} else if (OP == OP_CBF_COMMIT) {
+	} else if (OP == OP_CBF_COMMIT || OP == OP_BFCHK_COMMIT) {
+		// pass 2: a k-mer none of whose slots is contended shares no slot with any other k-mer of the
+		// batch, so its update commutes with all of them and is applied now; the others are deferred
+		// to the index-ordered residual rounds (list_round_*)
 		uint32_t mask = (1u << P.resv_log2) - 1u;
 		bool contended = false;
 		for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t, uint64_t hv, bool) {
@@ -448,13 +459,18 @@ BTL_HD void window_op(const SeqParams& P, const TileSmem& sm, uint64_t t0, uint3
 			return true;
 		});
 		if (!contended) {
-			cbf_commit_one<SPACED, POW2>(P, sm, w, F, RC);
+			bool found;
+			if (OP == OP_CBF_COMMIT)
+				found = cbf_commit_one<SPACED, POW2>(P, sm, w, F, RC) >= P.threshold;
+			else
+				found = bfchk_commit_one<SPACED, POW2>(P, sm, w, F, RC);
+			if (found)
+				out.hitw |= 1u << s;
 		} else {
 			uint32_t slot = mem_atomic_inc(P.pending_count);
 			P.pending[slot] = (uint32_t)(t0 + w);
-			out.hitw |= 1u << s; // counts deferred k-mers in stats[1]
 		}
-	} else if (OP == OP_CBF_CLEAR) {
+	} else if (OP == OP_RESV_CLEAR) {
 		uint32_t mask = (1u << P.resv_log2) - 1u;
 		for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t, uint64_t hv, bool) {
 			uint32_t e = (uint32_t)fastmod<POW2>(hv, P.fm) & mask;
@@ -598,49 +614,67 @@ BTL_HD void list_for_each_hash(const SeqParams& P, uint32_t w, Fn&& fn)
 	}
 }
 
-// phase 0: reserve every slot with (epoch, window index); the smallest value wins, i.e. the newest
-// round and, within it, the earliest k-mer in reference order.
-// phase 1: a k-mer holding all its reservations commits; the others go to list_out.
-template<bool POW2>
-BTL_HD void list_phase(int phase, const SeqParams& P, const ListParams& L, uint32_t item)
+// Residual rounds of the ordered updates ("deterministic reservations").  Every pending k-mer writes
+// tag = (~epoch, window index) into the reservation table at each of its (hashed) slots with
+// atomicMin: the smallest tag wins, i.e. the newest round and, within it, the earliest k-mer in
+// reference order.  A k-mer holding all its reservations precedes every pending k-mer it conflicts
+// with, so applying its update now is exactly the sequential result; the others wait a round.
+// KIND 0: CountingBloomFilter::incrementMin, KIND 1: BloomFilter::insertAndCheck.
+BTL_HD uint64_t list_tag(uint32_t epoch, uint32_t w)
 {
-	uint32_t n = *L.count_in;
-	if (item >= n)
-		return;
-	uint32_t w = L.list_in[item];
-	uint64_t* R = reinterpret_cast<uint64_t*>(L.resv_idx);
-	uint64_t emask = ((uint64_t)1 << L.resv_idx_log2) - 1;
-	uint64_t tag = ((uint64_t)(0xffffffffu - L.epoch) << 32) | w;
-	if (phase == 0) {
+	return ((uint64_t)(0xffffffffu - epoch) << 32) | w;
+}
+
+template<bool POW2>
+BTL_HD void list_round_reserve(const SeqParams& P, uint64_t* R, uint64_t emask, uint32_t epoch, uint32_t w)
+{
+	uint64_t tag = list_tag(epoch, w);
+	list_for_each_hash<POW2>(P, w, [&](uint64_t slot) {
+		mem_atomic_min64(R + (slot & emask), tag);
+		return true;
+	});
+}
+
+// returns true when the k-mer was committed, false when it must wait for the next round
+template<bool POW2, int KIND>
+BTL_HD bool list_round_commit(const SeqParams& P, const uint64_t* R, uint64_t emask, uint32_t epoch, uint32_t w)
+{
+	uint64_t tag = list_tag(epoch, w);
+	bool own = true;
+	list_for_each_hash<POW2>(P, w, [&](uint64_t slot) {
+		own = ld_cg(R + (slot & emask)) == tag;
+		return own;
+	});
+	if (!own)
+		return false;
+	if (KIND == 0) {
+		uint8_t* cnt = (uint8_t*)P.filter;
+		uint32_t mn = 255;
 		list_for_each_hash<POW2>(P, w, [&](uint64_t slot) {
-			mem_atomic_min64(R + (slot & emask), tag);
+			uint32_t v = ld_cg(cnt + slot);
+			mn = v < mn ? v : mn;
 			return true;
 		});
-	} else {
-		bool own = true;
-		list_for_each_hash<POW2>(P, w, [&](uint64_t slot) {
-			own = ld_cg(R + (slot & emask)) == tag;
-			return own;
-		});
-		if (own) {
-			uint8_t* cnt = (uint8_t*)P.filter;
-			uint32_t mn = 255;
+		if (mn != 255)
 			list_for_each_hash<POW2>(P, w, [&](uint64_t slot) {
-				uint32_t v = ld_cg(cnt + slot);
-				mn = v < mn ? v : mn;
+				if (ld_cg(cnt + slot) == mn)
+					*(volatile uint8_t*)(cnt + slot) = (uint8_t)(mn + 1);
 				return true;
 			});
-			if (mn != 255)
-				list_for_each_hash<POW2>(P, w, [&](uint64_t slot) {
-					if (ld_cg(cnt + slot) == mn)
-						*(volatile uint8_t*)(cnt + slot) = (uint8_t)(mn + 1);
-					return true;
-				});
-		} else {
-			uint32_t o = mem_atomic_inc(L.count_out);
-			L.list_out[o] = w;
-		}
+		if (mn >= P.threshold && P.hit_bits)
+			mem_red_or(P.hit_bits + (w >> 5), 1u << (w & 31));
+	} else {
+		uint32_t* words = (uint32_t*)P.filter;
+		bool found = true;
+		list_for_each_hash<POW2>(P, w, [&](uint64_t n) {
+			uint32_t bit = 1u << (uint32_t)(n & 31);
+			found &= (mem_atomic_or(words + (n >> 5), bit) & bit) != 0;
+			return true;
+		});
+		if (found && P.hit_bits)
+			mem_red_or(P.hit_bits + (w >> 5), 1u << (w & 31));
 	}
+	return true;
 }
 
 } // namespace btl

@@ -15,7 +15,8 @@
  *     CountingBloomFilter.hpp:190-196            -> btlbf_contains_seqs / _dev
  *   - CountingBloomFilter<uint8_t>::minCount, CountingBloomFilter.hpp:53-64 -> btlbf_mincount_seqs
  *   - CountingBloomFilter<uint8_t>::incrementAll, :164-183                   -> btlbf_increment_all_seqs
- *   - BloomFilter::insertAndCheck, BloomFilter.hpp:200-214                   -> btlbf_insert_and_check_seqs
+ *   - BloomFilter::insertAndCheck, BloomFilter.hpp:200-214, and
+ *     CountingBloomFilter::insertAndCheck, CountingBloomFilter.hpp:206-214   -> btlbf_insert_and_check_seqs
  *   - ntHashIterator::operator* / stHashIterator::operator*, strandArray()
  *     (vendor/ntHashIterator.hpp:93-96, vendor/stHashIterator.hpp:94-104)    -> btlbf_hash_seqs
  *   - BloomFilter::getPop (BloomFilter.hpp:316-323), CountingBloomFilter::popCount /
@@ -75,7 +76,9 @@ int btlbf_ctx_sync(btlbf_ctx *ctx);
 /* number of kernels this context has launched so far (for accounting / tests) */
 int btlbf_ctx_launch_count(btlbf_ctx *ctx, uint64_t *count);
 /* tuning / debugging knobs: "force_generic" (1: byte-LUT hashing path for every tile),
- * "query_mode" (0: all probes in flight, 1: early-exit probing), "chunk_bases", "cbf_batch" */
+ * "query_mode" (0: all probes in flight, 1: early-exit probing), "chunk_bases" (windows per
+ * pipeline stage of the host-buffer calls), "cbf_batch" (windows per batch of the ordered updates),
+ * "resv_log2", "list_log2", "drain_threshold" (sizes of the ordered-update reservation tables) */
 int btlbf_ctx_set_option(btlbf_ctx *ctx, const char *key, int64_t value);
 
 /* ---- filters ---- */
@@ -110,8 +113,14 @@ int btlbf_filter_set_seeds(btlbf_filter *f, const char *const *seeds, unsigned n
  * array of the same size (a peer GPU's mapped memory is fine): the local step of the multi-GPU merge */
 int btlbf_filter_merge_from_device(btlbf_filter *f, const void *src_device, uint64_t nbytes);
 
+/* order-dependent updates (counting insert, insert_and_check): number of k-mers that had to wait for
+ * the index-ordered residual rounds, and the number of such rounds, since the filter was created */
+int btlbf_filter_ordered_stats(btlbf_filter *f, uint64_t *deferred, uint64_t *rounds);
+
 /* ---- batched sequence operations, HOST buffers (copies are inside the call) ---- */
-/* All outputs may be NULL when not wanted.  n_kmers = number of valid windows processed. */
+/* All outputs may be NULL when not wanted.  n_kmers = number of valid windows processed.
+ * insert_seqs on a COUNTING8 filter and insert_and_check_seqs reproduce the reference's
+ * single-threaded, read-order, position-order loop exactly (these updates are order-dependent). */
 int btlbf_insert_seqs(btlbf_filter *f, const char *bases, const uint64_t *offsets, uint64_t n_seqs,
                       uint64_t *n_kmers);
 int btlbf_contains_seqs(btlbf_filter *f, const char *bases, const uint64_t *offsets,
@@ -131,6 +140,28 @@ int btlbf_hash_seqs(btlbf_ctx *ctx, unsigned hash_num, unsigned kmer_size, const
                     unsigned n_seeds, unsigned h2, const char *bases, const uint64_t *offsets,
                     uint64_t n_seqs, uint64_t *hashes, uint8_t *strands, uint8_t *valid_bits,
                     uint64_t *n_kmers);
+
+/* ---- legacy per-k-mer interface: the caller supplies the hash_num precomputed hash values of each of
+ * n_kmers k-mers (hashes[i*hash_num + j]), exactly what the reference's insert/contains(const uint64_t[])
+ * take (BloomFilter.hpp:185-262, CountingBloomFilter.hpp:53-64,134-214).  Order-dependent updates
+ * (counting insert; insert with `found` requested) are applied one k-mer after the other. ---- */
+/* BLOOM: insert (found == NULL) or insertAndCheck (found[i] = 1 when every bit was already set);
+ * COUNTING8: incrementMin; found[i] = minCount >= threshold before the update (insertAndCheck) */
+int btlbf_insert_hashes(btlbf_filter *f, const uint64_t *hashes, uint64_t n_kmers, uint8_t *found);
+int btlbf_contains_hashes(btlbf_filter *f, const uint64_t *hashes, uint64_t n_kmers, uint8_t *hit);
+int btlbf_mincount_hashes(btlbf_filter *f, const uint64_t *hashes, uint64_t n_kmers, uint8_t *counts);
+int btlbf_increment_all_hashes(btlbf_filter *f, const uint64_t *hashes, uint64_t n_kmers);
+
+/* ---- file layout: "[BTLBloomFilter_v1]" / "[BTLCountingBloomFilter_v1]" TOML header, "[HeaderEnd]",
+ * raw array -- byte-identical to storeFilter (BloomFilter.hpp:264-314, CountingBloomFilter.hpp:331-379)
+ * and readable by loadFilter (BloomFilter.hpp:107-166, CountingBloomFilter.hpp:268-329).
+ * dFPR / nEntry / tEntry are the BloomFilter members of those names (ignored for COUNTING8). ---- */
+int btlbf_filter_store(btlbf_filter *f, const char *path, double dFPR, uint64_t nEntry, uint64_t tEntry);
+int btlbf_filter_load(btlbf_ctx *ctx, const char *path, int kind, unsigned threshold, btlbf_filter **filter,
+                      double *dFPR, uint64_t *nEntry, uint64_t *tEntry);
+/* the header text alone (no device needed); *len = strlen, buf may be NULL to query the length */
+int btlbf_format_header(int kind, uint64_t size, uint64_t size_bytes, unsigned hash_num, unsigned kmer_size,
+                        double dFPR, uint64_t nEntry, uint64_t tEntry, char *buf, size_t cap, size_t *len);
 
 /* ---- the same operations on DEVICE-resident batches (asynchronous on the context's stream) ---- */
 /* d_bases: n_bases bytes, 16-byte aligned; d_offsets: n_seqs+1 uint64; d_hit_bits / d_valid_bits:
