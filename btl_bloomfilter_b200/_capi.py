@@ -60,7 +60,7 @@ SIGNATURES = {
     "btlbf_contains_seqs_dev": [vp, vp, u64, vp, u64, vp, vp, vp],
     "btlbf_mincount_seqs_dev": [vp, vp, u64, vp, u64, vp, vp, vp],
     "btlbf_synth_genome_dev": [vp, vp, u64, u64, u64],
-    "btlbf_synth_reads_dev": [vp, vp, u64, u64, u32, u64, u64, u64],
+    "btlbf_synth_reads_dev": [vp, vp, u64, u64, u32, u64, u64, u64, u64],
     "btlbf_random_access_probe": [vp, vp, u64, u64, C.c_int, C.POINTER(C.c_float)],
 }
 

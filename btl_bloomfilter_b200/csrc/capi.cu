@@ -1055,14 +1055,15 @@ extern "C" int btlbf_synth_genome_dev(btlbf_ctx* ctx, void* d_out, uint64_t star
 }
 
 extern "C" int btlbf_synth_reads_dev(btlbf_ctx* ctx, void* d_out, uint64_t first_read, uint64_t n_reads,
-                                     unsigned read_len, uint64_t g_len, uint64_t genome_seed, uint64_t read_seed)
+                                     unsigned read_len, uint64_t g_start, uint64_t g_len, uint64_t genome_seed,
+                                     uint64_t read_seed)
 {
 	TRY(use(ctx));
 	if (n_reads && !d_out)
 		return fail(BTLBF_ERR_ARG, "null output");
 	if (read_len == 0 || g_len <= read_len)
 		return fail(BTLBF_ERR_ARG, "need 0 < read_len < g_len");
-	cudaError_t e = launch_synth_reads((uint8_t*)d_out, first_read, n_reads, read_len, g_len, genome_seed, read_seed,
+	cudaError_t e = launch_synth_reads((uint8_t*)d_out, first_read, n_reads, read_len, g_start, g_len, genome_seed, read_seed,
 	                                   ctx->active);
 	if (e != cudaSuccess)
 		return fail(BTLBF_ERR_CUDA, "synth_reads launch failed: %s", cudaGetErrorString(e));

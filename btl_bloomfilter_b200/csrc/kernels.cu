@@ -407,27 +407,27 @@ cudaError_t launch_synth_genome(uint8_t* out, uint64_t start, uint64_t n, uint64
 }
 
 __global__ void __launch_bounds__(256) synth_reads_kernel(uint8_t* out, uint64_t first_read, uint64_t n_reads,
-                                                          unsigned read_len, uint64_t g_len, uint64_t gseed,
-                                                          uint64_t rseed)
+                                                          unsigned read_len, uint64_t g_start, uint64_t g_len,
+                                                          uint64_t gseed, uint64_t rseed)
 {
 	uint64_t total = n_reads * read_len;
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
 		uint64_t r = i / read_len;
 		unsigned j = (unsigned)(i - r * read_len);
-		uint64_t st = splitmix64(rseed + first_read + r) % (g_len - read_len);
+		uint64_t st = g_start + splitmix64(rseed + first_read + r) % (g_len - read_len);
 		out[i] = "ACGT"[synth_code(st + j, gseed)];
 	}
 }
 
 cudaError_t launch_synth_reads(uint8_t* out, uint64_t first_read, uint64_t n_reads, unsigned read_len,
-                               uint64_t g_len, uint64_t gseed, uint64_t rseed, cudaStream_t stream)
+                               uint64_t g_start, uint64_t g_len, uint64_t gseed, uint64_t rseed, cudaStream_t stream)
 {
 	uint64_t total = n_reads * read_len;
 	if (total == 0)
 		return cudaSuccess;
 	uint64_t want = (total + 255) / 256;
 	unsigned grid = (unsigned)(want > 148 * 64 ? 148 * 64 : want);
-	synth_reads_kernel<<<grid, 256, 0, stream>>>(out, first_read, n_reads, read_len, g_len, gseed, rseed);
+	synth_reads_kernel<<<grid, 256, 0, stream>>>(out, first_read, n_reads, read_len, g_start, g_len, gseed, rseed);
 	return cudaGetLastError();
 }
 

@@ -103,8 +103,8 @@ cudaError_t launch_merge(void* dst, const void* src, uint64_t nbytes, int satura
 cudaError_t launch_synth_genome(uint8_t* out, uint64_t start, uint64_t n, uint64_t seed,
                                 cudaStream_t stream);
 cudaError_t launch_synth_reads(uint8_t* out, uint64_t first_read, uint64_t n_reads,
-                               unsigned read_len, uint64_t g_len, uint64_t gseed, uint64_t rseed,
-                               cudaStream_t stream);
+                               unsigned read_len, uint64_t g_start, uint64_t g_len, uint64_t gseed,
+                               uint64_t rseed, cudaStream_t stream);
 cudaError_t launch_random_probe(uint32_t* arr, uint64_t n_words, uint64_t n_access, int mode,
                                 unsigned long long* d_sink, cudaStream_t stream);
 

@@ -179,9 +179,11 @@ int btlbf_mincount_seqs_dev(btlbf_filter *f, const void *d_bases, uint64_t n_bas
 /* ---- synthetic inputs generated in HBM (bench / tests; replayable by the oracle) ---- */
 /* base(i) = "ACGT"[(splitmix64(seed ^ (i>>5)) >> 2*(i&31)) & 3] for i in [start, start+n) */
 int btlbf_synth_genome_dev(btlbf_ctx *ctx, void *d_out, uint64_t start, uint64_t n, uint64_t seed);
-/* read r = genome[s .. s+read_len) with s = splitmix64(read_seed + r) % (g_len - read_len) */
+/* read r (first_read <= r < first_read+n_reads) = genome[s .. s+read_len) with
+ * s = g_start + splitmix64(read_seed + r) % (g_len - read_len): reads sampled from the region
+ * [g_start, g_start+g_len) of the synthetic genome */
 int btlbf_synth_reads_dev(btlbf_ctx *ctx, void *d_out, uint64_t first_read, uint64_t n_reads,
-                          unsigned read_len, uint64_t g_len, uint64_t genome_seed,
+                          unsigned read_len, uint64_t g_start, uint64_t g_len, uint64_t genome_seed,
                           uint64_t read_seed);
 /* random-sector microbenchmark that establishes the measured roofline denominator:
  * mode 0: one 4-byte load per access, mode 1: one atomicOr per access, over a device array of

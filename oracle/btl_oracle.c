@@ -694,10 +694,10 @@ void ora_synth_genome(char *out, uint64_t start, uint64_t n, uint64_t seed)
 }
 
 void ora_synth_reads(char *out, uint64_t first_read, uint64_t n_reads, unsigned read_len,
-                     uint64_t g_len, uint64_t genome_seed, uint64_t read_seed)
+                     uint64_t g_start, uint64_t g_len, uint64_t genome_seed, uint64_t read_seed)
 {
 	for (uint64_t r = 0; r < n_reads; r++) {
-		uint64_t st = ora_splitmix64(read_seed + first_read + r) % (g_len - read_len);
+		uint64_t st = g_start + ora_splitmix64(read_seed + first_read + r) % (g_len - read_len);
 		for (unsigned j = 0; j < read_len; j++)
 			out[r * read_len + j] = synth_base(st + j, genome_seed);
 	}

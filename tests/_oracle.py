@@ -108,7 +108,7 @@ class Oracle:
         L.ora_cbf_header.restype = C.c_int
         L.ora_cbf_header.argtypes = [C.c_char_p, C.c_size_t, u64, u64, u32, u32, u32]
         L.ora_synth_genome.argtypes = [u8p, u64, u64, u64]
-        L.ora_synth_reads.argtypes = [u8p, u64, u64, u32, u64, u64, u64]
+        L.ora_synth_reads.argtypes = [u8p, u64, u64, u32, u64, u64, u64, u64]
         L.ora_bench_bf.restype = C.c_double
         L.ora_bench_bf.argtypes = [u8p, u64, u32, u32, u8p, u64p, u64, C.c_int, C.c_int, u64p, u64p]
         L.ora_max_threads.restype = C.c_int
@@ -235,9 +235,9 @@ class Oracle:
         self.L.ora_synth_genome(_p8(out), start, n, seed)
         return out
 
-    def synth_reads(self, first, n_reads, read_len, g_len, gseed, rseed):
+    def synth_reads(self, first, n_reads, read_len, g_len, gseed, rseed, g_start=0):
         out = np.empty(n_reads * read_len, np.uint8)
-        self.L.ora_synth_reads(_p8(out), first, n_reads, read_len, g_len, gseed, rseed)
+        self.L.ora_synth_reads(_p8(out), first, n_reads, read_len, g_start, g_len, gseed, rseed)
         return out
 
 

@@ -1,0 +1,308 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libbtlbf_cuda.so via the Python host
+classes), against the oracle on the same seeded inputs and against the golden vectors generated from the
+reference.  Bit-exact.  Needs a B200."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import _oracle as O
+import parity_suite as S
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from _backends import GpuBackend
+    return GpuBackend()
+
+
+@pytest.fixture(scope="module")
+def gpu_small():
+    from _backends import GpuBackend
+    return GpuBackend(chunk=4096, batch=4096, resv_log2=10, list_log2=6, drain_threshold=16)
+
+
+def test_library_loaded_is_in_tree():
+    import btl_bloomfilter_b200 as B
+    L = B.lib()
+    assert L.btlbf_version() >= 100
+    assert os.path.dirname(B._build.LIB).endswith("btl_bloomfilter_b200")
+
+
+def test_golden_hashes(gpu, golden):
+    S.check_golden_hashes(gpu, golden)
+
+
+def test_golden_hashes_generic_path(golden):
+    from _backends import GpuBackend
+    S.check_golden_hashes(GpuBackend(force_generic=1), golden)
+
+
+def test_golden_bf(gpu, golden):
+    S.check_golden_bf(gpu, golden)
+
+
+def test_golden_bf_early_exit_mode(golden):
+    from _backends import GpuBackend
+    S.check_golden_bf(GpuBackend(query_mode=1), golden)
+
+
+def test_golden_cbf(gpu, golden):
+    S.check_golden_cbf(gpu, golden)
+
+
+def test_golden_small_tables(gpu_small, golden):
+    S.check_golden_cbf(gpu_small, golden)
+    S.check_golden_bf(gpu_small, golden)
+
+
+@pytest.mark.parametrize("k,h", [(1, 1), (2, 3), (4, 5), (25, 4), (31, 2), (32, 6), (33, 3), (64, 4), (100, 2)])
+def test_random_hashes(gpu, oracle, k, h):
+    S.check_random_hashes(gpu, oracle, k, h, seed=1000 * k + h)
+
+
+def test_random_hashes_exotic_bytes(gpu, oracle):
+    S.check_random_hashes(gpu, oracle, 5, 3, seed=77, exotic=0.05)
+    S.check_random_hashes(gpu, oracle, 25, 4, seed=78, exotic=0.01)
+
+
+def test_random_hashes_multi_tile(gpu_small, oracle):
+    S.check_random_hashes(gpu_small, oracle, 25, 4, seed=5, n_seqs=120, max_len=400)
+    S.check_random_hashes(gpu_small, oracle, 64, 2, seed=6, n_seqs=3, max_len=9000)
+
+
+@pytest.mark.parametrize("k,n_seeds,h2", [(5, 2, 2), (31, 2, 1), (16, 3, 3), (40, 1, 4)])
+def test_random_spaced(gpu, oracle, k, n_seeds, h2):
+    S.check_random_spaced(gpu, oracle, k, n_seeds, h2, seed=k)
+
+
+@pytest.mark.parametrize("k,h,bits", [(25, 4, 1 << 16), (32, 6, 8 * 1237), (4, 5, 1024), (21, 3, 8 * 4099)])
+def test_random_bf(gpu, oracle, k, h, bits):
+    S.check_random_bf(gpu, oracle, k, h, bits, seed=bits + k)
+
+
+def test_random_bf_multi_chunk(gpu_small, oracle):
+    S.check_random_bf(gpu_small, oracle, 25, 4, 8 * 3001, seed=11, n_seqs=100, max_len=300)
+
+
+@pytest.mark.parametrize("k,h,m", [(25, 4, 4096), (8, 5, 100008), (5, 3, 64), (11, 4, 512)])
+def test_random_cbf(gpu, oracle, k, h, m):
+    S.check_random_cbf(gpu, oracle, k, h, m, seed=m + k)
+
+
+def test_random_cbf_small_tables(gpu_small, oracle):
+    S.check_random_cbf(gpu_small, oracle, 9, 4, 256, seed=1, n_seqs=80, max_len=200)
+    f = gpu_small.filter(1, 64, 3, 5)
+    f.insert(["ACGTA" * 40] * 8)
+    d, r = f.ordered_stats()
+    assert d > 0 and r > 1
+
+
+def test_edge_cases(gpu, oracle):
+    S.check_edge_cases(gpu, oracle)
+
+
+def test_cfg1(gpu, oracle, golden):
+    S.check_cfg1(gpu, oracle, golden)
+
+
+# ---------------------------------------------------------------- larger seeded runs against the oracle
+def test_counting_build_200k(gpu, oracle):
+    """CountingBloomFilter<uint8_t> build at a size where thousands of k-mers collide inside a batch:
+    counter values must equal the single-threaded reference-order result."""
+    g = oracle.synth_genome(0, 200_000, 42)
+    reads = oracle.synth_reads(0, 1500, 150, g.size, 42, 9)  # overlapping reads: repeated k-mers
+    b = np.concatenate([g, reads])
+    off = np.concatenate([[0, g.size], g.size + 150 * np.arange(1, 1501)]).astype(np.uint64)
+    m = 400_000
+    f = gpu.filter(1, m, 4, 25, thr=2)
+    cnt = np.zeros(m, np.uint8)
+    assert f.insert((b, off)) == oracle.cbf_insert_seqs(cnt, m, 4, 25, b, off)
+    assert np.array_equal(f.bytes(), cnt)
+    e = oracle.cbf_contains_seqs(cnt, m, 4, 25, 2, reads, (150 * np.arange(1501)).astype(np.uint64))
+    gq = f.contains((reads, (150 * np.arange(1501)).astype(np.uint64)))
+    assert e[:2] == gq[:2] and np.array_equal(e[2], gq[2])
+
+
+def test_bf_non_pow2_large_modulus(gpu, oracle):
+    """cfg2's filter size (31,568,113,856 bits) is not a power of two: the exact 64-bit modulo must agree.
+    Only the touched words are compared (the oracle cannot hold 4 GB cheaply): query parity + popcount."""
+    bits = 31_568_113_856
+    g = oracle.synth_genome(0, 300_000, 42)
+    off = np.array([0, g.size], np.uint64)
+    f = gpu.filter(0, bits, 4, 25)
+    n = f.insert((g, off))
+    assert n == g.size - 24
+    # expected set of bit indices from the oracle's hashes
+    _, hs, _ = oracle.hash_seqs(4, 25, g, off)
+    idx = np.unique(hs[: g.size - 24].reshape(-1) % np.uint64(bits))
+    assert f.f.getPop() == idx.size
+    nq, nh, hits, valid = f.contains((g, off))
+    assert nq == nh == g.size - 24
+    miss = oracle.synth_genome(0, 100_000, 43 << 40)
+    nq, nh, hits, _ = f.contains((miss, np.array([0, miss.size], np.uint64)))
+    _, mh, _ = oracle.hash_seqs(4, 25, miss, np.array([0, miss.size], np.uint64))
+    exp = np.isin(mh[: miss.size - 24] % np.uint64(bits), idx).all(axis=1)
+    assert nh == int(exp.sum())
+    assert np.array_equal(O.bits_to_bool(hits, miss.size)[: miss.size - 24], exp)
+
+
+def test_full_size_properties(gpu, oracle):
+    """Size-independent properties at a BASELINE-scale shape (4 GiB filter, 150 bp reads, k=32, h=6):
+    inserted => contained; insert is idempotent (popcount unchanged by re-inserting); the count of
+    valid k-mers equals reads * (150 - 32 + 1); hits on an unrelated sequence match a popcount-based FPR."""
+    import btl_bloomfilter_b200 as B
+    bits = 1 << 35
+    f = B.BloomFilter(bits, 6, 32, ctx=gpu.ctx)
+    reads = oracle.synth_reads(0, 20000, 150, 3_000_000_000, 42, 1)
+    off = (150 * np.arange(20001)).astype(np.uint64)
+    n = f.insertSeqs((reads, off))
+    assert n == 20000 * 119
+    pop = f.getPop()
+    assert 0 < pop <= 6 * n
+    r = f.containsSeqs((reads, off))
+    assert r.n_kmers == n and r.n_hits == n
+    assert f.insertSeqs((reads, off)) == n and f.getPop() == pop
+    miss = oracle.synth_genome(0, 1_000_000, 43 << 40)
+    r = f.containsSeqs((miss, np.array([0, miss.size], np.uint64)))
+    assert r.n_hits <= 2  # occupancy ~3e-4 -> FPR ~1e-21
+    del f
+
+
+# ---------------------------------------------------------------- file layout, both directions
+def test_store_files_match_reference_bytes(gpu, golden, tmp_path):
+    import btl_bloomfilter_b200 as B
+    for i, c in enumerate(golden["bf_cases"]):
+        f = B.BloomFilter(c["bits"], c["h"], c["k"], ctx=gpu.ctx)
+        f.insertSeqs(c["seqs"])
+        p = tmp_path / ("bf%d.bf" % i)
+        f.storeFilter(str(p))
+        raw = p.read_bytes()
+        assert hashlib.md5(raw).hexdigest() == c["file_md5"]
+        assert raw.startswith(c["header"].encode())
+        g = B.BloomFilter(str(p), ctx=gpu.ctx)
+        assert (g.getFilterSize(), g.getHashNum(), g.getKmerSize()) == (c["bits"], c["h"], c["k"])
+        assert g.to_numpy().tobytes().hex() == c["filter_hex"]
+        assert g.getPop() == c["pop"]
+    for i, c in enumerate(golden["cbf_cases"]):
+        f = B.CountingBloomFilter(c["size"], c["h"], c["k"], c["threshold"], ctx=gpu.ctx)
+        assert f.size() == c["size_rounded"] == f.sizeInBytes()
+        f.insertSeqs(c["seqs"])
+        p = tmp_path / ("cbf%d.bf" % i)
+        f.storeFilter(str(p))
+        assert hashlib.md5(p.read_bytes()).hexdigest() == c["file_md5"]
+        g = B.CountingBloomFilter(str(p), c["threshold"], ctx=gpu.ctx)
+        assert g.popCount() == c["popcount"] and g.filtered_popcount() == c["filtered_popcount"]
+
+
+def test_files_interoperate_with_reference(gpu, ref, oracle, tmp_path):
+    """GPU-written file loaded by the reference, reference-written file loaded by the GPU class."""
+    import btl_bloomfilter_b200 as B
+    rng = np.random.default_rng(8)
+    b, off = S.rand_batch(rng, 30, 200)
+    f = B.BloomFilter(8 * 5000, 4, 25, ctx=gpu.ctx)
+    f.setnEntry(123)
+    f.settEntry(456)
+    f.insertSeqs((b, off))
+    p = str(tmp_path / "gpu.bf")
+    f.storeFilter(p)
+    rf = ref.L.ref_bf_load(p.encode())
+    assert np.array_equal(ref.bf_bytes(rf), f.to_numpy())
+    ne, te = O.u64(), O.u64()
+    ref.L.ref_bf_get_meta(rf, O.C.byref(ne), O.C.byref(te))
+    assert (ne.value, te.value) == (123, 456)
+    p2 = str(tmp_path / "ref.bf")
+    ref.L.ref_bf_set_meta(rf, 0.015625, 7, 9)
+    ref.L.ref_bf_store(rf, p2.encode())
+    g = B.BloomFilter(p2, ctx=gpu.ctx)
+    assert np.array_equal(g.to_numpy(), f.to_numpy())
+    assert (g.m_dFPR, g.getnEntry(), g.gettEntry()) == (0.015625, 7, 9)
+    g.storeFilter(str(tmp_path / "again.bf"))
+    assert open(p2, "rb").read() == open(str(tmp_path / "again.bf"), "rb").read()
+    ref.L.ref_bf_free(rf)
+    # counting
+    cf = B.CountingBloomFilter(3001, 3, 17, 2, ctx=gpu.ctx)
+    cf.insertSeqs((b, off))
+    p3 = str(tmp_path / "gpu.cbf")
+    cf.storeFilter(p3)
+    rc = ref.L.ref_cbf_load(p3.encode(), 2)
+    assert np.array_equal(ref.cbf_bytes(rc), cf.to_numpy())
+    p4 = str(tmp_path / "ref.cbf")
+    ref.L.ref_cbf_store(rc, p4.encode())
+    assert open(p3, "rb").read() == open(p4, "rb").read()
+    ref.L.ref_cbf_free(rc)
+
+
+# ---------------------------------------------------------------- legacy per-k-mer interface (reference unit tests)
+def test_reference_unit_scenario_bloom(gpu, oracle, tmp_path):
+    """Tests/Unit/BloomFilterTests.cpp:53-146 against the GPU class: 1 Gbit filter, h=5, k=4, "ACGTAC"."""
+    import btl_bloomfilter_b200 as B
+    filterSize, numHashes, k = 1000000000, 5, 4
+    f = B.BloomFilter(filterSize, numHashes, k, ctx=gpu.ctx)
+    seq = "ACGTAC"
+    b, off = O.as_batch([seq])
+    _, hs, _ = oracle.hash_seqs(numHashes, k, b, off)
+    for p in range(3):
+        f.insert(hs[p])
+    for p in range(3):
+        assert f.contains(hs[p])
+    assert f.getPop() == len(np.unique(hs[:3].reshape(-1) % np.uint64(filterSize)))
+    p = str(tmp_path / "unit.bf")
+    f.storeFilter(p)
+    raw = open(p, "rb").read()
+    end = raw.index(b"[HeaderEnd]\n") + len(b"[HeaderEnd]\n")
+    assert len(raw) - end == f.sizeInBytes() == filterSize // 8
+    g = B.BloomFilter(p, ctx=gpu.ctx)
+    for q in range(3):
+        assert g.contains(hs[q])
+    assert g.insertAndCheck(hs[0]) is True
+    assert g.insertAndCheck(np.array([1, 2, 3, 4, 5], np.uint64)) is False
+    assert g.insertAndCheck(np.array([1, 2, 3, 4, 5], np.uint64)) is True
+
+
+def test_reference_unit_scenario_counting(gpu, oracle, tmp_path):
+    """Tests/Unit/CountingBloomFilterTests.cpp:54-246 for uint8_t: 100001 bytes (-> 100008), h=5, k=8."""
+    import btl_bloomfilter_b200 as B
+    f = B.CountingBloomFilter(100001, 5, 8, 1, ctx=gpu.ctx)
+    assert f.size() == f.sizeInBytes() == 100008
+    seq = "ACGTACACTGGACTGAGTCT"
+    b, off = O.as_batch([seq])
+    n, hs, _ = oracle.hash_seqs(5, 8, b, off)
+    for p in range(n):
+        f.insert(hs[p])
+    for p in range(n):
+        assert f.contains(hs[p])
+    rng = np.random.default_rng(0)
+    rb, ro = O.as_batch(["".join(rng.choice(list("ACGT"), size=60).tolist())])
+    rn, rh, _ = oracle.hash_seqs(5, 8, rb, ro)
+    cnt = np.zeros(100008, np.uint8)
+    oracle.cbf_insert_seqs(cnt, 100008, 5, 8, b, off)
+    assert np.array_equal(f.to_numpy(), cnt)
+    exp = np.array([cnt[rh[p] % np.uint64(100008)].min() >= 1 for p in range(rn)])
+    assert np.array_equal(f.contains(rh[:rn]), exp)
+    assert np.array_equal(f.minCount(hs[:n]), np.array([cnt[hs[p] % np.uint64(100008)].min() for p in range(n)]))
+    p = str(tmp_path / "unit.cbf")
+    f.storeFilter(p)
+    g = B.CountingBloomFilter(p, 1, ctx=gpu.ctx)
+    assert g.size() == g.sizeInBytes() == 100008 and np.array_equal(g.to_numpy(), cnt)
+    # incrementAll + saturation
+    h0 = hs[:1]
+    for _ in range(300):
+        g.incrementAll(h0)
+    assert g.minCount(h0[0]) == 255
+
+
+def test_errors_are_reported_not_fatal(gpu):
+    import btl_bloomfilter_b200 as B
+    with pytest.raises(ValueError):
+        B.BloomFilter(1001, 4, 5, ctx=gpu.ctx)  # "Filter Size ... is not a multiple of 8"
+    with pytest.raises(B.BtlbfError):
+        B.BloomFilter("/nonexistent/file.bf", ctx=gpu.ctx)
+    f = B.BloomFilter(1024, 4, 5, ctx=gpu.ctx)
+    with pytest.raises(B.BtlbfError):
+        f.setSeeds(["11011", "1101"], 2)  # wrong seed length
+    with pytest.raises(B.BtlbfError):
+        f.setSeeds(["11011"], 2)  # hashNum != n_seeds*h2
