@@ -1,0 +1,391 @@
+#!/usr/bin/env python3
+"""bench.py -- k-mer insert + query throughput of the BloomFilter hot path on B200.
+
+Workload (BASELINE.json configs[1], "cfg2"): 3 Gbp synthetic genome, k=25, 4 hashes, 31,568,113,856-bit
+filter (the reference's calcOptimalSize(3e9, 0.01), 3.95 GB), built in chunks, then 150 bp read queries.
+One STEP = one pass of the hot path over one batch: insert one 64 Mi-window genome chunk into the filter
+and query one batch of 150 bp reads sampled from that chunk (all k-mers present: no early exit).
+
+  value     whole-job Gk-mer/s (inserted + queried) with the batches already resident in HBM
+            (btlbf_insert_seqs_dev / btlbf_contains_seqs_dev), CUDA events, max over ranks
+  e2e       the same steps through the host-buffer C-ABI calls (btlbf_insert_seqs / btlbf_contains_seqs):
+            pinned host inputs, H2D + kernels + D2H of the hit bits inside the timed region
+  roofline  the dominant kernel (bf_insert): (64*h + 1) algorithmic bytes per k-mer / its mean launch
+            duration (CUDA events inside the timed region) against the measured HBM copy bandwidth
+  cpu_baseline  the reference's own CPU path (oracle/_ref: unmodified headers, OpenMP over reads / chunks)
+            on a bounded sample of the same workload, same filter size, on this box's host cores
+
+`--impl reference` times only that CPU path, K bounded-sample steps.  N > 1 (torchrun): one rank per GPU,
+units (genome chunks / read batches) sharded across ranks, no data-path collective ("weak" scaling);
+the partial filters are merged afterwards (all-to-all of 1/N slices + OR + all-gather) and that merge
+is timed and reported separately under "merge".
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+G_LEN = 3_000_000_000
+K, H = 25, 4
+FILTER_BITS = 31_568_113_856  # BloomFilter::calcOptimalSize(3e9, 0.01) with 4 hashes (BloomFilter.hpp:406-413)
+CHUNK = 64 << 20              # windows per insert launch
+READ_LEN = 150
+GENOME_SEED, READ_SEED = 42, 7
+WORKLOAD = "cfg2: 3 Gbp synthetic genome build (k=25, h=4, 31.57 Gbit filter) + 150 bp read query"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------- CPU reference arm
+def cpu_reference_run(n_steps, warmup, sample_bases, threads=0, verbose=False):
+    """The reference's CPU path on a bounded sample per step: insert `sample_bases` of the genome
+    (64 kb pieces, OpenMP over pieces) + query sample_bases/150 reads sampled from it."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle as O
+    orc = O.Oracle()
+    use_ref = O.Ref.available()
+    piece = 65536
+    if use_ref:
+        R = O.Ref()
+        cores = R.L.ref_max_threads()
+        filt = R.bf_new(FILTER_BITS, H, K)
+    else:
+        cores = orc.L.ora_max_threads()
+        filt = np.zeros(FILTER_BITS // 8, np.uint8)
+    threads = threads or cores
+    n_reads = sample_bases // READ_LEN
+    roff = (READ_LEN * np.arange(n_reads + 1)).astype(np.uint64)
+    tot_k, tot_t, per = 0, 0.0, []
+    for s in range(warmup + n_steps):
+        g0 = (s * sample_bases) % (G_LEN - sample_bases - K)
+        g = orc.synth_genome(g0, sample_bases + K - 1, GENOME_SEED)
+        # 64 kb pieces overlapping by k-1 so that every window is inserted exactly once
+        starts = np.arange(0, sample_bases, piece, dtype=np.uint64)
+        pieces = [g[int(a): int(min(a + piece + K - 1, g.size))] for a in starts]
+        pb = np.concatenate(pieces)
+        poff = np.concatenate([[0], np.cumsum([p.size for p in pieces])]).astype(np.uint64)
+        reads = orc.synth_reads(0, n_reads, READ_LEN, sample_bases, GENOME_SEED, READ_SEED + s, g_start=g0)
+        nk, nh = O.u64(), O.u64()
+        if use_ref:
+            t_i = R.L.ref_bench_bf(filt, O._p8(pb), O._p64(poff), poff.size - 1, 1, threads, C.byref(nk), C.byref(nh))
+            k_i = nk.value
+            t_q = R.L.ref_bench_bf(filt, O._p8(reads), O._p64(roff), n_reads, 0, threads, C.byref(nk), C.byref(nh))
+        else:
+            t_i = orc.L.ora_bench_bf(O._p8(filt), FILTER_BITS, H, K, O._p8(pb), O._p64(poff), poff.size - 1, 1, threads,
+                                     C.byref(nk), C.byref(nh))
+            k_i = nk.value
+            t_q = orc.L.ora_bench_bf(O._p8(filt), FILTER_BITS, H, K, O._p8(reads), O._p64(roff), n_reads, 0, threads,
+                                     C.byref(nk), C.byref(nh))
+        k_q = nk.value
+        assert nh.value == k_q, "CPU reference: a k-mer of an inserted region was not found"
+        if s >= warmup:
+            tot_k += k_i + k_q
+            tot_t += t_i + t_q
+            per.append((k_i / t_i, k_q / t_q))
+        if verbose:
+            print("cpu step %d: insert %.2f Mk/s, query %.2f Mk/s" % (s, k_i / t_i / 1e6, k_q / t_q / 1e6), file=sys.stderr)
+    if use_ref:
+        R.L.ref_bf_free(filt)
+    return {"value": tot_k / tot_t / 1e9, "unit": "Gk-mer/s", "cores": int(threads),
+            "kind": "reference" if use_ref else "port",
+            "sample": "%d steps x (%d bp genome insert in 64 kb pieces + %d reads x %d bp query), %d-bit filter, "
+                      "OpenMP over pieces/reads" % (n_steps, sample_bases, n_reads, READ_LEN, FILTER_BITS),
+            "insert_gkmers_s": float(np.mean([p[0] for p in per])) / 1e9,
+            "query_gkmers_s": float(np.mean([p[1] for p in per])) / 1e9,
+            "ms_per_step": tot_t / n_steps * 1e3, "kmers_per_step": tot_k / n_steps}
+
+
+# ---------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=42)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=8 << 20, help="bases per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--chunk", type=int, default=CHUNK)
+    ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity (0: leave as is)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": WORKLOAD, "k": K, "hashes": H, "filter_bits": FILTER_BITS, "genome_bp": G_LEN,
+              "read_len": READ_LEN, "chunk_windows": args.chunk,
+              "l2": "inputs larger than L2 (64 MiB per batch, 3.95 GB filter); no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, args.steps)
+        r = cpu_reference_run(steps, min(args.warmup, 1), args.cpu_sample)
+        line = {"impl": "reference", "metric": "k-mers/s inserted+queried", "value": r["value"], "unit": "Gk-mer/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": config, "cpu_baseline": r,
+                "e2e": {"value": r["value"], "unit": "Gk-mer/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import btl_bloomfilter_b200 as B
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = B.Context(local_rank)
+    # the library's kernels run on torch's current stream so that torch.cuda.Event brackets them
+    # (a non-default stream: the C ABI treats a NULL stream as "use the context's own")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    if args.l2_fetch:
+        ctx.set_option("l2_fetch_granularity", args.l2_fetch)
+
+    chunk = args.chunk // 4096 * 4096
+    n_chunks = (G_LEN + chunk - 1) // chunk
+    W, S = args.warmup, args.steps
+    n_reads = chunk // READ_LEN
+    read_bases = n_reads * READ_LEN
+    filt = B.BloomFilter(FILTER_BITS, H, K, ctx=ctx)
+
+    # ---- synthetic inputs generated in HBM (replayable by the oracle: tests/test_gpu_parity.py)
+    n_buf = min(W + S, n_chunks)
+    d_genome, d_reads, g_lens = [], [], []
+    for i in range(n_buf):
+        c = (i * world + rank) % n_chunks
+        g0 = c * chunk
+        glen = min(chunk + K - 1, G_LEN - g0)
+        tg = torch.empty(chunk + 64, dtype=torch.uint8, device=dev)
+        ctx.synth_genome_device(tg.data_ptr(), g0, glen, GENOME_SEED)
+        tr = torch.empty(read_bases + 64, dtype=torch.uint8, device=dev)
+        ctx.synth_reads_device(tr.data_ptr(), 0, n_reads, READ_LEN, g0, glen, GENOME_SEED, READ_SEED + c)
+        d_genome.append(tg)
+        d_reads.append(tr)
+        g_lens.append(glen)
+    d_goff = [torch.tensor([0, gl], dtype=torch.int64, device=dev) for gl in sorted(set(g_lens))]
+    goff_of = {int(t[1]): t for t in d_goff}
+    d_roff = torch.arange(0, read_bases + 1, READ_LEN, dtype=torch.int64, device=dev)
+    d_hits = torch.zeros((read_bases + 31) // 32 + 8, dtype=torch.int32, device=dev)
+    d_stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+
+    def step_dev(i, evs=None):
+        j = i % n_buf
+        if evs:
+            evs[0].record(stream)
+        filt.insertSeqsDevice(d_genome[j].data_ptr(), g_lens[j], goff_of[g_lens[j]].data_ptr(), 1, d_stats.data_ptr())
+        if evs:
+            evs[1].record(stream)
+        filt.containsSeqsDevice(d_reads[j].data_ptr(), read_bases, d_roff.data_ptr(), n_reads, d_hits.data_ptr(), 0,
+                                d_stats[2:].data_ptr())
+        if evs:
+            evs[2].record(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for i in range(W):
+        step_dev(i)
+    torch.cuda.synchronize()
+    d_stats.zero_()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(S)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    barrier()
+    torch.cuda.synchronize()
+    t_start.record(stream)
+    for i in range(S):
+        step_dev(W + i, evs[i])
+    t_end.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = t_start.elapsed_time(t_end)
+    ms_insert = sum(e[0].elapsed_time(e[1]) for e in evs)
+    ms_query = sum(e[1].elapsed_time(e[2]) for e in evs)
+    st = d_stats.cpu().numpy()
+    k_ins, k_qry, k_hit = int(st[0]), int(st[2]), int(st[3])
+    assert k_hit == k_qry, "a k-mer of an inserted chunk was not found (%d of %d)" % (k_hit, k_qry)
+
+    # ---- end to end through the host-buffer C ABI (pinned inputs; H2D, kernels and D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        n_host = min(n_buf, 4)
+        h_genome = [torch.empty(g_lens[j], dtype=torch.uint8).pin_memory() for j in range(n_host)]
+        h_reads = [torch.empty(read_bases, dtype=torch.uint8).pin_memory() for _ in range(n_host)]
+        for j in range(n_host):
+            h_genome[j].copy_(d_genome[j][: g_lens[j]])
+            h_reads[j].copy_(d_reads[j][:read_bases])
+        h_hits = torch.zeros((read_bases + 31) // 32 * 4, dtype=torch.uint8).pin_memory()
+        h_roff = np.arange(0, read_bases + 1, READ_LEN, dtype=np.uint64)
+        torch.cuda.synchronize()
+
+        def step_host(i):
+            j = i % n_host
+            gl = g_lens[j]
+            a = filt.insertSeqs((h_genome[j].numpy(), np.array([0, gl], np.uint64)))
+            r = filt.containsSeqs((h_reads[j].numpy(), h_roff), hit_out=h_hits.numpy(), want_valid=False)
+            return a, r.n_kmers, r.n_hits
+
+        for i in range(min(W, 2)):
+            step_host(i)
+        S2 = min(S, 12)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ke = 0
+        for i in range(S2):
+            a, q, hq = step_host(i)
+            assert hq == q
+            ke += a + q
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        e2e = {"kmers": ke, "seconds": dt, "steps": S2,
+               "h2d": int(np.mean(g_lens[:n_host])) + read_bases + (n_reads + 1) * 8 + 16,
+               "d2h": int(h_hits.numel()) + 32}
+
+    # ---- reductions over ranks (max time, summed work)
+    if world > 1:
+        t = torch.tensor([ms_total, ms_insert, ms_query, e2e["seconds"] if e2e else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_insert, ms_query = float(t[0]), float(t[1]), float(t[2])
+        w = torch.tensor([k_ins, k_qry, e2e["kmers"] if e2e else 0, launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        k_ins_all, k_qry_all, ke_all, launches_all = [int(x) for x in w]
+        if e2e:
+            e2e["seconds"] = float(t[3])
+            e2e["kmers"] = ke_all
+    else:
+        k_ins_all, k_qry_all, launches_all = k_ins, k_qry, launches
+
+    merge = None
+    if world > 1:
+        from btl_bloomfilter_b200 import parallel
+        merge = parallel.bench_merge(filt, ctx, dev)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    # roofline of the dominant kernel (bf_insert), per rank: algorithmic bytes = 64 B per hash (32 B sector
+    # read + 32 B dirty write-back) + 1 input byte per k-mer
+    ins_bytes = (64 * H + 1) * (k_ins / S)
+    ins_ms = ms_insert / S
+    qry_bytes = (32 * H + 1) * (k_qry / S)
+    qry_ms = ms_query / S
+    roof = {"bound": "hbm", "kernel": "seq_kernel<OP_BF_INSERT>", "achieved": ins_bytes / (ins_ms * 1e-3) / 1e9,
+            "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None,
+            "bytes_per_kmer": 64 * H + 1, "kmers_per_launch": k_ins / S, "launch_ms": ins_ms,
+            "gkmers_s": k_ins / S / (ins_ms * 1e-3) / 1e9}
+    roof["frac"] = roof["achieved"] / peak
+    roof_q = {"bound": "hbm", "kernel": "seq_kernel<OP_BF_CONTAINS>", "achieved": qry_bytes / (qry_ms * 1e-3) / 1e9,
+              "peak": peak, "unit": "GB/s", "bytes_per_kmer": 32 * H + 1, "kmers_per_launch": k_qry / S,
+              "launch_ms": qry_ms, "gkmers_s": k_qry / S / (qry_ms * 1e-3) / 1e9}
+    roof_q["frac"] = roof_q["achieved"] / peak
+    prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(prof):
+        try:
+            t = json.load(open(prof))
+            roof["traffic"] = t.get("bf_insert_dram_bytes_per_launch")
+            roof_q["traffic"] = t.get("bf_contains_dram_bytes_per_launch")
+        except Exception:
+            pass
+    line = {"metric": "k-mers/s inserted+queried", "value": (k_ins_all + k_qry_all) / (ms_total * 1e-3) / 1e9,
+            "unit": "Gk-mer/s", "n_gpus": world, "steps": S, "warmup": W, "ms_per_step": ms_total / S,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": config, "insert_gkmers_s": k_ins_all / (ms_insert * 1e-3) / 1e9,
+            "query_gkmers_s": k_qry_all / (ms_query * 1e-3) / 1e9, "kmers_per_step": (k_ins_all + k_qry_all) / S,
+            "roofline": roof, "roofline_query": roof_q, "gpu_launches": launches_all, "clocks": clocks}
+    if e2e:
+        line["e2e"] = {"value": e2e["kmers"] / e2e["seconds"] / 1e9, "unit": "Gk-mer/s", "steps": e2e["steps"],
+                       "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"]}
+    if merge:
+        line["merge"] = merge
+    if world == 1 and not args.no_cpu_baseline:
+        cb = cpu_reference_run(2, 1, args.cpu_sample)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "insert_gkmers_s",
+                                                   "query_gkmers_s")}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

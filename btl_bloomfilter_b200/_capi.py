@@ -41,6 +41,7 @@ SIGNATURES = {
     "btlbf_filter_count_ge": [vp, u32, u64p],
     "btlbf_filter_set_seeds": [vp, cpp, u32, u32],
     "btlbf_filter_merge_from_device": [vp, vp, u64],
+    "btlbf_merge_device_buffers": [vp, C.c_int, vp, vp, u64],
     "btlbf_filter_ordered_stats": [vp, u64p, u64p],
     "btlbf_insert_seqs": [vp, vp, u64p, u64, u64p],
     "btlbf_contains_seqs": [vp, vp, u64p, u64, vp, vp, u64p, u64p],

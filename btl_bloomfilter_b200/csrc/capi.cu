@@ -330,6 +330,13 @@ extern "C" int btlbf_ctx_set_option(btlbf_ctx* ctx, const char* key, int64_t val
 		if (value < 6 || value > 28)
 			return fail(BTLBF_ERR_ARG, "list_log2 out of range");
 		ctx->list_log2 = value;
+	} else if (k == "l2_fetch_granularity") {
+		// device-wide hint: bytes fetched from HBM per L2 sector miss (32, 64 or 128).  Random 32-byte
+		// sector probes waste bandwidth at the larger settings.
+		if (value != 32 && value != 64 && value != 128)
+			return fail(BTLBF_ERR_ARG, "l2_fetch_granularity must be 32, 64 or 128");
+		TRY(use(ctx));
+		CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
 	} else if (k == "drain_threshold") {
 		if (value < 0)
 			return fail(BTLBF_ERR_ARG, "drain_threshold out of range");
@@ -570,6 +577,23 @@ extern "C" int btlbf_filter_merge_from_device(btlbf_filter* f, const void* src_d
 	if (e != cudaSuccess)
 		return fail(BTLBF_ERR_CUDA, "merge launch failed: %s", cudaGetErrorString(e));
 	f->ctx->launches++;
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_merge_device_buffers(btlbf_ctx* ctx, int kind, void* dst_device, const void* src_device,
+                                          uint64_t nbytes)
+{
+	TRY(use(ctx));
+	if (kind != BTLBF_BLOOM && kind != BTLBF_COUNTING8)
+		return fail(BTLBF_ERR_ARG, "unknown filter kind %d", kind);
+	if (!dst_device || !src_device)
+		return fail(BTLBF_ERR_ARG, "null argument");
+	if (((uintptr_t)dst_device | (uintptr_t)src_device) & 15u)
+		return fail(BTLBF_ERR_ARG, "merge buffers must be 16-byte aligned");
+	cudaError_t e = launch_merge(dst_device, src_device, nbytes, kind == BTLBF_COUNTING8, ctx->active);
+	if (e != cudaSuccess)
+		return fail(BTLBF_ERR_CUDA, "merge launch failed: %s", cudaGetErrorString(e));
+	ctx->launches++;
 	return BTLBF_OK;
 }
 

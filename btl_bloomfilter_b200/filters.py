@@ -117,6 +117,18 @@ class Context:
         check(self.L.btlbf_ctx_launch_count(self.handle, C.byref(n)))
         return n.value
 
+    def synth_genome_device(self, d_out, start, n, seed):
+        check(self.L.btlbf_synth_genome_dev(self.handle, C.c_void_p(d_out), start, n, seed))
+
+    def synth_reads_device(self, d_out, first_read, n_reads, read_len, g_start, g_len, genome_seed, read_seed):
+        check(self.L.btlbf_synth_reads_dev(self.handle, C.c_void_p(d_out), first_read, n_reads, read_len, g_start,
+                                           g_len, genome_seed, read_seed))
+
+    def random_access_probe(self, d_array, nbytes, n_access, mode):
+        ms = C.c_float()
+        check(self.L.btlbf_random_access_probe(self.handle, C.c_void_p(d_array), nbytes, n_access, mode, C.byref(ms)))
+        return ms.value
+
     def hash_seqs(self, seqs, hashNum, kmerSize, seeds=None, h2=1):
         """Raw iterator output (ntHashIterator, or stHashIterator when seeds are given):
         (n_kmers, hashes[n_bases, H], strands[n_bases, H], valid_bits)."""
@@ -163,6 +175,26 @@ class _DeviceFilter:
         check(self._ctx.L.btlbf_filter_create(self._ctx.handle, self.KIND, size, hashNum, kmerSize, threshold,
                                               C.byref(h)))
         self._h = h
+
+    @classmethod
+    def from_device_memory(cls, tensor, size, hashNum, kmerSize, threshold=0, ctx=None):
+        """Filter over caller-owned device memory (a torch uint8 tensor, 16-byte aligned, at least
+        round_up(bytes, 16) long; used as is, not cleared): btlbf_filter_wrap."""
+        self = cls.__new__(cls)
+        _DeviceFilter.__init__(self)
+        if cls.KIND == BLOOM:
+            cls._check_size(size)
+            self.m_dFPR, self.m_nEntry, self.m_tEntry, self.m_FPR = 0.0, 0, 0, 0.0
+        else:
+            self._threshold = int(threshold)
+        self._ctx = ctx or Context.default()
+        self._tensor = tensor
+        h = C.c_void_p()
+        check(self._ctx.L.btlbf_filter_wrap(self._ctx.handle, cls.KIND, size, hashNum, kmerSize, threshold,
+                                            C.c_void_p(tensor.data_ptr()), tensor.numel() * tensor.element_size(),
+                                            C.byref(h)))
+        self._h = h
+        return self
 
     def _release(self):
         if self._h is not None and self._ctx is not None and self._ctx.handle:
@@ -220,16 +252,29 @@ class _DeviceFilter:
         check(self._L.btlbf_insert_seqs(self._h, _ptr(bases), _p64(off), off.size - 1, C.byref(nk)))
         return nk.value
 
-    def containsSeqs(self, seqs):
-        """contains() of every k-mer of every sequence (README.md:46-57): QueryResult."""
+    def containsSeqs(self, seqs, hit_out=None, valid_out=None, want_valid=True):
+        """contains() of every k-mer of every sequence (README.md:46-57): QueryResult.
+        hit_out / valid_out: optional preallocated uint8 arrays of bit_bytes(n_bases) bytes (e.g. pinned)."""
         bases, off = as_batch(seqs)
         n = bases.size
-        hits = np.zeros(bit_bytes(n), np.uint8)
-        valid = np.zeros(bit_bytes(n), np.uint8)
+        hits = np.zeros(bit_bytes(n), np.uint8) if hit_out is None else hit_out
+        valid = valid_out if valid_out is not None else (np.zeros(bit_bytes(n), np.uint8) if want_valid else None)
+        if hits.size < bit_bytes(n) or (valid is not None and valid.size < bit_bytes(n)):
+            raise ValueError("output arrays need %d bytes" % bit_bytes(n))
         nk, nh = C.c_uint64(), C.c_uint64()
         check(self._L.btlbf_contains_seqs(self._h, _ptr(bases), _p64(off), off.size - 1, _ptr(hits), _ptr(valid),
                                           C.byref(nk), C.byref(nh)))
         return QueryResult(n, off, self.getKmerSize(), hits, valid, nk.value, nh.value)
+
+    # -- device-resident batches (asynchronous on the context's stream; pointers are raw device addresses)
+    def insertSeqsDevice(self, d_bases, n_bases, d_offsets, n_seqs, d_stats=0):
+        check(self._L.btlbf_insert_seqs_dev(self._h, C.c_void_p(d_bases), n_bases, C.c_void_p(d_offsets), n_seqs,
+                                            C.c_void_p(d_stats or 0)))
+
+    def containsSeqsDevice(self, d_bases, n_bases, d_offsets, n_seqs, d_hit_bits=0, d_valid_bits=0, d_stats=0):
+        check(self._L.btlbf_contains_seqs_dev(self._h, C.c_void_p(d_bases), n_bases, C.c_void_p(d_offsets), n_seqs,
+                                              C.c_void_p(d_hit_bits or 0), C.c_void_p(d_valid_bits or 0),
+                                              C.c_void_p(d_stats or 0)))
 
     def orderedStats(self):
         d, r = C.c_uint64(), C.c_uint64()

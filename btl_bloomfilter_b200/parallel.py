@@ -1,0 +1,134 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed).
+
+The hot path shards by sequence: queries run against a filter replicated on every GPU (no data-path
+collective), builds produce one partial filter per GPU.  The partial filters are merged into the
+reference layout by   all-to-all of 1/N array slices  ->  local OR (BloomFilter) or saturating add
+(CountingBloomFilter<uint8_t>) kernel  ->  all-gather.   OR is commutative, associative and idempotent,
+so the merged BloomFilter is bit-identical to a single-GPU build of the same sequences for any sharding.
+The counting merge (saturating add of per-shard incrementMin builds) is a different function from the
+sequential single-filter build; its oracle is "N sequential partial builds, then saturating add".
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+ALIGN = 16
+
+
+def shard_range(n_units, rank, world):
+    """Contiguous, balanced shard [lo, hi) of n_units independent units (reads, chunks) for this rank."""
+    base, rem = divmod(int(n_units), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def slice_len(nbytes, world):
+    """Length of the equal 1/N slices (16-byte aligned) a filter of nbytes is exchanged in."""
+    per = (int(nbytes) + world - 1) // world
+    return (per + ALIGN - 1) // ALIGN * ALIGN
+
+
+def padded_bytes(nbytes, world):
+    return slice_len(nbytes, world) * world
+
+
+def device_tensor_from_ptr(ptr, nbytes, device):
+    """uint8 tensor view of raw device memory (no copy)."""
+    class _Mem:
+        __cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                    "version": 2}
+    return torch.as_tensor(_Mem(), device=device)
+
+
+def merge_partials(t, reduce_fn, group=None):
+    """In-place merge of the per-rank partial arrays `t` (uint8, length world*slice, identical layout on
+    every rank): afterwards every rank holds reduce(all partials).  reduce_fn(dst_view, src_view) folds
+    src into dst (the CUDA OR / saturating-add kernel on GPUs)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world == 1:
+        return t
+    n = t.numel()
+    assert n % world == 0 and (n // world) % ALIGN == 0, "pad the array with padded_bytes()"
+    L = n // world
+    mine = t[rank * L:(rank + 1) * L]
+    recv = torch.empty(n, dtype=t.dtype, device=t.device)
+    backend = dist.get_backend(group)
+    if backend == "nccl":
+        # slice j of my partial goes to rank j; slice `rank` of every peer's partial comes to me
+        dist.all_to_all_single(recv, t, group=group)
+    else:
+        ops = []
+        for peer in range(world):
+            if peer == rank:
+                continue
+            ops.append(dist.P2POp(dist.isend, t[peer * L:(peer + 1) * L], peer, group))
+            ops.append(dist.P2POp(dist.irecv, recv[peer * L:(peer + 1) * L], peer, group))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    for peer in range(world):
+        if peer != rank:
+            reduce_fn(mine, recv[peer * L:(peer + 1) * L])
+    del recv
+    if backend == "nccl":
+        dist.all_gather_into_tensor(t, mine.clone(), group=group)
+    else:
+        parts = [torch.empty(L, dtype=t.dtype, device=t.device) for _ in range(world)]
+        dist.all_gather(parts, mine.clone(), group=group)
+        for peer in range(world):
+            t[peer * L:(peer + 1) * L].copy_(parts[peer])
+    return t
+
+
+def cuda_reduce_fn(ctx, kind):
+    """The local step on the GPU: btlbf_merge_device_buffers (OR for BLOOM, saturating add for COUNTING8)."""
+    L = ctx.L
+    from ._capi import check
+
+    def fn(dst, src):
+        check(L.btlbf_merge_device_buffers(ctx.handle, kind, C.c_void_p(dst.data_ptr()), C.c_void_p(src.data_ptr()),
+                                           dst.numel()))
+    return fn
+
+
+def merge_filter(filt, group=None):
+    """Merge the per-rank partial filters behind `filt` (created with from_device_memory over a tensor of
+    padded_bytes()) in place; returns the tensor."""
+    t = filt._tensor
+    # kernels of the context and NCCL must be ordered: both run on torch's current stream
+    filt._ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    return merge_partials(t, cuda_reduce_fn(filt._ctx, filt.KIND), group)
+
+
+def bench_merge(filt, ctx, dev, repeats=3):
+    """Times the build-side merge of bench.py's per-rank partial filters (max over ranks, CUDA events)."""
+    world = dist.get_world_size()
+    ptr, nbytes = filt.device_ptr()
+    pad = padded_bytes(nbytes, world)
+    # the library's allocation is only padded to 16 bytes: merge through a padded staging tensor
+    stage = torch.zeros(pad, dtype=torch.uint8, device=dev)
+    view = device_tensor_from_ptr(ptr, nbytes, dev)
+    stage[:nbytes].copy_(view)
+    fn = cuda_reduce_fn(ctx, filt.KIND)
+    times = []
+    for _ in range(repeats):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        a.record()
+        merge_partials(stage, fn)
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    tt = torch.tensor([min(times)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    view.copy_(stage[:nbytes])
+    pop = torch.tensor([filt.getPop()], dtype=torch.int64, device=dev)
+    pops = [torch.zeros_like(pop) for _ in range(world)]
+    dist.all_gather(pops, pop)
+    ms = float(tt[0])
+    traffic = 2.0 * (world - 1) / world * pad  # bytes sent (= received) per GPU: all-to-all + all-gather
+    return {"ms": ms, "filter_bytes": int(nbytes), "bytes_per_gpu_each_way": int(traffic),
+            "GBps_per_gpu_each_way": traffic / (ms * 1e-3) / 1e9,
+            "identical_popcount_on_all_ranks": len({int(p) for p in pops}) == 1, "popcount": int(pops[0])}

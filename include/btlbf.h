@@ -113,6 +113,10 @@ int btlbf_filter_set_seeds(btlbf_filter *f, const char *const *seeds, unsigned n
  * array of the same size (a peer GPU's mapped memory is fine): the local step of the multi-GPU merge */
 int btlbf_filter_merge_from_device(btlbf_filter *f, const void *src_device, uint64_t nbytes);
 
+/* the same on raw device arrays (slices of partial filters exchanged between GPUs): dst |= src (BLOOM)
+ * or dst = saturating dst + src (COUNTING8), asynchronous on the context's stream */
+int btlbf_merge_device_buffers(btlbf_ctx *ctx, int kind, void *dst_device, const void *src_device,
+                               uint64_t nbytes);
 /* order-dependent updates (counting insert, insert_and_check): number of k-mers that had to wait for
  * the index-ordered residual rounds, and the number of such rounds, since the filter was created */
 int btlbf_filter_ordered_stats(btlbf_filter *f, uint64_t *deferred, uint64_t *rounds);

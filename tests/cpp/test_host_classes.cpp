@@ -1,0 +1,171 @@
+// test_host_classes.cpp -- the reference's unit scenarios (Tests/Unit/BloomFilterTests.cpp:53-146,
+// Tests/Unit/CountingBloomFilterTests.cpp:54-246) and README usage, written against the GPU-backed
+// drop-in classes in include/btlbf/.  Hash values come from the test oracle (plain-C restatement),
+// which plays the role of the reference's ntHashIterator here.  Run by tests/test_cpp_host.py on a GPU.
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "btlbf/BloomFilter.hpp"
+#include "btlbf/BloomFilterUtil.h"
+#include "btlbf/CountingBloomFilter.hpp"
+
+extern "C" {
+#include "../../oracle/btl_oracle.h"
+}
+
+#define CHECK(cond)                                                                    \
+	do {                                                                               \
+		if (!(cond)) {                                                                 \
+			fprintf(stderr, "CHECK failed at %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+			exit(1);                                                                   \
+		}                                                                              \
+	} while (0)
+
+static size_t
+fileSize(const std::string& p)
+{
+	std::ifstream f(p, std::ios::binary | std::ios::ate);
+	return (size_t)f.tellg();
+}
+
+static void
+bloomScenario(const std::string& tmp)
+{
+	const size_t filterSize = 1000000000;
+	const unsigned numHashes = 5, k = 4;
+	const std::string seq = "ACGTAC";
+	BloomFilter filter(filterSize, numHashes, k);
+	ora_nt_iter it;
+	for (ora_nt_iter_init(&it, seq.data(), seq.size(), numHashes, k); it.pos != ORA_END; ora_nt_iter_next(&it))
+		filter.insert(it.hv);
+	for (ora_nt_iter_init(&it, seq.data(), seq.size(), numHashes, k); it.pos != ORA_END; ora_nt_iter_next(&it))
+		CHECK(filter.contains(it.hv));
+	std::vector<uint64_t> v(it.hv, it.hv + numHashes);
+	ora_nt_iter_init(&it, seq.data(), seq.size(), numHashes, k);
+	std::vector<uint64_t> first(it.hv, it.hv + numHashes);
+	CHECK(filter.contains(first));
+	CHECK(filter.insertAndCheck(first));
+	const std::string path = tmp + "/unit.bf";
+	filter.storeFilter(path);
+	// "[HeaderEnd]" present and the body is exactly sizeInBytes
+	std::ifstream in(path, std::ios::binary);
+	std::string line;
+	bool end = false;
+	size_t headerBytes = 0;
+	while (std::getline(in, line)) {
+		headerBytes += line.size() + 1;
+		if (line == "[HeaderEnd]") {
+			end = true;
+			break;
+		}
+	}
+	CHECK(end);
+	CHECK(fileSize(path) - headerBytes == filter.sizeInBytes());
+	CHECK(filter.sizeInBytes() == filterSize / 8);
+	BloomFilter filter2(path);
+	CHECK(filter2.getFilterSize() == filterSize && filter2.getHashNum() == numHashes && filter2.getKmerSize() == k);
+	for (ora_nt_iter_init(&it, seq.data(), seq.size(), numHashes, k); it.pos != ORA_END; ora_nt_iter_next(&it))
+		CHECK(filter2.contains(it.hv));
+	CHECK(filter2.getPop() == filter.getPop());
+	// operator<< writes the same bytes as storeFilter
+	BloomFilter small(1024, 3, 5);
+	insertSeq(small, "TAGAATCACCCAAAGA", 3, 5);
+	std::ostringstream os;
+	os << small;
+	small.storeFilter(tmp + "/small.bf");
+	std::ifstream sf(tmp + "/small.bf", std::ios::binary);
+	std::stringstream ss;
+	ss << sf.rdbuf();
+	CHECK(os.str() == ss.str());
+	// batched path == per-k-mer path
+	BloomFilter a(8 * 1237, 4, 7), b(8 * 1237, 4, 7);
+	std::vector<std::string> seqs = { "TAGAATCACCCAAAGANNTAGGACCA", "", "acgtagctagcattgGGATCGATTTAGC", "ACG" };
+	uint64_t n = a.insertSeqs(seqs);
+	uint64_t m = 0;
+	for (const auto& s : seqs)
+		for (ora_nt_iter_init(&it, s.data(), s.size(), 4, 7); it.pos != ORA_END; ora_nt_iter_next(&it)) {
+			b.insert(it.hv);
+			m++;
+		}
+	CHECK(n == m);
+	std::ostringstream oa, ob;
+	oa << a;
+	ob << b;
+	CHECK(oa.str() == ob.str());
+	btlbf::SeqHits h = a.containsSeqs(seqs);
+	CHECK(h.nKmers == n && h.nHits == n);
+	btlbf::SeqBatch batch(seqs);
+	for (size_t s = 0; s < seqs.size(); s++)
+		for (ora_nt_iter_init(&it, seqs[s].data(), seqs[s].size(), 4, 7); it.pos != ORA_END; ora_nt_iter_next(&it))
+			CHECK(h.valid(batch.offsets[s] + it.pos) && h.hit(batch.offsets[s] + it.pos));
+	printf("bloom scenario ok (%llu k-mers)\n", (unsigned long long)n);
+}
+
+static void
+countingScenario(const std::string& tmp)
+{
+	const size_t expectedSize = 100001;
+	const unsigned numHashes = 5, k = 8, threshold = 1;
+	const std::string seq = "ACGTACACTGGACTGAGTCT";
+	CountingBloomFilter<uint8_t> filter(expectedSize, numHashes, k, threshold);
+	CHECK(filter.sizeInBytes() == 100008 && filter.size() == filter.sizeInBytes());
+	ora_nt_iter it;
+	for (ora_nt_iter_init(&it, seq.data(), seq.size(), numHashes, k); it.pos != ORA_END; ora_nt_iter_next(&it))
+		filter.insert(it.hv);
+	for (ora_nt_iter_init(&it, seq.data(), seq.size(), numHashes, k); it.pos != ORA_END; ora_nt_iter_next(&it)) {
+		CHECK(filter.contains(it.hv));
+		CHECK(filter.minCount(it.hv) >= 1);
+	}
+	// a sequence that was not inserted is absent (fixed instead of srand(time(0)))
+	const std::string other = "GGCATTAGCCGATATTTCAGGCAATCGGCTAAATTTCCGGAATCGCGCTATAAGCTTTCAG";
+	for (ora_nt_iter_init(&it, other.data(), other.size(), numHashes, k); it.pos != ORA_END; ora_nt_iter_next(&it))
+		CHECK(!filter.contains(it.hv));
+	const std::string path = tmp + "/unit.cbf";
+	filter.storeFilter(path);
+	CountingBloomFilter<uint8_t> filter2(path, threshold);
+	CHECK(filter2.size() == filter.size() && filter2.sizeInBytes() == filter.sizeInBytes());
+	CHECK(filter2.getHashNum() == numHashes && filter2.getKmerSize() == k);
+	CHECK(filter2.popCount() == filter.popCount());
+	for (ora_nt_iter_init(&it, seq.data(), seq.size(), numHashes, k); it.pos != ORA_END; ora_nt_iter_next(&it))
+		CHECK(filter2.contains(it.hv));
+	// batched insert == per-k-mer insert, including repeats (order-dependent updates)
+	CountingBloomFilter<uint8_t> a(512, 4, 11, 2), b(512, 4, 11, 2);
+	std::vector<std::string> seqs = { std::string(200, 'A'), "ACACACACACACACACACACACACACAC", "ACGTTGCATGCATGCCGATGCATGCAGT",
+		                              "ACGTTGCATGCATGCCGATGCATGCAGT" };
+	uint64_t n = a.insertSeqs(seqs);
+	uint64_t m = 0;
+	for (const auto& s : seqs)
+		for (ora_nt_iter_init(&it, s.data(), s.size(), 4, 11); it.pos != ORA_END; ora_nt_iter_next(&it)) {
+			b.insert(it.hv);
+			m++;
+		}
+	CHECK(n == m);
+	std::ostringstream oa, ob;
+	oa << a;
+	ob << b;
+	CHECK(oa.str() == ob.str());
+	CHECK(a.filtered_popcount() == b.filtered_popcount());
+	// saturation: 300 increments stop at 255
+	ora_nt_iter_init(&it, seq.data(), seq.size(), numHashes, k);
+	for (int i = 0; i < 300; i++)
+		filter.incrementAll(it.hv);
+	CHECK(filter.minCount(it.hv) == 255);
+	CHECK(filter.insertAndCheck(it.hv));
+	CHECK(filter.minCount(it.hv) == 255);
+	printf("counting scenario ok (%llu k-mers)\n", (unsigned long long)n);
+}
+
+int
+main(int argc, char** argv)
+{
+	std::string tmp = argc > 1 ? argv[1] : "/tmp";
+	bloomScenario(tmp);
+	countingScenario(tmp);
+	printf("ALL OK\n");
+	return 0;
+}
