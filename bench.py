@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--chunk", type=int, default=CHUNK)
     ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity (0: leave as is)")
+    ap.add_argument("--opt", action="append", default=[], help="context option key=value (tuning experiments)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -209,6 +210,10 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     if args.l2_fetch:
         ctx.set_option("l2_fetch_granularity", args.l2_fetch)
+    for kv in args.opt:
+        key, val = kv.split("=")
+        ctx.set_option(key, int(val))
+        config.setdefault("options", {})[key] = int(val)
 
     chunk = args.chunk // 4096 * 4096
     n_chunks = (G_LEN + chunk - 1) // chunk

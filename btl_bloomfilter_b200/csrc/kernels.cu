@@ -12,14 +12,10 @@
 
 namespace btl {
 
+// one tile: stage -> classify/pack -> roll + fused operation -> per-window result words + statistics
 template<int OP, bool SPACED, bool POW2>
-__global__ void __launch_bounds__(kTPB) seq_kernel(const __grid_constant__ SeqParams P)
+__device__ __forceinline__ void run_tile(const SeqParams& P, const TileSmem& sm, uint64_t t0, int tid)
 {
-	extern __shared__ __align__(16) uint8_t smem_raw[];
-	const TileSmem sm = carve_smem(smem_raw, P.k, SPACED);
-	const int tid = threadIdx.x;
-	const uint64_t t0 = (uint64_t)blockIdx.x * kTile;
-
 	tile_phase_a(P, sm, t0, tid, kTPB);
 	__syncthreads();
 	tile_phase_b(P, sm, t0, tid, kTPB);
@@ -56,6 +52,310 @@ __global__ void __launch_bounds__(kTPB) seq_kernel(const __grid_constant__ SeqPa
 				atomicAdd((unsigned long long*)&P.stats[1], (unsigned long long)sh);
 		}
 	}
+}
+
+template<int OP, bool SPACED, bool POW2>
+__global__ void __launch_bounds__(kTPB) seq_kernel(const __grid_constant__ SeqParams P)
+{
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	const TileSmem sm = carve_smem(smem_raw, P.k, SPACED);
+	run_tile<OP, SPACED, POW2>(P, sm, (uint64_t)blockIdx.x * kTile, threadIdx.x);
+}
+
+// ---------------------------------------------------------------- partitioned build, pass 1
+// Persistent CTAs.  Every WARP is the only writer of its own sub-bucket of each filter partition:
+//   * the warp's append cursors and one 32-byte staging line per partition live in shared memory;
+//   * the 32 bit indices a warp produces per step are ranked inside the warp with ballots (lanes that hit
+//     the same partition get consecutive positions; one lane bumps the cursor) -- no atomics;
+//   * offsets are written to the staging line and leave for HBM as whole 32-byte sectors.
+// Shared memory per warp: n_bins * 36 bytes, so this kernel serves n_bins <= kMaxWarpBins; filters with
+// more partitions use bin_kernel_cta below (CTA-shared cursors, shared-memory atomics, 4-byte stores).
+constexpr uint32_t kMaxWarpBins = 256;
+constexpr uint32_t kFullMask = 0xffffffffu;
+
+struct WarpBins
+{
+	uint32_t* cursor; // [n_bins] offsets appended so far by this warp
+	uint32_t* line;   // [n_bins][8] current partial line
+	uint32_t writer;  // global warp index
+	uint32_t nbits;   // ceil(log2(n_bins))
+};
+
+__device__ __forceinline__ void bin_direct_or(const SeqParams& P, uint32_t part, uint32_t off)
+{
+	uint64_t n = ((uint64_t)part << P.bin_shift) | off;
+	atomicOr((uint32_t*)P.filter + (n >> 5), 1u << (uint32_t)(n & 31));
+}
+
+// stores one full staging line (8 offsets at sub-bucket position `start`, a multiple of 8); a sub-bucket
+// that is full (skewed input) applies the offsets to the filter directly instead -- OR is order-free
+__device__ __forceinline__ void bin_flush_line(const SeqParams& P, const WarpBins& wb, uint32_t part, uint32_t start)
+{
+	const uint4* src = reinterpret_cast<const uint4*>(wb.line + part * 8);
+	uint4 a = src[0], b = src[1];
+	if (start < P.bin_cap) {
+		uint4* dst = reinterpret_cast<uint4*>(P.bin_items + ((uint64_t)part * P.bin_writers + wb.writer) * P.bin_cap + start);
+		dst[0] = a;
+		dst[1] = b;
+	} else {
+		bin_direct_or(P, part, a.x); bin_direct_or(P, part, a.y); bin_direct_or(P, part, a.z); bin_direct_or(P, part, a.w);
+		bin_direct_or(P, part, b.x); bin_direct_or(P, part, b.y); bin_direct_or(P, part, b.z); bin_direct_or(P, part, b.w);
+	}
+}
+
+// warp-synchronous: every lane of the warp calls this the same number of times
+__device__ __forceinline__ void warp_bin_emit(const SeqParams& P, const WarpBins& wb, uint64_t n, bool active)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t part = (uint32_t)(n >> P.bin_shift);
+	const uint32_t off = (uint32_t)n & P.bin_mask;
+	uint32_t peers = __ballot_sync(kFullMask, active);
+	if (peers == 0)
+		return;
+	for (uint32_t bit = 0; bit < wb.nbits; bit++) {
+		uint32_t mine = (part >> bit) & 1u;
+		uint32_t v = __ballot_sync(kFullMask, mine);
+		peers &= mine ? v : ~v;
+	}
+	const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+	uint32_t c = 0;
+	if (active && rank == 0) {
+		c = wb.cursor[part];
+		wb.cursor[part] = c + __popc(peers);
+	}
+	c = __shfl_sync(kFullMask, c, active ? (uint32_t)(__ffs(peers) - 1) : lane);
+	const uint32_t pos = c + rank;
+	const uint32_t round = (pos >> 3) - (c >> 3); // lines this partition advances before my slot is free
+	bool pending = active;
+	for (uint32_t r = 0; __any_sync(kFullMask, pending); r++) {
+		const bool now = pending && round == r;
+		if (now)
+			wb.line[part * 8 + (pos & 7u)] = off;
+		__syncwarp();
+		if (now && (pos & 7u) == 7u)
+			bin_flush_line(P, wb, part, pos - 7u);
+		__syncwarp();
+		if (now)
+			pending = false;
+	}
+}
+
+template<bool SPACED, bool POW2>
+__global__ void __launch_bounds__(kTPB) bin_kernel_warp(const __grid_constant__ SeqParams P)
+{
+	extern __shared__ __align__(32) uint8_t smem_raw[];
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	// [warp][n_bins] cursors, [warp][n_bins][8] lines, then the tile staging area
+	uint32_t* cur_all = reinterpret_cast<uint32_t*>(smem_raw);
+	const uint32_t nb = P.n_bins, nb8 = (nb + 7u) & ~7u;
+	uint32_t* line_all = cur_all + (kTPB / 32) * nb8;
+	uint8_t* tile_raw = reinterpret_cast<uint8_t*>(line_all + (size_t)(kTPB / 32) * nb8 * 8);
+	const TileSmem sm = carve_smem(tile_raw, P.k, SPACED);
+	WarpBins wb;
+	wb.cursor = cur_all + warp * nb8;
+	wb.line = line_all + (size_t)warp * nb8 * 8;
+	wb.writer = blockIdx.x * (kTPB / 32) + warp;
+	wb.nbits = 32 - __clz(nb > 1 ? nb - 1 : 1);
+	for (uint32_t i = lane; i < nb; i += 32)
+		wb.cursor[i] = 0;
+	__syncwarp();
+
+	const uint64_t tiles = (P.n_windows + kTile - 1) / kTile;
+	for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+		const uint64_t t0 = t * kTile;
+		__syncthreads(); // the previous tile is fully consumed before its staging area is overwritten
+		tile_phase_a(P, sm, t0, tid, kTPB);
+		__syncthreads();
+		tile_phase_b(P, sm, t0, tid, kTPB);
+		__syncthreads();
+		uint32_t validw = 0;
+		const uint32_t p0 = (uint32_t)tid * kWPT;
+		roll_windows(P, sm, t0, tid, [&](uint32_t s, bool ok, uint64_t F, uint64_t RC) {
+			validw |= (uint32_t)ok << s;
+			for_each_hash<SPACED>(P, sm, p0 + s, F, RC, [&](uint32_t, uint64_t hv, bool) {
+				warp_bin_emit(P, wb, fastmod<POW2>(hv, P.fm), ok);
+				return true;
+			});
+		});
+		uint64_t widx = (t0 >> 5) + tid;
+		if (P.valid_bits && widx < P.out_words)
+			P.valid_bits[widx] = validw;
+		if (P.stats) {
+			uint32_t nv = __reduce_add_sync(kFullMask, __popc(validw));
+			if (lane == 0 && nv)
+				atomicAdd((unsigned long long*)&P.stats[0], (unsigned long long)nv);
+		}
+	}
+	// drain the partial lines and publish the cursors
+	__syncwarp();
+	for (uint32_t part = lane; part < nb; part += 32) {
+		const uint32_t c = wb.cursor[part], start = c & ~7u;
+		for (uint32_t i = 0; i < (c & 7u); i++) {
+			uint32_t off = wb.line[part * 8 + i];
+			if (start < P.bin_cap)
+				P.bin_items[((uint64_t)part * P.bin_writers + wb.writer) * P.bin_cap + start + i] = off;
+			else
+				bin_direct_or(P, part, off);
+		}
+		P.bin_counts[(uint64_t)part * P.bin_writers + wb.writer] = c;
+	}
+}
+
+static size_t bin_warp_smem_bytes(uint32_t k, bool spaced, uint32_t n_bins)
+{
+	uint32_t nb8 = (n_bins + 7u) & ~7u;
+	return (size_t)(kTPB / 32) * nb8 * 36 + tile_smem_bytes(k, spaced) + 32;
+}
+
+// Fallback for filters with more than kMaxWarpBins partitions: CTA-shared cursors bumped with
+// shared-memory atomics, offsets stored one by one (window_op<OP_BF_BIN>).
+template<bool SPACED, bool POW2>
+__global__ void __launch_bounds__(kTPB) bin_kernel_cta(const __grid_constant__ SeqParams P)
+{
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	TileSmem sm = carve_smem(smem_raw, P.k, SPACED, P.n_bins);
+	sm.writer = blockIdx.x;
+	for (uint32_t i = threadIdx.x; i < P.n_bins; i += kTPB)
+		sm.cursors[i] = 0;
+	const uint64_t tiles = (P.n_windows + kTile - 1) / kTile;
+	for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+		__syncthreads(); // previous tile fully consumed (and the cursors initialised) before restaging
+		run_tile<OP_BF_BIN, SPACED, POW2>(P, sm, t * kTile, threadIdx.x);
+	}
+	__syncthreads();
+	for (uint32_t i = threadIdx.x; i < P.n_bins; i += kTPB)
+		P.bin_counts[(uint64_t)i * P.bin_writers + blockIdx.x] = sm.cursors[i];
+}
+
+// ---------------------------------------------------------------- partitioned build, pass 2
+// Blocks are ordered partition-major, so at any moment the whole GPU is ORing into one or two
+// 2^bin_shift-bit regions of the filter, which stay resident in L2 (one HBM read and one write-back per
+// line instead of one 128-byte fetch per random bit).  One warp drains one sub-bucket at a time.
+constexpr int kApplyThreads = 256;
+__global__ void __launch_bounds__(kApplyThreads) apply_bins_kernel(const __grid_constant__ SeqParams P, uint32_t blocks_per_part)
+{
+	const uint32_t part = blockIdx.x / blocks_per_part, sub = blockIdx.x % blocks_per_part;
+	uint32_t* region = (uint32_t*)P.filter + ((uint64_t)part << (P.bin_shift - 5));
+	// Software pipeline: while partition `part` is being updated, pull the next partition's lines into L2
+	// with full-line prefetches, so that its atomics hit in L2 instead of waiting on one HBM sector each.
+	if (part + 1 < P.n_bins) {
+		const uint64_t next_bit0 = (uint64_t)(part + 1) << P.bin_shift;
+		uint64_t bits = P.fm.m - next_bit0;
+		if (bits > ((uint64_t)1 << P.bin_shift))
+			bits = (uint64_t)1 << P.bin_shift;
+		const uint64_t lines = (bits + 1023) >> 10; // 128-byte lines
+		const char* base = (const char*)P.filter + (next_bit0 >> 3);
+		for (uint64_t l = (uint64_t)sub * kApplyThreads + threadIdx.x; l < lines; l += (uint64_t)blocks_per_part * kApplyThreads)
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (l << 7)));
+	}
+	const uint32_t warps = kApplyThreads / 32, lane = threadIdx.x & 31;
+	for (uint32_t w = sub * warps + (threadIdx.x >> 5); w < P.bin_writers; w += blocks_per_part * warps) {
+		uint32_t n = __ldg(P.bin_counts + (uint64_t)part * P.bin_writers + w);
+		n = n < P.bin_cap ? n : P.bin_cap;
+		const uint32_t* items = P.bin_items + ((uint64_t)part * P.bin_writers + w) * P.bin_cap;
+		const uint4* v = reinterpret_cast<const uint4*>(items); // bin_cap is a multiple of 8
+		const uint32_t nv = n / 4;
+		for (uint32_t i = lane; i < nv; i += 32) {
+			uint4 x = __ldcs(v + i);
+			atomicOr(region + (x.x >> 5), 1u << (x.x & 31));
+			atomicOr(region + (x.y >> 5), 1u << (x.y & 31));
+			atomicOr(region + (x.z >> 5), 1u << (x.z & 31));
+			atomicOr(region + (x.w >> 5), 1u << (x.w & 31));
+		}
+		for (uint32_t i = nv * 4 + lane; i < n; i += 32) {
+			uint32_t o = __ldcs(items + i);
+			atomicOr(region + (o >> 5), 1u << (o & 31));
+		}
+	}
+}
+
+template<bool SPACED, bool POW2>
+static cudaError_t bin_occupancy(const SeqParams& P, uint32_t n_bins, bool* warp_mode, size_t* smem_out, int* blocks_per_sm)
+{
+	*warp_mode = n_bins <= kMaxWarpBins;
+	size_t smem = *warp_mode ? bin_warp_smem_bytes(P.k, SPACED, n_bins) : tile_smem_bytes(P.k, SPACED, n_bins);
+	const void* kern = *warp_mode ? (const void*)bin_kernel_warp<SPACED, POW2> : (const void*)bin_kernel_cta<SPACED, POW2>;
+	if (smem > 48 * 1024) {
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess)
+			return e;
+	}
+	*smem_out = smem;
+	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, kTPB, smem);
+}
+
+static cudaError_t bin_dispatch(const SeqParams& P, uint32_t n_bins, bool* warp_mode, size_t* smem, int* occ)
+{
+	bool spaced = P.n_seeds != 0, pow2 = P.fm.pow2 != 0;
+	if (spaced)
+		return pow2 ? bin_occupancy<true, true>(P, n_bins, warp_mode, smem, occ)
+		            : bin_occupancy<true, false>(P, n_bins, warp_mode, smem, occ);
+	return pow2 ? bin_occupancy<false, true>(P, n_bins, warp_mode, smem, occ)
+	            : bin_occupancy<false, false>(P, n_bins, warp_mode, smem, occ);
+}
+
+// number of sub-bucket writers (warps or CTAs) the bin kernel will run with, and its grid size
+cudaError_t bin_plan(const SeqParams& P, uint32_t n_bins, uint32_t* writers, uint32_t* grid)
+{
+	size_t smem;
+	bool warp_mode;
+	int occ = 0, dev = 0, sms = 0;
+	cudaError_t e = bin_dispatch(P, n_bins, &warp_mode, &smem, &occ);
+	if (e != cudaSuccess)
+		return e;
+	if ((e = cudaGetDevice(&dev)) != cudaSuccess)
+		return e;
+	if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
+		return e;
+	if (occ < 1)
+		return cudaErrorLaunchOutOfResources;
+	uint64_t tiles = (P.n_windows + kTile - 1) / kTile;
+	uint64_t g = (uint64_t)sms * (uint64_t)occ;
+	g = tiles < g ? (tiles ? tiles : 1) : g;
+	*grid = (uint32_t)g;
+	*writers = (uint32_t)(warp_mode ? g * (kTPB / 32) : g);
+	return cudaSuccess;
+}
+
+cudaError_t launch_bin(const SeqParams& P, uint32_t grid, cudaStream_t stream)
+{
+	size_t smem;
+	bool warp_mode;
+	int occ = 0;
+	cudaError_t e = bin_dispatch(P, P.n_bins, &warp_mode, &smem, &occ);
+	if (e != cudaSuccess)
+		return e;
+	bool spaced = P.n_seeds != 0, pow2 = P.fm.pow2 != 0;
+#define BTL_LAUNCH_BIN(KERN)                                                      \
+	do {                                                                          \
+		if (spaced) {                                                             \
+			if (pow2) KERN<true, true><<<grid, kTPB, smem, stream>>>(P);          \
+			else KERN<true, false><<<grid, kTPB, smem, stream>>>(P);              \
+		} else {                                                                  \
+			if (pow2) KERN<false, true><<<grid, kTPB, smem, stream>>>(P);         \
+			else KERN<false, false><<<grid, kTPB, smem, stream>>>(P);             \
+		}                                                                         \
+	} while (0)
+	if (warp_mode)
+		BTL_LAUNCH_BIN(bin_kernel_warp);
+	else
+		BTL_LAUNCH_BIN(bin_kernel_cta);
+#undef BTL_LAUNCH_BIN
+	return cudaGetLastError();
+}
+
+cudaError_t launch_apply_bins(const SeqParams& P, cudaStream_t stream)
+{
+	// enough blocks per partition to fill the GPU, never more warps than sub-buckets
+	uint32_t want = (P.bin_writers + (kApplyThreads / 32) - 1) / (kApplyThreads / 32);
+	uint32_t bpp = want < 592u ? (want ? want : 1u) : 592u;
+	uint64_t grid = (uint64_t)P.n_bins * bpp;
+	if (grid == 0)
+		return cudaSuccess;
+	if (grid > 0x7fffffffULL)
+		return cudaErrorInvalidValue;
+	apply_bins_kernel<<<(unsigned)grid, kApplyThreads, 0, stream>>>(P, bpp);
+	return cudaGetLastError();
 }
 
 size_t seq_kernel_smem_bytes(uint32_t k, bool spaced)

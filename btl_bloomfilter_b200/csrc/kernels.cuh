@@ -23,7 +23,8 @@ enum SeqOp {
 	OP_RESV_TOUCH = 5,   // pass 1: mark reservation bits, detect contended slots
 	OP_CBF_COMMIT = 6,   // pass 2 (incrementMin): commit uncontended k-mers, defer the rest
 	OP_RESV_CLEAR = 7,   // pass 3: clear the reservation bits this batch set
-	OP_BFCHK_COMMIT = 8  // pass 2 (insertAndCheck)
+	OP_BFCHK_COMMIT = 8, // pass 2 (insertAndCheck)
+	OP_BF_BIN = 9        // partitioned BloomFilter build, pass 1: bin bit indices by filter partition
 };
 
 struct SeqParams
@@ -53,6 +54,15 @@ struct SeqParams
 	uint32_t resv_log2;
 	uint32_t* pending;       // deferred window list (chunk-local window indices)
 	uint32_t* pending_count;
+	// partitioned build: sub-bucket (partition p, writer w) holds up to bin_cap 32-bit offsets at
+	// bin_items[(p*bin_writers + w)*bin_cap ...]; bin_counts[p*bin_writers + w] = appended (may exceed cap)
+	uint32_t* bin_items;
+	uint32_t* bin_counts;
+	uint32_t bin_shift;   // log2(bits per partition)
+	uint32_t bin_mask;    // (1 << bin_shift) - 1
+	uint32_t bin_cap;
+	uint32_t bin_writers;
+	uint32_t n_bins;
 	// outputs (chunk-local indexing by window)
 	uint32_t* hit_bits;
 	uint32_t* valid_bits;
@@ -69,6 +79,13 @@ struct SeqParams
 size_t seq_kernel_smem_bytes(uint32_t k, bool spaced);
 // launches seq_kernel<op> for P on stream; returns cudaGetLastError()
 cudaError_t launch_seq(SeqOp op, const SeqParams& P, cudaStream_t stream);
+
+// Partitioned BloomFilter build.  bin_plan: number of persistent writer CTAs the bin kernel will use for
+// P (so that the caller can size the sub-buckets); launch_bin: pass 1 (hash + bin, persistent CTAs);
+// launch_apply_bins: pass 2 (per partition, OR the binned offsets into the L2-resident filter region).
+cudaError_t bin_plan(const SeqParams& P, uint32_t n_bins, uint32_t* writers, uint32_t* grid);
+cudaError_t launch_bin(const SeqParams& P, uint32_t grid, cudaStream_t stream);
+cudaError_t launch_apply_bins(const SeqParams& P, cudaStream_t stream);
 
 // residual rounds of the ordered updates on the compacted list of deferred windows
 struct ListParams

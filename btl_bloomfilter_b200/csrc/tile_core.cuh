@@ -33,6 +33,7 @@ BTL_HD uint64_t mem_atomic_min64(uint64_t* p, uint64_t v)
 {
 	return atomicMin((unsigned long long*)p, (unsigned long long)v);
 }
+BTL_HD uint32_t smem_atomic_inc(uint32_t* p) { return atomicAdd(p, 1u); }
 BTL_HD uint32_t ld_ro(const uint32_t* p) { return __ldg(p); }      // read-only filter gathers
 BTL_HD uint8_t ld_ro(const uint8_t* p) { return __ldg(p); }
 BTL_HD uint8_t ld_cg(const uint8_t* p) { return __ldcg(p); }        // L2-coherent counter reads
@@ -51,6 +52,7 @@ BTL_HD uint64_t mem_atomic_min64(uint64_t* p, uint64_t v)
 		*p = v;
 	return old;
 }
+BTL_HD uint32_t smem_atomic_inc(uint32_t* p) { return (*p)++; }
 BTL_HD uint32_t ld_ro(const uint32_t* p) { return *p; }
 BTL_HD uint8_t ld_ro(const uint8_t* p) { return *p; }
 BTL_HD uint8_t ld_cg(const uint8_t* p) { return *(const volatile uint8_t*)p; }
@@ -78,6 +80,8 @@ struct TileSmem
 	uint64_t* sttab;   // spaced: TF[k][8], TR[k][8]
 	uint8_t* lut;      // byte -> class
 	uint64_t* scratch; // [0] first sequence index of the tile, [1] exotic flag, [2..] reductions
+	uint32_t* cursors; // binned build: per-partition append cursor of this CTA (persists across its tiles)
+	uint32_t writer;   // binned build: index of this CTA's private sub-buckets
 	uint32_t nb;       // staged bytes (multiple of 32)
 };
 
@@ -86,7 +90,7 @@ BTL_HD uint32_t tile_bytes(uint32_t k)
 	return ((uint32_t)kTile + k - 1 + 31u) / 32u * 32u + 32u;
 }
 
-BTL_HD size_t tile_smem_bytes(uint32_t k, bool spaced)
+BTL_HD size_t tile_smem_bytes(uint32_t k, bool spaced, uint32_t nbins = 0)
 {
 	uint32_t nb = tile_bytes(k);
 	size_t s = nb;                       // tile
@@ -96,10 +100,11 @@ BTL_HD size_t tile_smem_bytes(uint32_t k, bool spaced)
 	s += spaced ? (size_t)k * 16 * 8 : 0; // sttab
 	s += 256;                            // lut
 	s += 16 * 8;                         // scratch
+	s += ((size_t)nbins * 4 + 15) / 16 * 16; // cursors
 	return (s + 15) / 16 * 16;
 }
 
-BTL_HD TileSmem carve_smem(uint8_t* raw, uint32_t k, bool spaced)
+BTL_HD TileSmem carve_smem(uint8_t* raw, uint32_t k, bool spaced, uint32_t nbins = 0)
 {
 	TileSmem sm;
 	sm.nb = tile_bytes(k);
@@ -107,6 +112,8 @@ BTL_HD TileSmem carve_smem(uint8_t* raw, uint32_t k, bool spaced)
 	sm.gtab = (uint64_t*)p;    p += 64 * 8;
 	sm.scratch = (uint64_t*)p; p += 16 * 8;
 	sm.sttab = (uint64_t*)p;   p += spaced ? (size_t)k * 16 * 8 : 0;
+	sm.cursors = (uint32_t*)p; p += ((size_t)nbins * 4 + 15) / 16 * 16;
+	sm.writer = 0;
 	sm.tile = p;               p += sm.nb; // nb is a multiple of 32 -> keeps 16-byte alignment
 	sm.codes = (uint32_t*)p;   p += (sm.nb / 16 + 4) * 4;
 	sm.badw = (uint32_t*)p;    p += (sm.nb / 32 + 4) * 4;
@@ -437,6 +444,21 @@ BTL_HD void window_op(const SeqParams& P, const TileSmem& sm, uint64_t t0, uint3
 			counter_sat_inc(cnt, fastmod<POW2>(hv, P.fm));
 			return true;
 		});
+	} else if (OP == OP_BF_BIN) {
+		// partitioned build, pass 1: the bit index is split into (filter partition, offset inside it) and
+		// the offset is appended to this CTA's private sub-bucket of that partition.  A sub-bucket that is
+		// full (skewed input) falls back to the direct atomic -- OR is order-free, so any mix is exact.
+		uint32_t* words = (uint32_t*)P.filter;
+		for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t, uint64_t hv, bool) {
+			uint64_t n = fastmod<POW2>(hv, P.fm);
+			uint32_t part = (uint32_t)(n >> P.bin_shift);
+			uint32_t pos = smem_atomic_inc(sm.cursors + part);
+			if (pos < P.bin_cap)
+				P.bin_items[((uint64_t)part * P.bin_writers + sm.writer) * P.bin_cap + pos] = (uint32_t)n & P.bin_mask;
+			else
+				mem_red_or(words + (n >> 5), 1u << (uint32_t)(n & 31));
+			return true;
+		});
 	} else if (OP == OP_RESV_TOUCH) {
 		// ordered updates, pass 1: mark every (hashed) slot; a slot marked twice is contended
 		uint32_t mask = (1u << P.resv_log2) - 1u;
@@ -482,17 +504,16 @@ BTL_HD void window_op(const SeqParams& P, const TileSmem& sm, uint64_t t0, uint3
 }
 
 // ---------------------------------------------------------------- phase C: roll + operate
-template<int OP, bool SPACED, bool POW2>
-BTL_HD ThreadOut tile_phase_c(const SeqParams& P, const TileSmem& sm, uint64_t t0, int tid)
+// Rolls the canonical ntHash over the thread's kWPT consecutive windows and calls fn(s, ok, F, RC) for
+// every s in [0, kWPT) -- for every thread, in the same order, so that fn may contain warp-synchronous
+// code.  ok: window p0+s is a k-mer the reference's iterator visits (all k bases hashable, inside one
+// sequence, inside the launch's window range); F / RC are only meaningful when ok.
+template<class Fn>
+BTL_HD void roll_windows(const SeqParams& P, const TileSmem& sm, uint64_t t0, int tid, Fn&& fn)
 {
-	ThreadOut out;
-	out.validw = 0;
-	out.hitw = 0;
 	uint64_t nwin64 = P.n_windows > t0 ? P.n_windows - t0 : 0;
 	uint32_t nwin = nwin64 > (uint64_t)kTile ? (uint32_t)kTile : (uint32_t)nwin64;
 	uint32_t p0 = (uint32_t)tid * kWPT;
-	if (p0 >= nwin)
-		return out;
 	const uint32_t k = P.k;
 	const uint64_t* Gf = sm.gtab;
 	const uint64_t* Gfk = sm.gtab + 16;
@@ -527,10 +548,9 @@ BTL_HD ThreadOut tile_phase_c(const SeqParams& P, const TileSmem& sm, uint64_t t
 			RC = sror(RC);
 			bool st = (sm.startw[q >> 5] >> (q & 31)) & 1u;
 			g = (cin & kClsBad) ? 0u : (st ? 1u : g + 1u);
-			if (g >= k && p0 + s < nwin)
-				window_op<OP, SPACED, POW2>(P, sm, t0, p0 + s, s, F, RC, out);
+			fn(s, g >= k && p0 + s < nwin, F, RC);
 		}
-		return out;
+		return;
 	}
 
 	// 2-bit packed path
@@ -568,9 +588,24 @@ BTL_HD ThreadOut tile_phase_c(const SeqParams& P, const TileSmem& sm, uint64_t t
 		}
 		RC = sror(RC);
 		g = ((in_bad >> s) & 1u) ? 0u : (((in_start >> s) & 1u) ? 1u : g + 1u);
-		if (g >= k && p0 + s < nwin)
-			window_op<OP, SPACED, POW2>(P, sm, t0, p0 + s, s, F, RC, out);
+		fn(s, g >= k && p0 + s < nwin, F, RC);
 	}
+}
+
+template<int OP, bool SPACED, bool POW2>
+BTL_HD ThreadOut tile_phase_c(const SeqParams& P, const TileSmem& sm, uint64_t t0, int tid)
+{
+	ThreadOut out;
+	out.validw = 0;
+	out.hitw = 0;
+	uint64_t nwin64 = P.n_windows > t0 ? P.n_windows - t0 : 0;
+	const uint32_t p0 = (uint32_t)tid * kWPT;
+	if (p0 >= nwin64)
+		return out;
+	roll_windows(P, sm, t0, tid, [&](uint32_t s, bool ok, uint64_t F, uint64_t RC) {
+		if (ok)
+			window_op<OP, SPACED, POW2>(P, sm, t0, p0 + s, s, F, RC, out);
+	});
 	return out;
 }
 

@@ -53,11 +53,12 @@ class _EmuFilter:
         valid = np.zeros(bit_bytes(n) // 4 + 1, np.uint32) if want_valid else None
         counts = np.zeros(n + 1, np.uint8) if want_counts else None
         stats = np.zeros(2, np.uint64)
-        info = np.zeros(2, np.uint64)
+        info = np.zeros(3, np.uint64)
         self.be._call(op, self.kind, self.size, self.h, self.k, self.thr, self.seeds, self.h2, self.data, bases, off,
                       hit, valid, counts, None, None, stats, info)
         self.deferred += int(info[0])
         self.rounds += int(info[1])
+        self.be.bin_overflow = int(info[2])
         nb = bit_bytes(n)
         return (n, int(stats[0]), int(stats[1]),
                 None if hit is None else hit.view(np.uint8)[:nb].copy(),
@@ -96,11 +97,14 @@ class _EmuFilter:
 class EmuBackend:
     name = "emu"
 
-    def __init__(self, chunk=1 << 20, batch=1 << 20, resv_log2=16, list_log2=10, force_generic=0, query_mode=0):
+    def __init__(self, chunk=1 << 20, batch=1 << 20, resv_log2=16, list_log2=10, force_generic=0, query_mode=0,
+                 bin_shift=0, bin_writers=3, bin_slack_pct=20):
         build_emu()
         self.L = C.CDLL(EMU_SO)
+        self.bin_overflow = 0
         self.opts = dict(chunk=chunk, batch=batch, resv_log2=resv_log2, list_log2=list_log2,
-                         force_generic=force_generic, query_mode=query_mode)
+                         force_generic=force_generic, query_mode=query_mode, bin_shift=bin_shift,
+                         bin_writers=bin_writers, bin_slack_pct=bin_slack_pct)
 
     def _call(self, op, kind, size, h, k, thr, seeds, h2, filt, bases, off, hit, valid, counts, hashes, strands, stats,
               info):
@@ -114,7 +118,8 @@ class EmuBackend:
                                p(bases) if bases.size else C.c_void_p(0), p(off), C.c_uint64(off.size - 1), p(hit),
                                p(valid), p(counts), p(hashes), p(strands), p(stats), C.c_int(o["force_generic"]),
                                C.c_int(o["query_mode"]), C.c_uint64(o["chunk"]), C.c_uint64(o["batch"]),
-                               C.c_uint(o["resv_log2"]), C.c_uint(o["list_log2"]), p(info), msg, C.c_size_t(256))
+                               C.c_uint(o["resv_log2"]), C.c_uint(o["list_log2"]), p(info), msg, C.c_size_t(256),
+                               C.c_uint(o["bin_shift"]), C.c_uint(o["bin_writers"]), C.c_uint(o["bin_slack_pct"]))
         if rc != 0:
             raise ValueError(msg.value.decode())
 
@@ -183,7 +188,10 @@ class GpuBackend:
         self.B = B
         self.ctx = B.Context(0)
         # translate the emulator's option names
-        m = {"chunk": "chunk_bases", "batch": "cbf_batch"}
+        m = {"chunk": "chunk_bases", "batch": "cbf_batch", "bin_shift": "bin_part_log2"}
+        if "bin_shift" in opts:
+            opts = dict(opts, bin_mode=1)
+        opts.pop("bin_writers", None)
         for k, v in opts.items():
             self.ctx.set_option(m.get(k, k), v)
 

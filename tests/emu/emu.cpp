@@ -68,6 +68,63 @@ void run(SeqOp op, const SeqParams& P)
 	}
 }
 
+// mirrors bin_kernel / apply_bins_kernel of kernels.cu (persistent writers, private sub-buckets)
+template<bool SPACED, bool POW2>
+void run_bin_grid(const SeqParams& P)
+{
+	uint64_t tiles = (P.n_windows + kTile - 1) / kTile;
+	std::vector<uint8_t> raw(tile_smem_bytes(P.k, SPACED, P.n_bins) + 64);
+	uint8_t* base = raw.data() + ((16 - ((uintptr_t)raw.data() & 15)) & 15);
+	for (uint32_t w = 0; w < P.bin_writers; w++) {
+		TileSmem sm = carve_smem(base, P.k, SPACED, P.n_bins);
+		sm.writer = w;
+		for (uint32_t i = 0; i < P.n_bins; i++) sm.cursors[i] = 0;
+		for (uint64_t t = w; t < tiles; t += P.bin_writers) {
+			uint64_t t0 = t * kTile;
+			for (int tid = 0; tid < kTPB; tid++) tile_phase_a(P, sm, t0, tid, kTPB);
+			for (int tid = 0; tid < kTPB; tid++) tile_phase_b(P, sm, t0, tid, kTPB);
+			for (int tid = 0; tid < kTPB; tid++) {
+				ThreadOut out = tile_phase_c<OP_BF_BIN, SPACED, POW2>(P, sm, t0, tid);
+				uint64_t widx = (t0 >> 5) + tid;
+				if (widx < P.out_words && P.valid_bits) P.valid_bits[widx] = out.validw;
+				if (P.stats) P.stats[0] += __builtin_popcount(out.validw);
+			}
+		}
+		for (uint32_t i = 0; i < P.n_bins; i++) P.bin_counts[(uint64_t)i * P.bin_writers + w] = sm.cursors[i];
+	}
+}
+
+uint64_t g_bin_overflow = 0;
+
+void binned_insert(SeqParams P, uint64_t size_bits, uint32_t shift, uint32_t writers, uint32_t slack_pct)
+{
+	uint64_t n_bins = (size_bits + (((uint64_t)1 << shift) - 1)) >> shift;
+	P.n_bins = (uint32_t)n_bins;
+	P.bin_shift = shift;
+	P.bin_mask = (uint32_t)(((uint64_t)1 << shift) - 1);
+	uint64_t tiles = (P.n_windows + kTile - 1) / kTile;
+	P.bin_writers = (uint32_t)(tiles < writers ? (tiles ? tiles : 1) : writers);
+	double parts = (double)size_bits / (double)((uint64_t)1 << shift);
+	double expect = (double)P.n_windows * P.h / parts / P.bin_writers;
+	uint64_t cap = (uint64_t)(expect * (1.0 + slack_pct / 100.0)) + 4;
+	P.bin_cap = (uint32_t)((cap + 3) / 4 * 4);
+	std::vector<uint32_t> items(n_bins * P.bin_writers * P.bin_cap), counts(n_bins * P.bin_writers, 0xdeadbeefu);
+	P.bin_items = items.data();
+	P.bin_counts = counts.data();
+	bool sp = P.n_seeds != 0, p2 = P.fm.pow2 != 0;
+	if (sp) { if (p2) run_bin_grid<true, true>(P); else run_bin_grid<true, false>(P); }
+	else    { if (p2) run_bin_grid<false, true>(P); else run_bin_grid<false, false>(P); }
+	uint32_t* words = (uint32_t*)P.filter;
+	for (uint64_t part = 0; part < n_bins; part++)
+		for (uint32_t w = 0; w < P.bin_writers; w++) {
+			uint32_t n = counts[part * P.bin_writers + w];
+			if (n > P.bin_cap) { g_bin_overflow += n - P.bin_cap; n = P.bin_cap; }
+			const uint32_t* it = items.data() + (part * P.bin_writers + w) * P.bin_cap;
+			uint32_t* region = words + (part << (shift - 5));
+			for (uint32_t i = 0; i < n; i++) region[it[i] >> 5] |= 1u << (it[i] & 31);
+		}
+}
+
 struct Ordered
 {
 	std::vector<uint32_t> touched, contended, pend[2];
@@ -155,7 +212,7 @@ int emu_seq_op(int pub_op, int kind, uint64_t size, unsigned h, unsigned k, unsi
                const uint64_t* offsets, uint64_t n_seqs, uint32_t* hit, uint32_t* valid, uint8_t* counts,
                uint64_t* hashes, uint8_t* strands, uint64_t* stats, int force_generic, int query_mode,
                uint64_t chunk, uint64_t batch, unsigned resv_log2, unsigned list_log2, uint64_t* info,
-               char* msg, size_t msg_cap)
+               char* msg, size_t msg_cap, unsigned bin_shift, unsigned bin_writers, unsigned bin_slack_pct)
 {
 	SeqParams proto;
 	HostSeedTables t;
@@ -208,7 +265,9 @@ int emu_seq_op(int pub_op, int kind, uint64_t size, unsigned h, unsigned k, unsi
 		P.stats = stats;
 		switch (pub_op) {
 		case 0:
-			if (kind == 0) run(OP_BF_INSERT, P); else ordered_apply(st, P, 0, batch);
+			if (kind == 0 && bin_shift && size % 32 == 0) binned_insert(P, size, bin_shift, bin_writers, bin_slack_pct);
+			else if (kind == 0) run(OP_BF_INSERT, P);
+			else ordered_apply(st, P, 0, batch);
 			break;
 		case 1: run(kind == 0 ? OP_BF_CONTAINS : OP_CBF_MINCOUNT, P); break;
 		case 2: ordered_apply(st, P, 1, batch); break;
@@ -221,6 +280,7 @@ int emu_seq_op(int pub_op, int kind, uint64_t size, unsigned h, unsigned k, unsi
 	if (info) {
 		info[0] = st.deferred;
 		info[1] = st.rounds;
+		info[2] = g_bin_overflow;
 	}
 	return 0;
 }

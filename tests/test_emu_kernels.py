@@ -96,3 +96,31 @@ def test_edge_cases(emu, oracle):
 
 def test_cfg1(emu, oracle, golden):
     S.check_cfg1(emu, oracle, golden)
+
+
+# ---------------------------------------------------------------- partitioned (binned) BloomFilter build
+@pytest.mark.parametrize("shift,writers,slack", [(10, 3, 20), (8, 5, 0), (12, 1, 300), (5, 2, 50)])
+def test_binned_build_equals_direct(oracle, golden, shift, writers, slack):
+    be = EmuBackend(bin_shift=shift, bin_writers=writers, bin_slack_pct=slack)
+    S.check_golden_bf(be, golden)
+    S.check_random_bf(be, oracle, 25, 4, 1 << 16, seed=3)
+    S.check_random_bf(be, oracle, 32, 6, 32 * 1237, seed=4)   # non-power-of-two size, partial last partition
+    S.check_random_spaced(be, oracle, 16, 3, 3, seed=16)
+
+
+def test_binned_build_overflow_falls_back_to_direct_atomics(oracle):
+    """A skewed batch (one k-mer repeated) overflows its sub-buckets; the overflow goes through the direct path."""
+    be = EmuBackend(bin_shift=8, bin_writers=2, bin_slack_pct=0)
+    f = be.filter(0, 1 << 14, 4, 11)
+    seqs = ["A" * 3000, "ACGT" * 500]
+    import numpy as np
+    import _oracle as O
+    b, off = O.as_batch(seqs)
+    filt = np.zeros((1 << 14) // 8, np.uint8)
+    assert f.insert(seqs) == oracle.bf_insert_seqs(filt, 1 << 14, 4, 11, b, off)
+    assert np.array_equal(f.bytes(), filt)
+    assert be.bin_overflow > 0
+
+
+def test_binned_build_cfg1(oracle, golden):
+    S.check_cfg1(EmuBackend(bin_shift=16, bin_writers=7), oracle, golden)

@@ -306,3 +306,59 @@ def test_errors_are_reported_not_fatal(gpu):
         f.setSeeds(["11011", "1101"], 2)  # wrong seed length
     with pytest.raises(B.BtlbfError):
         f.setSeeds(["11011"], 2)  # hashNum != n_seeds*h2
+
+
+# ---------------------------------------------------------------- partitioned (binned) BloomFilter build
+@pytest.mark.parametrize("shift", [8, 12, 20])
+def test_binned_build_equals_oracle(oracle, golden, shift):
+    from _backends import GpuBackend
+    be = GpuBackend(bin_shift=shift)
+    S.check_golden_bf(be, golden)
+    S.check_random_bf(be, oracle, 25, 4, 1 << 16, seed=3)
+    S.check_random_bf(be, oracle, 32, 6, 32 * 1237, seed=4)
+    S.check_random_spaced(be, oracle, 16, 3, 3, seed=16)
+    S.check_cfg1(be, oracle, golden)
+
+
+def test_binned_build_skewed_input(oracle):
+    from _backends import GpuBackend
+    be = GpuBackend(bin_shift=8, bin_slack_pct=0)
+    f = be.filter(0, 1 << 14, 4, 11)
+    seqs = ["A" * 30000, "ACGT" * 5000, "ACGTTGCA" * 3000]
+    b, off = O.as_batch(seqs)
+    filt = np.zeros((1 << 14) // 8, np.uint8)
+    assert f.insert(seqs) == oracle.bf_insert_seqs(filt, 1 << 14, 4, 11, b, off)
+    assert np.array_equal(f.bytes(), filt)
+
+
+def test_binned_build_full_size_equals_direct_build(gpu, oracle):
+    """cfg2's filter (31,568,113,856 bits, not a power of two), 24 Mbp of the synthetic genome generated in
+    HBM: the partitioned build (auto-selected at this size) and the direct-atomics build must produce the
+    same 3.95 GB array, and a prefix replayed by the oracle must be fully contained."""
+    import torch
+    import btl_bloomfilter_b200 as B
+    from btl_bloomfilter_b200 import parallel
+    bits, n = 31_568_113_856, 24_000_000
+    ctx = gpu.ctx
+    dev = torch.device("cuda", 0)
+    g = torch.empty(n + 64, dtype=torch.uint8, device=dev)
+    ctx.synth_genome_device(g.data_ptr(), 5_000_000, n, 42)
+    off = torch.tensor([0, n], dtype=torch.int64, device=dev)
+    stats = torch.zeros(2, dtype=torch.int64, device=dev)
+    arrays = []
+    for mode in (-1, 1, 0):
+        ctx.set_option("bin_mode", mode)
+        f = B.BloomFilter(bits, 4, 25, ctx=ctx)
+        l0 = ctx.launch_count
+        f.insertSeqsDevice(g.data_ptr(), n, off.data_ptr(), 1, stats.data_ptr())
+        ctx.sync()
+        assert ctx.launch_count - l0 == (1 if mode == -1 else 2)  # auto picks the two-pass build here
+        ptr, nbytes = f.device_ptr()
+        arrays.append((f, parallel.device_tensor_from_ptr(ptr, nbytes, dev)))
+    ctx.set_option("bin_mode", 0)
+    assert int(stats[0]) == 3 * (n - 24)
+    assert torch.equal(arrays[0][1], arrays[1][1]) and torch.equal(arrays[0][1], arrays[2][1])
+    head = oracle.synth_genome(5_000_000, 200_000, 42)
+    assert np.array_equal(head, g[:200_000].cpu().numpy())
+    r = arrays[1][0].containsSeqs((head, np.array([0, head.size], np.uint64)))
+    assert r.n_kmers == r.n_hits == head.size - 24
