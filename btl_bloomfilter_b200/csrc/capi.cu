@@ -82,8 +82,9 @@ struct btlbf_ctx
 	int64_t bin_mode = 0;       // partitioned BloomFilter build: 0 auto, 1 always, -1 never
 	int64_t bin_part_log2 = 27; // bits per filter partition (2^27 bits = 16 MiB: two of them resident in L2)
 	int64_t bin_slack_pct = 20;
+	int64_t bin_query_mode = 0; // partitioned query: 0 auto, 1 always (when supported), -1 never
 	Slot slot[2];
-	DevBuf offsets, bin_items, bin_counts;
+	DevBuf offsets, bin_items, bin_counts, q_hit, q_valid;
 	uint64_t binned_launches = 0;
 };
 
@@ -280,6 +281,8 @@ extern "C" int btlbf_ctx_destroy(btlbf_ctx* ctx)
 	release(ctx->offsets);
 	release(ctx->bin_items);
 	release(ctx->bin_counts);
+	release(ctx->q_hit);
+	release(ctx->q_valid);
 	if (ctx->d_scalars) cudaFree(ctx->d_scalars);
 	if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
 	if (ctx->own) cudaStreamDestroy(ctx->own);
@@ -347,6 +350,10 @@ extern "C" int btlbf_ctx_set_option(btlbf_ctx* ctx, const char* key, int64_t val
 		if (value < -1 || value > 1)
 			return fail(BTLBF_ERR_ARG, "bin_mode must be -1, 0 or 1");
 		ctx->bin_mode = value;
+	} else if (k == "bin_query_mode") {
+		if (value < -1 || value > 1)
+			return fail(BTLBF_ERR_ARG, "bin_query_mode must be -1, 0 or 1");
+		ctx->bin_query_mode = value;
 	} else if (k == "bin_part_log2") {
 		if (value < 8 || value > 31)
 			return fail(BTLBF_ERR_ARG, "bin_part_log2 out of range [8,31]");
@@ -758,7 +765,8 @@ static bool want_binned(const btlbf_filter* f, const SeqParams& P)
 	return f->bytes >= ((uint64_t)96 << 20) && P.n_windows * P.h >= f->bytes / 64;
 }
 
-static int binned_insert(btlbf_filter* f, SeqParams P, cudaStream_t s)
+// partition geometry + sub-bucket storage shared by the partitioned build and query
+static int bin_setup(btlbf_filter* f, SeqParams& P, bool query, uint32_t* grid)
 {
 	btlbf_ctx* ctx = f->ctx;
 	uint32_t shift = (uint32_t)ctx->bin_part_log2;
@@ -766,32 +774,85 @@ static int binned_insert(btlbf_filter* f, SeqParams P, cudaStream_t s)
 		shift++;
 	uint64_t n_bins = (f->size + (((uint64_t)1 << shift) - 1)) >> shift;
 	if (n_bins > 4096)
-		return fail(BTLBF_ERR_ARG, "filter too large for the partitioned build");
+		return fail(BTLBF_ERR_ARG, "filter too large for the partitioned path");
 	P.n_bins = (uint32_t)n_bins;
 	P.bin_shift = shift;
 	P.bin_mask = (uint32_t)(((uint64_t)1 << shift) - 1);
-	uint32_t writers = 0, grid = 0;
-	cudaError_t e = bin_plan(P, P.n_bins, &writers, &grid);
+	uint32_t writers = 0;
+	cudaError_t e = bin_plan(P, P.n_bins, query, &writers, grid);
 	if (e != cudaSuccess)
-		return fail(BTLBF_ERR_CUDA, "planning the partitioned build failed: %s", cudaGetErrorString(e));
+		return fail(BTLBF_ERR_CUDA, "planning the partitioned pass failed: %s", cudaGetErrorString(e));
 	P.bin_writers = writers;
 	double parts = (double)f->size / (double)((uint64_t)1 << shift); // fractional: the last one is partial
 	double expect = (double)P.n_windows * P.h / parts / writers;
 	uint64_t cap = (uint64_t)(expect * (1.0 + ctx->bin_slack_pct / 100.0)) + 96;
 	cap = (cap + 7) / 8 * 8; // whole 32-byte lines
-	if (cap > 0x7fffffffULL)
-		cap = 0x7ffffffcULL;
+	if (cap > 0x7ffffff8ULL)
+		cap = 0x7ffffff8ULL;
 	P.bin_cap = (uint32_t)cap;
-	TRY(ensure(ctx->bin_items, n_bins * writers * cap * 4));
+	TRY(ensure(ctx->bin_items, n_bins * writers * cap * (query ? 8 : 4)));
 	TRY(ensure(ctx->bin_counts, n_bins * writers * 4));
 	P.bin_items = (uint32_t*)ctx->bin_items.p;
 	P.bin_counts = (uint32_t*)ctx->bin_counts.p;
-	e = launch_bin(P, grid, s);
+	return BTLBF_OK;
+}
+
+static int binned_insert(btlbf_filter* f, SeqParams P, cudaStream_t s)
+{
+	btlbf_ctx* ctx = f->ctx;
+	uint32_t grid = 0;
+	TRY(bin_setup(f, P, false, &grid));
+	cudaError_t e = launch_bin(P, false, grid, s);
 	if (e == cudaSuccess)
 		e = launch_apply_bins(P, s);
 	if (e != cudaSuccess)
 		return fail(BTLBF_ERR_CUDA, "partitioned build launch failed: %s", cudaGetErrorString(e));
 	ctx->launches += 2;
+	ctx->binned_launches++;
+	return BTLBF_OK;
+}
+
+// Partitioned query: bin (offset, window) pairs by filter partition, test them while the partition is
+// resident in L2, clear the hit bit of every window with a missing bit.  Same booleans as the direct path.
+static bool want_binned_query(const btlbf_filter* f, const SeqParams& P)
+{
+	const btlbf_ctx* ctx = f->ctx;
+	if (ctx->bin_query_mode < 0 || f->kind != BTLBF_BLOOM || f->size % 32 != 0 || P.n_windows > 0xffffffffULL)
+		return false;
+	uint32_t shift = (uint32_t)ctx->bin_part_log2;
+	if (!bin_query_supported((uint32_t)((f->size + (((uint64_t)1 << shift) - 1)) >> shift)))
+		return false;
+	if (((uintptr_t)P.hit_bits | (uintptr_t)P.valid_bits) & 3u)
+		return false;
+	if (ctx->bin_query_mode > 0)
+		return true;
+	return f->bytes >= ((uint64_t)96 << 20) && P.n_windows * P.h >= f->bytes / 64;
+}
+
+static int binned_query(btlbf_filter* f, SeqParams P, cudaStream_t s)
+{
+	btlbf_ctx* ctx = f->ctx;
+	uint32_t grid = 0;
+	TRY(bin_setup(f, P, true, &grid));
+	const uint64_t words = P.out_words;
+	if (!P.hit_bits) {
+		TRY(ensure(ctx->q_hit, words * 4));
+		P.hit_bits = (uint32_t*)ctx->q_hit.p;
+	}
+	if (!P.valid_bits) {
+		TRY(ensure(ctx->q_valid, words * 4));
+		P.valid_bits = (uint32_t*)ctx->q_valid.p;
+	}
+	uint64_t* stats = P.stats;
+	CU(cudaMemsetAsync(P.hit_bits, 0xff, words * 4, s));
+	cudaError_t e = launch_bin(P, true, grid, s);
+	if (e == cudaSuccess)
+		e = launch_probe_bins(P, s);
+	if (e == cudaSuccess)
+		e = launch_finalize_hits(P.hit_bits, P.valid_bits, words, stats ? (unsigned long long*)(stats + 1) : nullptr, s);
+	if (e != cudaSuccess)
+		return fail(BTLBF_ERR_CUDA, "partitioned query launch failed: %s", cudaGetErrorString(e));
+	ctx->launches += 3;
 	ctx->binned_launches++;
 	return BTLBF_OK;
 }
@@ -846,6 +907,8 @@ static int filter_op_dev(btlbf_filter* f, PublicOp op, const ChunkIO& io, cudaSt
 		}
 		return ordered_apply(f, P, 0, s);
 	case PUB_CONTAINS:
+		if (f->kind == BTLBF_BLOOM && P.n_windows && want_binned_query(f, P))
+			return binned_query(f, P, s);
 		return launch(ctx, f->kind == BTLBF_BLOOM ? OP_BF_CONTAINS : OP_CBF_MINCOUNT, P, s);
 	case PUB_INSERT_CHECK:
 		return ordered_apply(f, P, f->kind == BTLBF_BLOOM ? 1 : 0, s);

@@ -87,16 +87,30 @@ __device__ __forceinline__ void bin_direct_or(const SeqParams& P, uint32_t part,
 	atomicOr((uint32_t*)P.filter + (n >> 5), 1u << (uint32_t)(n & 31));
 }
 
-// stores one full staging line (8 offsets at sub-bucket position `start`, a multiple of 8); a sub-bucket
-// that is full (skewed input) applies the offsets to the filter directly instead -- OR is order-free
+// query flavour: the bit is tested right away; a miss clears the window's hit bit
+__device__ __forceinline__ void bin_direct_probe(const SeqParams& P, uint32_t part, uint32_t off, uint32_t wid)
+{
+	uint64_t n = ((uint64_t)part << P.bin_shift) | off;
+	if (!((__ldg((const uint32_t*)P.filter + (n >> 5)) >> (uint32_t)(n & 31)) & 1u))
+		atomicAnd(P.hit_bits + (wid >> 5), ~(1u << (wid & 31)));
+}
+
+// Stores one full 32-byte staging line at sub-bucket item position `start`: 8 offsets (build), or 4
+// (offset, window) pairs (QUERY).  A sub-bucket that is full (skewed input) handles the line's items
+// directly instead -- OR / AND-of-probes are order-free, so any mix of the two paths is exact.
+template<bool QUERY>
 __device__ __forceinline__ void bin_flush_line(const SeqParams& P, const WarpBins& wb, uint32_t part, uint32_t start)
 {
 	const uint4* src = reinterpret_cast<const uint4*>(wb.line + part * 8);
 	uint4 a = src[0], b = src[1];
 	if (start < P.bin_cap) {
-		uint4* dst = reinterpret_cast<uint4*>(P.bin_items + ((uint64_t)part * P.bin_writers + wb.writer) * P.bin_cap + start);
+		uint64_t item0 = ((uint64_t)part * P.bin_writers + wb.writer) * P.bin_cap + start;
+		uint4* dst = reinterpret_cast<uint4*>(P.bin_items + (QUERY ? item0 * 2 : item0));
 		dst[0] = a;
 		dst[1] = b;
+	} else if (QUERY) {
+		bin_direct_probe(P, part, a.x, a.y); bin_direct_probe(P, part, a.z, a.w);
+		bin_direct_probe(P, part, b.x, b.y); bin_direct_probe(P, part, b.z, b.w);
 	} else {
 		bin_direct_or(P, part, a.x); bin_direct_or(P, part, a.y); bin_direct_or(P, part, a.z); bin_direct_or(P, part, a.w);
 		bin_direct_or(P, part, b.x); bin_direct_or(P, part, b.y); bin_direct_or(P, part, b.z); bin_direct_or(P, part, b.w);
@@ -104,8 +118,10 @@ __device__ __forceinline__ void bin_flush_line(const SeqParams& P, const WarpBin
 }
 
 // warp-synchronous: every lane of the warp calls this the same number of times
-__device__ __forceinline__ void warp_bin_emit(const SeqParams& P, const WarpBins& wb, uint64_t n, bool active)
+template<bool QUERY>
+__device__ __forceinline__ void warp_bin_emit(const SeqParams& P, const WarpBins& wb, uint64_t n, uint32_t wid, bool active)
 {
+	constexpr uint32_t L = QUERY ? 4u : 8u, LOG_L = QUERY ? 2u : 3u; // items per 32-byte line
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t part = (uint32_t)(n >> P.bin_shift);
 	const uint32_t off = (uint32_t)n & P.bin_mask;
@@ -125,24 +141,29 @@ __device__ __forceinline__ void warp_bin_emit(const SeqParams& P, const WarpBins
 	}
 	c = __shfl_sync(kFullMask, c, active ? (uint32_t)(__ffs(peers) - 1) : lane);
 	const uint32_t pos = c + rank;
-	const uint32_t round = (pos >> 3) - (c >> 3); // lines this partition advances before my slot is free
+	const uint32_t round = (pos >> LOG_L) - (c >> LOG_L); // lines this partition advances before my slot is free
 	bool pending = active;
 	for (uint32_t r = 0; __any_sync(kFullMask, pending); r++) {
 		const bool now = pending && round == r;
-		if (now)
-			wb.line[part * 8 + (pos & 7u)] = off;
+		if (now) {
+			if (QUERY)
+				*reinterpret_cast<uint2*>(wb.line + part * 8 + (pos & (L - 1)) * 2) = make_uint2(off, wid);
+			else
+				wb.line[part * 8 + (pos & (L - 1))] = off;
+		}
 		__syncwarp();
-		if (now && (pos & 7u) == 7u)
-			bin_flush_line(P, wb, part, pos - 7u);
+		if (now && (pos & (L - 1)) == L - 1)
+			bin_flush_line<QUERY>(P, wb, part, pos - (L - 1));
 		__syncwarp();
 		if (now)
 			pending = false;
 	}
 }
 
-template<bool SPACED, bool POW2>
+template<bool SPACED, bool POW2, bool QUERY>
 __global__ void __launch_bounds__(kTPB) bin_kernel_warp(const __grid_constant__ SeqParams P)
 {
+	constexpr uint32_t L = QUERY ? 4u : 8u;
 	extern __shared__ __align__(32) uint8_t smem_raw[];
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	// [warp][n_bins] cursors, [warp][n_bins][8] lines, then the tile staging area
@@ -173,7 +194,7 @@ __global__ void __launch_bounds__(kTPB) bin_kernel_warp(const __grid_constant__ 
 		roll_windows(P, sm, t0, tid, [&](uint32_t s, bool ok, uint64_t F, uint64_t RC) {
 			validw |= (uint32_t)ok << s;
 			for_each_hash<SPACED>(P, sm, p0 + s, F, RC, [&](uint32_t, uint64_t hv, bool) {
-				warp_bin_emit(P, wb, fastmod<POW2>(hv, P.fm), ok);
+				warp_bin_emit<QUERY>(P, wb, fastmod<POW2>(hv, P.fm), (uint32_t)t0 + p0 + s, ok);
 				return true;
 			});
 		});
@@ -189,13 +210,22 @@ __global__ void __launch_bounds__(kTPB) bin_kernel_warp(const __grid_constant__ 
 	// drain the partial lines and publish the cursors
 	__syncwarp();
 	for (uint32_t part = lane; part < nb; part += 32) {
-		const uint32_t c = wb.cursor[part], start = c & ~7u;
-		for (uint32_t i = 0; i < (c & 7u); i++) {
-			uint32_t off = wb.line[part * 8 + i];
-			if (start < P.bin_cap)
-				P.bin_items[((uint64_t)part * P.bin_writers + wb.writer) * P.bin_cap + start + i] = off;
-			else
-				bin_direct_or(P, part, off);
+		const uint32_t c = wb.cursor[part], start = c & ~(L - 1);
+		const uint64_t item0 = ((uint64_t)part * P.bin_writers + wb.writer) * P.bin_cap + start;
+		for (uint32_t i = 0; i < (c & (L - 1)); i++) {
+			if (QUERY) {
+				uint2 it = *reinterpret_cast<const uint2*>(wb.line + part * 8 + i * 2);
+				if (start < P.bin_cap)
+					*reinterpret_cast<uint2*>(P.bin_items + (item0 + i) * 2) = it;
+				else
+					bin_direct_probe(P, part, it.x, it.y);
+			} else {
+				uint32_t off = wb.line[part * 8 + i];
+				if (start < P.bin_cap)
+					P.bin_items[item0 + i] = off;
+				else
+					bin_direct_or(P, part, off);
+			}
 		}
 		P.bin_counts[(uint64_t)part * P.bin_writers + wb.writer] = c;
 	}
@@ -269,12 +299,75 @@ __global__ void __launch_bounds__(kApplyThreads) apply_bins_kernel(const __grid_
 	}
 }
 
+// Partitioned query, pass 2: same schedule; every (offset, window) pair tests its bit in the L2-resident
+// region and a miss clears the window's hit bit (the hit words start as all ones and are ANDed with the
+// valid words by finalize_hits_kernel).
+__device__ __forceinline__ void probe_one(const uint32_t* region, uint32_t* hit, uint32_t off, uint32_t wid)
+{
+	if (!((__ldg(region + (off >> 5)) >> (off & 31)) & 1u))
+		atomicAnd(hit + (wid >> 5), ~(1u << (wid & 31)));
+}
+
+__global__ void __launch_bounds__(kApplyThreads) probe_bins_kernel(const __grid_constant__ SeqParams P, uint32_t blocks_per_part)
+{
+	const uint32_t part = blockIdx.x / blocks_per_part, sub = blockIdx.x % blocks_per_part;
+	const uint32_t* region = (const uint32_t*)P.filter + ((uint64_t)part << (P.bin_shift - 5));
+	if (part + 1 < P.n_bins) {
+		const uint64_t next_bit0 = (uint64_t)(part + 1) << P.bin_shift;
+		uint64_t bits = P.fm.m - next_bit0;
+		if (bits > ((uint64_t)1 << P.bin_shift))
+			bits = (uint64_t)1 << P.bin_shift;
+		const uint64_t lines = (bits + 1023) >> 10;
+		const char* base = (const char*)P.filter + (next_bit0 >> 3);
+		for (uint64_t l = (uint64_t)sub * kApplyThreads + threadIdx.x; l < lines; l += (uint64_t)blocks_per_part * kApplyThreads)
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (l << 7)));
+	}
+	const uint32_t warps = kApplyThreads / 32, lane = threadIdx.x & 31;
+	for (uint32_t w = sub * warps + (threadIdx.x >> 5); w < P.bin_writers; w += blocks_per_part * warps) {
+		uint32_t n = __ldg(P.bin_counts + (uint64_t)part * P.bin_writers + w);
+		n = n < P.bin_cap ? n : P.bin_cap;
+		const uint32_t* items = P.bin_items + ((uint64_t)part * P.bin_writers + w) * P.bin_cap * 2;
+		const uint4* v = reinterpret_cast<const uint4*>(items); // two items per 16 bytes
+		const uint32_t nv = n / 2;
+		for (uint32_t i = lane; i < nv; i += 32) {
+			uint4 x = __ldcs(v + i);
+			probe_one(region, P.hit_bits, x.x, x.y);
+			probe_one(region, P.hit_bits, x.z, x.w);
+		}
+		if ((n & 1u) && lane == 0) {
+			uint2 x = __ldcs(reinterpret_cast<const uint2*>(items) + (n - 1));
+			probe_one(region, P.hit_bits, x.x, x.y);
+		}
+	}
+}
+
+// hit &= valid, and the number of hits is added to stats[1]
+__global__ void __launch_bounds__(256) finalize_hits_kernel(uint32_t* hit, const uint32_t* valid, uint64_t n_words,
+                                                            unsigned long long* hits_out)
+{
+	unsigned long long acc = 0;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint32_t h = hit[i] & valid[i];
+		hit[i] = h;
+		acc += __popc(h);
+	}
+	for (int o = 16; o > 0; o >>= 1)
+		acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	if ((threadIdx.x & 31) == 0 && acc && hits_out)
+		atomicAdd(hits_out, acc);
+}
+
 template<bool SPACED, bool POW2>
-static cudaError_t bin_occupancy(const SeqParams& P, uint32_t n_bins, bool* warp_mode, size_t* smem_out, int* blocks_per_sm)
+static cudaError_t bin_occupancy(const SeqParams& P, uint32_t n_bins, bool query, bool* warp_mode, size_t* smem_out,
+                                 int* blocks_per_sm)
 {
 	*warp_mode = n_bins <= kMaxWarpBins;
+	if (query && !*warp_mode)
+		return cudaErrorNotSupported;
 	size_t smem = *warp_mode ? bin_warp_smem_bytes(P.k, SPACED, n_bins) : tile_smem_bytes(P.k, SPACED, n_bins);
-	const void* kern = *warp_mode ? (const void*)bin_kernel_warp<SPACED, POW2> : (const void*)bin_kernel_cta<SPACED, POW2>;
+	const void* kern = !*warp_mode ? (const void*)bin_kernel_cta<SPACED, POW2>
+	                   : query    ? (const void*)bin_kernel_warp<SPACED, POW2, true>
+	                              : (const void*)bin_kernel_warp<SPACED, POW2, false>;
 	if (smem > 48 * 1024) {
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess)
@@ -284,23 +377,28 @@ static cudaError_t bin_occupancy(const SeqParams& P, uint32_t n_bins, bool* warp
 	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, kTPB, smem);
 }
 
-static cudaError_t bin_dispatch(const SeqParams& P, uint32_t n_bins, bool* warp_mode, size_t* smem, int* occ)
+static cudaError_t bin_dispatch(const SeqParams& P, uint32_t n_bins, bool query, bool* warp_mode, size_t* smem, int* occ)
 {
 	bool spaced = P.n_seeds != 0, pow2 = P.fm.pow2 != 0;
 	if (spaced)
-		return pow2 ? bin_occupancy<true, true>(P, n_bins, warp_mode, smem, occ)
-		            : bin_occupancy<true, false>(P, n_bins, warp_mode, smem, occ);
-	return pow2 ? bin_occupancy<false, true>(P, n_bins, warp_mode, smem, occ)
-	            : bin_occupancy<false, false>(P, n_bins, warp_mode, smem, occ);
+		return pow2 ? bin_occupancy<true, true>(P, n_bins, query, warp_mode, smem, occ)
+		            : bin_occupancy<true, false>(P, n_bins, query, warp_mode, smem, occ);
+	return pow2 ? bin_occupancy<false, true>(P, n_bins, query, warp_mode, smem, occ)
+	            : bin_occupancy<false, false>(P, n_bins, query, warp_mode, smem, occ);
+}
+
+bool bin_query_supported(uint32_t n_bins)
+{
+	return n_bins <= kMaxWarpBins;
 }
 
 // number of sub-bucket writers (warps or CTAs) the bin kernel will run with, and its grid size
-cudaError_t bin_plan(const SeqParams& P, uint32_t n_bins, uint32_t* writers, uint32_t* grid)
+cudaError_t bin_plan(const SeqParams& P, uint32_t n_bins, bool query, uint32_t* writers, uint32_t* grid)
 {
 	size_t smem;
 	bool warp_mode;
 	int occ = 0, dev = 0, sms = 0;
-	cudaError_t e = bin_dispatch(P, n_bins, &warp_mode, &smem, &occ);
+	cudaError_t e = bin_dispatch(P, n_bins, query, &warp_mode, &smem, &occ);
 	if (e != cudaSuccess)
 		return e;
 	if ((e = cudaGetDevice(&dev)) != cudaSuccess)
@@ -317,38 +415,68 @@ cudaError_t bin_plan(const SeqParams& P, uint32_t n_bins, uint32_t* writers, uin
 	return cudaSuccess;
 }
 
-cudaError_t launch_bin(const SeqParams& P, uint32_t grid, cudaStream_t stream)
+cudaError_t launch_bin(const SeqParams& P, bool query, uint32_t grid, cudaStream_t stream)
 {
 	size_t smem;
 	bool warp_mode;
 	int occ = 0;
-	cudaError_t e = bin_dispatch(P, P.n_bins, &warp_mode, &smem, &occ);
+	cudaError_t e = bin_dispatch(P, P.n_bins, query, &warp_mode, &smem, &occ);
 	if (e != cudaSuccess)
 		return e;
 	bool spaced = P.n_seeds != 0, pow2 = P.fm.pow2 != 0;
-#define BTL_LAUNCH_BIN(KERN)                                                      \
-	do {                                                                          \
-		if (spaced) {                                                             \
-			if (pow2) KERN<true, true><<<grid, kTPB, smem, stream>>>(P);          \
-			else KERN<true, false><<<grid, kTPB, smem, stream>>>(P);              \
-		} else {                                                                  \
-			if (pow2) KERN<false, true><<<grid, kTPB, smem, stream>>>(P);         \
-			else KERN<false, false><<<grid, kTPB, smem, stream>>>(P);             \
-		}                                                                         \
+#define BTL_LAUNCH_BIN(KERN, ...)                                                         \
+	do {                                                                                  \
+		if (spaced) {                                                                     \
+			if (pow2) KERN<true, true, ##__VA_ARGS__><<<grid, kTPB, smem, stream>>>(P);   \
+			else KERN<true, false, ##__VA_ARGS__><<<grid, kTPB, smem, stream>>>(P);       \
+		} else {                                                                          \
+			if (pow2) KERN<false, true, ##__VA_ARGS__><<<grid, kTPB, smem, stream>>>(P);  \
+			else KERN<false, false, ##__VA_ARGS__><<<grid, kTPB, smem, stream>>>(P);      \
+		}                                                                                 \
 	} while (0)
-	if (warp_mode)
-		BTL_LAUNCH_BIN(bin_kernel_warp);
-	else
+	if (!warp_mode)
 		BTL_LAUNCH_BIN(bin_kernel_cta);
+	else if (query)
+		BTL_LAUNCH_BIN(bin_kernel_warp, true);
+	else
+		BTL_LAUNCH_BIN(bin_kernel_warp, false);
 #undef BTL_LAUNCH_BIN
+	return cudaGetLastError();
+}
+
+static uint32_t blocks_per_partition(const SeqParams& P)
+{
+	// enough blocks per partition to fill the GPU, never more warps than sub-buckets
+	uint32_t want = (P.bin_writers + (kApplyThreads / 32) - 1) / (kApplyThreads / 32);
+	return want < 592u ? (want ? want : 1u) : 592u;
+}
+
+cudaError_t launch_probe_bins(const SeqParams& P, cudaStream_t stream)
+{
+	uint32_t bpp = blocks_per_partition(P);
+	uint64_t grid = (uint64_t)P.n_bins * bpp;
+	if (grid == 0)
+		return cudaSuccess;
+	if (grid > 0x7fffffffULL)
+		return cudaErrorInvalidValue;
+	probe_bins_kernel<<<(unsigned)grid, kApplyThreads, 0, stream>>>(P, bpp);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_finalize_hits(uint32_t* hit, const uint32_t* valid, uint64_t n_words, unsigned long long* hits_out,
+                                 cudaStream_t stream)
+{
+	if (n_words == 0)
+		return cudaSuccess;
+	uint64_t want = (n_words + 255) / 256;
+	unsigned grid = (unsigned)(want > 148 * 8 ? 148 * 8 : want);
+	finalize_hits_kernel<<<grid, 256, 0, stream>>>(hit, valid, n_words, hits_out);
 	return cudaGetLastError();
 }
 
 cudaError_t launch_apply_bins(const SeqParams& P, cudaStream_t stream)
 {
-	// enough blocks per partition to fill the GPU, never more warps than sub-buckets
-	uint32_t want = (P.bin_writers + (kApplyThreads / 32) - 1) / (kApplyThreads / 32);
-	uint32_t bpp = want < 592u ? (want ? want : 1u) : 592u;
+	uint32_t bpp = blocks_per_partition(P);
 	uint64_t grid = (uint64_t)P.n_bins * bpp;
 	if (grid == 0)
 		return cudaSuccess;

@@ -83,9 +83,15 @@ cudaError_t launch_seq(SeqOp op, const SeqParams& P, cudaStream_t stream);
 // Partitioned BloomFilter build.  bin_plan: number of persistent writer CTAs the bin kernel will use for
 // P (so that the caller can size the sub-buckets); launch_bin: pass 1 (hash + bin, persistent CTAs);
 // launch_apply_bins: pass 2 (per partition, OR the binned offsets into the L2-resident filter region).
-cudaError_t bin_plan(const SeqParams& P, uint32_t n_bins, uint32_t* writers, uint32_t* grid);
-cudaError_t launch_bin(const SeqParams& P, uint32_t grid, cudaStream_t stream);
+// query == true: the partitioned QUERY (items are (offset, window) pairs; pass 2 = launch_probe_bins, then
+// launch_finalize_hits ANDs the hit words with the valid words and counts the hits).
+cudaError_t bin_plan(const SeqParams& P, uint32_t n_bins, bool query, uint32_t* writers, uint32_t* grid);
+cudaError_t launch_bin(const SeqParams& P, bool query, uint32_t grid, cudaStream_t stream);
 cudaError_t launch_apply_bins(const SeqParams& P, cudaStream_t stream);
+cudaError_t launch_probe_bins(const SeqParams& P, cudaStream_t stream);
+cudaError_t launch_finalize_hits(uint32_t* hit, const uint32_t* valid, uint64_t n_words, unsigned long long* hits_out,
+                                 cudaStream_t stream);
+bool bin_query_supported(uint32_t n_bins);
 
 // residual rounds of the ordered updates on the compacted list of deferred windows
 struct ListParams

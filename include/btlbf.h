@@ -79,7 +79,8 @@ int btlbf_ctx_launch_count(btlbf_ctx *ctx, uint64_t *count);
  * "query_mode" (0: all probes in flight, 1: early-exit probing), "chunk_bases" (windows per
  * pipeline stage of the host-buffer calls), "cbf_batch" (windows per batch of the ordered updates),
  * "resv_log2", "list_log2", "drain_threshold" (sizes of the ordered-update reservation tables),
- * "bin_mode" (partitioned BloomFilter build: 0 auto, 1 always, -1 never), "bin_part_log2" (bits per
+ * "bin_mode" / "bin_query_mode" (partitioned BloomFilter build / query: 0 auto, 1 always, -1 never),
+ * "bin_part_log2" (bits per
  * L2-resident filter partition), "bin_slack_pct", "l2_fetch_granularity" */
 int btlbf_ctx_set_option(btlbf_ctx *ctx, const char *key, int64_t value);
 

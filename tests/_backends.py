@@ -190,7 +190,7 @@ class GpuBackend:
         # translate the emulator's option names
         m = {"chunk": "chunk_bases", "batch": "cbf_batch", "bin_shift": "bin_part_log2"}
         if "bin_shift" in opts:
-            opts = dict(opts, bin_mode=1)
+            opts = dict(opts, bin_mode=1, bin_query_mode=1)
         opts.pop("bin_writers", None)
         for k, v in opts.items():
             self.ctx.set_option(m.get(k, k), v)
