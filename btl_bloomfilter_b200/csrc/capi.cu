@@ -71,6 +71,15 @@ struct btlbf_ctx
 {
 	int device = 0;
 	cudaStream_t own = nullptr, active = nullptr, copy_in = nullptr, copy_out = nullptr;
+	// Background stream: pass 2 of the partitioned build (memory-bound) runs here, concurrently with
+	// whatever the active stream does next (typically the compute-bound pass 1 of the following batch).
+	cudaStream_t aux = nullptr;
+	cudaEvent_t ev_bin_done[2] = { nullptr, nullptr }, ev_apply_done[2] = { nullptr, nullptr };
+	bool slot_used[2] = { false, false };
+	int bin_slot = 0;
+	cudaEvent_t ev_aux_last = nullptr; // last event recorded on aux (one of ev_apply_done)
+	bool aux_pending = false;          // the active stream has not been ordered after ev_aux_last yet
+	int64_t overlap = 1;
 	uint64_t launches = 0;
 	unsigned long long* d_scalars = nullptr; // 16 device words: [0..1] stats, [2] popcount, [4..7] list counters
 	unsigned long long* h_scalars = nullptr; // pinned mirror
@@ -84,7 +93,7 @@ struct btlbf_ctx
 	int64_t bin_slack_pct = 20;
 	int64_t bin_query_mode = 0; // partitioned query: 0 auto, 1 always (when supported), -1 never
 	Slot slot[2];
-	DevBuf offsets, bin_items, bin_counts, q_hit, q_valid;
+	DevBuf offsets, ibin_items[2], ibin_counts[2], qbin_items, qbin_counts, q_hit, q_valid;
 	uint64_t binned_launches = 0;
 };
 
@@ -116,6 +125,17 @@ static int use(btlbf_ctx* ctx)
 		return fail(BTLBF_ERR_ARG, "null context");
 	CU(cudaSetDevice(ctx->device));
 	return BTLBF_OK;
+}
+
+// The active stream, ordered after all background (aux-stream) work: every operation that reads or
+// writes filter contents on the active stream goes through this.
+static cudaStream_t joined(btlbf_ctx* ctx)
+{
+	if (ctx->aux_pending) {
+		cudaStreamWaitEvent(ctx->active, ctx->ev_aux_last, 0);
+		ctx->aux_pending = false;
+	}
+	return ctx->active;
 }
 
 static int ensure(DevBuf& b, size_t bytes)
@@ -244,6 +264,13 @@ extern "C" int btlbf_ctx_create(int device, btlbf_ctx** out)
 	if (e == cudaSuccess)
 		e = cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking);
 	if (e == cudaSuccess)
+		e = cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking);
+	for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+		e = cudaEventCreateWithFlags(&ctx->ev_bin_done[i], cudaEventDisableTiming);
+		if (e == cudaSuccess)
+			e = cudaEventCreateWithFlags(&ctx->ev_apply_done[i], cudaEventDisableTiming);
+	}
+	if (e == cudaSuccess)
 		e = cudaMalloc(&ctx->d_scalars, 16 * sizeof(unsigned long long));
 	if (e == cudaSuccess)
 		e = cudaMemset(ctx->d_scalars, 0, 16 * sizeof(unsigned long long));
@@ -279,8 +306,15 @@ extern "C" int btlbf_ctx_destroy(btlbf_ctx* ctx)
 		if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
 	}
 	release(ctx->offsets);
-	release(ctx->bin_items);
-	release(ctx->bin_counts);
+	for (int i = 0; i < 2; i++) {
+		release(ctx->ibin_items[i]);
+		release(ctx->ibin_counts[i]);
+		if (ctx->ev_bin_done[i]) cudaEventDestroy(ctx->ev_bin_done[i]);
+		if (ctx->ev_apply_done[i]) cudaEventDestroy(ctx->ev_apply_done[i]);
+	}
+	release(ctx->qbin_items);
+	release(ctx->qbin_counts);
+	if (ctx->aux) cudaStreamDestroy(ctx->aux);
 	release(ctx->q_hit);
 	release(ctx->q_valid);
 	if (ctx->d_scalars) cudaFree(ctx->d_scalars);
@@ -295,14 +329,33 @@ extern "C" int btlbf_ctx_destroy(btlbf_ctx* ctx)
 extern "C" int btlbf_ctx_set_stream(btlbf_ctx* ctx, void* cuda_stream)
 {
 	TRY(use(ctx));
-	ctx->active = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own;
+	cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own;
+	if (ctx->aux_pending) // both the old and the new stream are ordered after the background work
+		CU(cudaStreamWaitEvent(next, ctx->ev_aux_last, 0));
+	joined(ctx);
+	ctx->active = next;
 	return BTLBF_OK;
 }
 
 extern "C" int btlbf_ctx_sync(btlbf_ctx* ctx)
 {
 	TRY(use(ctx));
-	CU(cudaStreamSynchronize(ctx->active));
+	CU(cudaStreamSynchronize(joined(ctx)));
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_ctx_flush(btlbf_ctx* ctx)
+{
+	TRY(use(ctx));
+	joined(ctx);
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_ctx_aux_stream(btlbf_ctx* ctx, void** cuda_stream)
+{
+	if (!ctx || !cuda_stream)
+		return fail(BTLBF_ERR_ARG, "null argument");
+	*cuda_stream = (void*)ctx->aux;
 	return BTLBF_OK;
 }
 
@@ -350,6 +403,8 @@ extern "C" int btlbf_ctx_set_option(btlbf_ctx* ctx, const char* key, int64_t val
 		if (value < -1 || value > 1)
 			return fail(BTLBF_ERR_ARG, "bin_mode must be -1, 0 or 1");
 		ctx->bin_mode = value;
+	} else if (k == "overlap") {
+		ctx->overlap = value != 0;
 	} else if (k == "bin_query_mode") {
 		if (value < -1 || value > 1)
 			return fail(BTLBF_ERR_ARG, "bin_query_mode must be -1, 0 or 1");
@@ -443,7 +498,7 @@ extern "C" int btlbf_filter_destroy(btlbf_filter* f)
 	if (!f)
 		return BTLBF_OK;
 	cudaSetDevice(f->ctx->device);
-	cudaStreamSynchronize(f->ctx->active);
+	cudaStreamSynchronize(joined(f->ctx));
 	if (f->owned && f->d_data)
 		cudaFree(f->d_data);
 	hashcfg_free(f->hc);
@@ -461,7 +516,7 @@ extern "C" int btlbf_filter_clear(btlbf_filter* f)
 	if (!f)
 		return fail(BTLBF_ERR_ARG, "null filter");
 	TRY(use(f->ctx));
-	CU(cudaMemsetAsync(f->d_data, 0, (f->bytes + 15) / 16 * 16, f->ctx->active));
+	CU(cudaMemsetAsync(f->d_data, 0, (f->bytes + 15) / 16 * 16, joined(f->ctx)));
 	return BTLBF_OK;
 }
 
@@ -495,7 +550,7 @@ extern "C" int btlbf_filter_upload(btlbf_filter* f, const void* host, uint64_t n
 		return fail(BTLBF_ERR_ARG, "upload of %llu bytes into a %llu-byte filter", (unsigned long long)nbytes,
 		            (unsigned long long)f->bytes);
 	TRY(use(f->ctx));
-	CU(cudaMemcpyAsync(f->d_data, host, nbytes, cudaMemcpyHostToDevice, f->ctx->active));
+	CU(cudaMemcpyAsync(f->d_data, host, nbytes, cudaMemcpyHostToDevice, joined(f->ctx)));
 	uint64_t pad = (f->bytes + 15) / 16 * 16 - f->bytes;
 	if (pad)
 		CU(cudaMemsetAsync(f->d_data + f->bytes, 0, pad, f->ctx->active));
@@ -511,7 +566,7 @@ extern "C" int btlbf_filter_download(btlbf_filter* f, void* host, uint64_t nbyte
 		return fail(BTLBF_ERR_ARG, "download of %llu bytes from a %llu-byte filter", (unsigned long long)nbytes,
 		            (unsigned long long)f->bytes);
 	TRY(use(f->ctx));
-	CU(cudaMemcpyAsync(host, f->d_data, nbytes, cudaMemcpyDeviceToHost, f->ctx->active));
+	CU(cudaMemcpyAsync(host, f->d_data, nbytes, cudaMemcpyDeviceToHost, joined(f->ctx)));
 	CU(cudaStreamSynchronize(f->ctx->active));
 	return BTLBF_OK;
 }
@@ -531,7 +586,7 @@ static int reduce_count(btlbf_filter* f, int mode, unsigned threshold, uint64_t*
 		return fail(BTLBF_ERR_ARG, "null argument");
 	btlbf_ctx* ctx = f->ctx;
 	TRY(use(ctx));
-	CU(cudaMemsetAsync(ctx->d_scalars + 2, 0, 8, ctx->active));
+	CU(cudaMemsetAsync(ctx->d_scalars + 2, 0, 8, joined(ctx)));
 	cudaError_t e = launch_popcount(f->d_data, f->bytes, mode, threshold, ctx->d_scalars + 2, ctx->active);
 	if (e != cudaSuccess)
 		return fail(BTLBF_ERR_CUDA, "popcount launch failed: %s", cudaGetErrorString(e));
@@ -598,7 +653,7 @@ extern "C" int btlbf_filter_merge_from_device(btlbf_filter* f, const void* src_d
 	if ((uintptr_t)src_device & 15u)
 		return fail(BTLBF_ERR_ARG, "merge source must be 16-byte aligned");
 	TRY(use(f->ctx));
-	cudaError_t e = launch_merge(f->d_data, src_device, nbytes, f->kind == BTLBF_COUNTING8, f->ctx->active);
+	cudaError_t e = launch_merge(f->d_data, src_device, nbytes, f->kind == BTLBF_COUNTING8, joined(f->ctx));
 	if (e != cudaSuccess)
 		return fail(BTLBF_ERR_CUDA, "merge launch failed: %s", cudaGetErrorString(e));
 	f->ctx->launches++;
@@ -615,7 +670,7 @@ extern "C" int btlbf_merge_device_buffers(btlbf_ctx* ctx, int kind, void* dst_de
 		return fail(BTLBF_ERR_ARG, "null argument");
 	if (((uintptr_t)dst_device | (uintptr_t)src_device) & 15u)
 		return fail(BTLBF_ERR_ARG, "merge buffers must be 16-byte aligned");
-	cudaError_t e = launch_merge(dst_device, src_device, nbytes, kind == BTLBF_COUNTING8, ctx->active);
+	cudaError_t e = launch_merge(dst_device, src_device, nbytes, kind == BTLBF_COUNTING8, joined(ctx));
 	if (e != cudaSuccess)
 		return fail(BTLBF_ERR_CUDA, "merge launch failed: %s", cudaGetErrorString(e));
 	ctx->launches++;
@@ -766,7 +821,7 @@ static bool want_binned(const btlbf_filter* f, const SeqParams& P)
 }
 
 // partition geometry + sub-bucket storage shared by the partitioned build and query
-static int bin_setup(btlbf_filter* f, SeqParams& P, bool query, uint32_t* grid)
+static int bin_setup(btlbf_filter* f, SeqParams& P, bool query, uint32_t* grid, DevBuf& items, DevBuf& counts)
 {
 	btlbf_ctx* ctx = f->ctx;
 	uint32_t shift = (uint32_t)ctx->bin_part_log2;
@@ -790,10 +845,15 @@ static int bin_setup(btlbf_filter* f, SeqParams& P, bool query, uint32_t* grid)
 	if (cap > 0x7ffffff8ULL)
 		cap = 0x7ffffff8ULL;
 	P.bin_cap = (uint32_t)cap;
-	TRY(ensure(ctx->bin_items, n_bins * writers * cap * (query ? 8 : 4)));
-	TRY(ensure(ctx->bin_counts, n_bins * writers * 4));
-	P.bin_items = (uint32_t*)ctx->bin_items.p;
-	P.bin_counts = (uint32_t*)ctx->bin_counts.p;
+	if (n_bins * writers * cap * (query ? 8 : 4) > items.cap || n_bins * writers * 4 > counts.cap) {
+		// growing a buffer frees the old one: nothing in flight may still use it
+		CU(cudaStreamSynchronize(ctx->aux));
+		CU(cudaStreamSynchronize(ctx->active));
+	}
+	TRY(ensure(items, n_bins * writers * cap * (query ? 8 : 4)));
+	TRY(ensure(counts, n_bins * writers * 4));
+	P.bin_items = (uint32_t*)items.p;
+	P.bin_counts = (uint32_t*)counts.p;
 	return BTLBF_OK;
 }
 
@@ -801,12 +861,31 @@ static int binned_insert(btlbf_filter* f, SeqParams P, cudaStream_t s)
 {
 	btlbf_ctx* ctx = f->ctx;
 	uint32_t grid = 0;
-	TRY(bin_setup(f, P, false, &grid));
+	const int slot = ctx->bin_slot;
+	ctx->bin_slot ^= 1;
+	TRY(bin_setup(f, P, false, &grid, ctx->ibin_items[slot], ctx->ibin_counts[slot]));
+	// pass 1 (hash + bin) on the active stream; it may not overwrite sub-buckets pass 2 is still reading
+	if (ctx->slot_used[slot])
+		CU(cudaStreamWaitEvent(s, ctx->ev_apply_done[slot], 0));
 	cudaError_t e = launch_bin(P, false, grid, s);
-	if (e == cudaSuccess)
-		e = launch_apply_bins(P, s);
 	if (e != cudaSuccess)
-		return fail(BTLBF_ERR_CUDA, "partitioned build launch failed: %s", cudaGetErrorString(e));
+		return fail(BTLBF_ERR_CUDA, "partitioned build (pass 1) launch failed: %s", cudaGetErrorString(e));
+	// pass 2 (OR into the L2-resident partitions): in the background when overlapping, so that it runs
+	// under the next batch's pass 1; anything that touches the filter later waits for it (joined()).
+	cudaStream_t s2 = ctx->overlap ? ctx->aux : s;
+	if (ctx->overlap) {
+		CU(cudaEventRecord(ctx->ev_bin_done[slot], s));
+		CU(cudaStreamWaitEvent(s2, ctx->ev_bin_done[slot], 0));
+	}
+	e = launch_apply_bins(P, s2);
+	if (e != cudaSuccess)
+		return fail(BTLBF_ERR_CUDA, "partitioned build (pass 2) launch failed: %s", cudaGetErrorString(e));
+	CU(cudaEventRecord(ctx->ev_apply_done[slot], s2));
+	ctx->slot_used[slot] = true;
+	if (ctx->overlap) {
+		ctx->ev_aux_last = ctx->ev_apply_done[slot];
+		ctx->aux_pending = true;
+	}
 	ctx->launches += 2;
 	ctx->binned_launches++;
 	return BTLBF_OK;
@@ -833,7 +912,7 @@ static int binned_query(btlbf_filter* f, SeqParams P, cudaStream_t s)
 {
 	btlbf_ctx* ctx = f->ctx;
 	uint32_t grid = 0;
-	TRY(bin_setup(f, P, true, &grid));
+	TRY(bin_setup(f, P, true, &grid, ctx->qbin_items, ctx->qbin_counts));
 	const uint64_t words = P.out_words;
 	if (!P.hit_bits) {
 		TRY(ensure(ctx->q_hit, words * 4));
@@ -845,9 +924,11 @@ static int binned_query(btlbf_filter* f, SeqParams P, cudaStream_t s)
 	}
 	uint64_t* stats = P.stats;
 	CU(cudaMemsetAsync(P.hit_bits, 0xff, words * 4, s));
-	cudaError_t e = launch_bin(P, true, grid, s);
-	if (e == cudaSuccess)
+	cudaError_t e = launch_bin(P, true, grid, s); // does not read the filter (bar overflow): may run under a pending pass 2
+	if (e == cudaSuccess) {
+		joined(ctx);
 		e = launch_probe_bins(P, s);
+	}
 	if (e == cudaSuccess)
 		e = launch_finalize_hits(P.hit_bits, P.valid_bits, words, stats ? (unsigned long long*)(stats + 1) : nullptr, s);
 	if (e != cudaSuccess)
@@ -898,6 +979,10 @@ static int filter_op_dev(btlbf_filter* f, PublicOp op, const ChunkIO& io, cudaSt
 	SeqParams P = filter_params(f);
 	fill_io(P, io);
 	btlbf_ctx* ctx = f->ctx;
+	const bool binned = f->kind == BTLBF_BLOOM && P.n_windows &&
+	                    ((op == PUB_INSERT && want_binned(f, P)) || (op == PUB_CONTAINS && want_binned_query(f, P)));
+	if (!binned)
+		joined(ctx); // the direct kernels read / write the filter right away
 	switch (op) {
 	case PUB_INSERT:
 		if (f->kind == BTLBF_BLOOM) {
@@ -1268,7 +1353,7 @@ static int hashes_op(btlbf_filter* f, int op, const uint64_t* hashes, uint64_t n
 		return fail(BTLBF_ERR_ARG, "null hashes");
 	btlbf_ctx* ctx = f->ctx;
 	TRY(use(ctx));
-	cudaStream_t s = ctx->active;
+	cudaStream_t s = joined(ctx);
 	Slot& sl = ctx->slot[0];
 	uint32_t h = f->hc.h;
 	TRY(ensure(sl.hashes, n * h * 8));
@@ -1461,7 +1546,7 @@ extern "C" int btlbf_filter_store(btlbf_filter* f, const char* path, double dFPR
 	cudaError_t e = cudaHostAlloc(&bounce, bsz ? bsz : 1, cudaHostAllocDefault);
 	for (uint64_t off = 0; ok && e == cudaSuccess && off < f->bytes; off += CH) {
 		size_t n = f->bytes - off < CH ? (size_t)(f->bytes - off) : CH;
-		e = cudaMemcpyAsync(bounce, f->d_data + off, n, cudaMemcpyDeviceToHost, ctx->active);
+		e = cudaMemcpyAsync(bounce, f->d_data + off, n, cudaMemcpyDeviceToHost, joined(ctx));
 		if (e == cudaSuccess)
 			e = cudaStreamSynchronize(ctx->active);
 		if (e == cudaSuccess)
@@ -1525,7 +1610,7 @@ extern "C" int btlbf_filter_load(btlbf_ctx* ctx, const char* path, int kind, uns
 		size_t n = body - off < CH ? (size_t)(body - off) : CH;
 		ok = fread(bounce, 1, n, fp) == n;
 		if (ok)
-			e = cudaMemcpyAsync(f->d_data + off, bounce, n, cudaMemcpyHostToDevice, ctx->active);
+			e = cudaMemcpyAsync(f->d_data + off, bounce, n, cudaMemcpyHostToDevice, joined(ctx));
 		if (ok && e == cudaSuccess)
 			e = cudaStreamSynchronize(ctx->active);
 	}

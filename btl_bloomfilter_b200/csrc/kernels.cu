@@ -65,8 +65,8 @@ __global__ void __launch_bounds__(kTPB) seq_kernel(const __grid_constant__ SeqPa
 // ---------------------------------------------------------------- partitioned build, pass 1
 // Persistent CTAs.  Every WARP is the only writer of its own sub-bucket of each filter partition:
 //   * the warp's append cursors and one 32-byte staging line per partition live in shared memory;
-//   * the 32 bit indices a warp produces per step are ranked inside the warp with ballots (lanes that hit
-//     the same partition get consecutive positions; one lane bumps the cursor) -- no atomics;
+//   * lanes that hit the same partition in one step are serialised by an optimistic claim on the cursor
+//     word (warp_bin_emit) -- no atomics;
 //   * offsets are written to the staging line and leave for HBM as whole 32-byte sectors.
 // Shared memory per warp: n_bins * 36 bytes, so this kernel serves n_bins <= kMaxWarpBins; filters with
 // more partitions use bin_kernel_cta below (CTA-shared cursors, shared-memory atomics, 4-byte stores).
@@ -117,46 +117,40 @@ __device__ __forceinline__ void bin_flush_line(const SeqParams& P, const WarpBin
 	}
 }
 
-// warp-synchronous: every lane of the warp calls this the same number of times
+// warp-synchronous: every lane of the warp calls this the same number of times.
+// Appends one item per active lane to the warp's sub-buckets.  Lanes that target the same partition are
+// serialised by an optimistic claim on the partition's cursor word (count << 5 | claiming lane): all
+// pending lanes read the word, all write count+1 tagged with their lane, and the lane whose tag survived
+// owns position `count`; the others retry against the updated word.  With 32 lanes over a few hundred
+// partitions this takes two rounds on average and needs no atomics, ballots or match instructions.
 template<bool QUERY>
 __device__ __forceinline__ void warp_bin_emit(const SeqParams& P, const WarpBins& wb, uint64_t n, uint32_t wid, bool active)
 {
-	constexpr uint32_t L = QUERY ? 4u : 8u, LOG_L = QUERY ? 2u : 3u; // items per 32-byte line
+	constexpr uint32_t L = QUERY ? 4u : 8u; // items per 32-byte line
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t part = (uint32_t)(n >> P.bin_shift);
 	const uint32_t off = (uint32_t)n & P.bin_mask;
-	uint32_t peers = __ballot_sync(kFullMask, active);
-	if (peers == 0)
-		return;
-	for (uint32_t bit = 0; bit < wb.nbits; bit++) {
-		uint32_t mine = (part >> bit) & 1u;
-		uint32_t v = __ballot_sync(kFullMask, mine);
-		peers &= mine ? v : ~v;
-	}
-	const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-	uint32_t c = 0;
-	if (active && rank == 0) {
-		c = wb.cursor[part];
-		wb.cursor[part] = c + __popc(peers);
-	}
-	c = __shfl_sync(kFullMask, c, active ? (uint32_t)(__ffs(peers) - 1) : lane);
-	const uint32_t pos = c + rank;
-	const uint32_t round = (pos >> LOG_L) - (c >> LOG_L); // lines this partition advances before my slot is free
+	uint32_t* cur = wb.cursor + part;
 	bool pending = active;
-	for (uint32_t r = 0; __any_sync(kFullMask, pending); r++) {
-		const bool now = pending && round == r;
-		if (now) {
+	while (__any_sync(kFullMask, pending)) {
+		uint32_t c = 0;
+		if (pending)
+			c = *cur;
+		__syncwarp(); // every read of this round precedes every write
+		if (pending)
+			*cur = ((c & ~31u) + 32u) | lane;
+		__syncwarp();
+		if (pending && (*cur & 31u) == lane) {
+			const uint32_t pos = c >> 5;
 			if (QUERY)
 				*reinterpret_cast<uint2*>(wb.line + part * 8 + (pos & (L - 1)) * 2) = make_uint2(off, wid);
 			else
 				wb.line[part * 8 + (pos & (L - 1))] = off;
-		}
-		__syncwarp();
-		if (now && (pos & (L - 1)) == L - 1)
-			bin_flush_line<QUERY>(P, wb, part, pos - (L - 1));
-		__syncwarp();
-		if (now)
+			if ((pos & (L - 1)) == L - 1) // the line is complete (earlier slots were filled in earlier rounds)
+				bin_flush_line<QUERY>(P, wb, part, pos - (L - 1));
 			pending = false;
+		}
+		__syncwarp(); // line contents are visible to whoever completes the line next
 	}
 }
 
@@ -210,7 +204,7 @@ __global__ void __launch_bounds__(kTPB) bin_kernel_warp(const __grid_constant__ 
 	// drain the partial lines and publish the cursors
 	__syncwarp();
 	for (uint32_t part = lane; part < nb; part += 32) {
-		const uint32_t c = wb.cursor[part], start = c & ~(L - 1);
+		const uint32_t c = wb.cursor[part] >> 5, start = c & ~(L - 1);
 		const uint64_t item0 = ((uint64_t)part * P.bin_writers + wb.writer) * P.bin_cap + start;
 		for (uint32_t i = 0; i < (c & (L - 1)); i++) {
 			if (QUERY) {
@@ -373,6 +367,9 @@ static cudaError_t bin_occupancy(const SeqParams& P, uint32_t n_bins, bool query
 		if (e != cudaSuccess)
 			return e;
 	}
+	// same L1/shared split as the pass-2 kernels, so that the two passes can share an SM (kernels that ask
+	// for different carve-outs cannot be co-resident)
+	cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 	*smem_out = smem;
 	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, kTPB, smem);
 }
@@ -482,6 +479,7 @@ cudaError_t launch_apply_bins(const SeqParams& P, cudaStream_t stream)
 		return cudaSuccess;
 	if (grid > 0x7fffffffULL)
 		return cudaErrorInvalidValue;
+	cudaFuncSetAttribute(apply_bins_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 	apply_bins_kernel<<<(unsigned)grid, kApplyThreads, 0, stream>>>(P, bpp);
 	return cudaGetLastError();
 }

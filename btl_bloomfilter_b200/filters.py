@@ -111,6 +111,16 @@ class Context:
     def sync(self):
         check(self.L.btlbf_ctx_sync(self.handle))
 
+    def flush(self):
+        """Order the active stream after the background (pass 2 of the partitioned build) stream."""
+        check(self.L.btlbf_ctx_flush(self.handle))
+
+    @property
+    def aux_stream(self):
+        p = C.c_void_p()
+        check(self.L.btlbf_ctx_aux_stream(self.handle, C.byref(p)))
+        return p.value
+
     @property
     def launch_count(self):
         n = C.c_uint64()
