@@ -75,11 +75,27 @@ constexpr uint32_t kFullMask = 0xffffffffu;
 
 struct WarpBins
 {
-	uint32_t* cursor; // [n_bins] offsets appended so far by this warp
-	uint32_t* line;   // [n_bins][8] current partial line
-	uint32_t writer;  // global warp index
-	uint32_t nbits;   // ceil(log2(n_bins))
+	uint32_t* cursor;   // [n_bins] cursor words of this warp: items appended so far << kTagBits | claimant tag
+	uint32_t* line;     // [n_bins][8] current partial line
+	uint32_t cursor_sa; // the same two arrays as shared-window byte addresses (cheap addressing in the hot loop)
+	uint32_t line_sa;
+	uint32_t writer;    // global warp index
 };
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t sa)
+{
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa) : "memory");
+	return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t sa, uint32_t v)
+{
+	asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u64(uint32_t sa, uint32_t lo, uint32_t hi)
+{
+	asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sa), "r"(lo), "r"(hi) : "memory");
+}
 
 __device__ __forceinline__ void bin_direct_or(const SeqParams& P, uint32_t part, uint32_t off)
 {
@@ -119,10 +135,12 @@ __device__ __forceinline__ void bin_flush_line(const SeqParams& P, const WarpBin
 
 // warp-synchronous: every lane of the warp calls this the same number of times.
 // Appends one item per active lane to the warp's sub-buckets.  Lanes that target the same partition are
-// serialised by an optimistic claim on the partition's cursor word (count << 5 | claiming lane): all
-// pending lanes read the word, all write count+1 tagged with their lane, and the lane whose tag survived
-// owns position `count`; the others retry against the updated word.  With 32 lanes over a few hundred
-// partitions this takes two rounds on average and needs no atomics, ballots or match instructions.
+// serialised by an optimistic claim on the partition's cursor word (count << kTagBits | claiming lane):
+// all pending lanes read the word, all write count+1 tagged with their lane, and the lane whose tag
+// survived owns position `count`; the others retry against the updated word.  With 32 lanes over a few
+// hundred partitions this takes two rounds on average and needs no atomics, ballots or match instructions.
+constexpr uint32_t kTagBits = 5, kTagMask = (1u << kTagBits) - 1u;
+
 template<bool QUERY>
 __device__ __forceinline__ void warp_bin_emit(const SeqParams& P, const WarpBins& wb, uint64_t n, uint32_t wid, bool active)
 {
@@ -130,27 +148,28 @@ __device__ __forceinline__ void warp_bin_emit(const SeqParams& P, const WarpBins
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t part = (uint32_t)(n >> P.bin_shift);
 	const uint32_t off = (uint32_t)n & P.bin_mask;
-	uint32_t* cur = wb.cursor + part;
+	const uint32_t cur = wb.cursor_sa + part * 4u;
 	bool pending = active;
 	while (__any_sync(kFullMask, pending)) {
 		uint32_t c = 0;
 		if (pending)
-			c = *cur;
+			c = lds_u32(cur);
 		__syncwarp(); // every read of this round precedes every write
 		if (pending)
-			*cur = ((c & ~31u) + 32u) | lane;
+			sts_u32(cur, ((c & ~kTagMask) + (kTagMask + 1u)) | lane);
 		__syncwarp();
-		if (pending && (*cur & 31u) == lane) {
-			const uint32_t pos = c >> 5;
+		if (pending && (lds_u32(cur) & kTagMask) == lane) {
+			const uint32_t pos = c >> kTagBits;
 			if (QUERY)
-				*reinterpret_cast<uint2*>(wb.line + part * 8 + (pos & (L - 1)) * 2) = make_uint2(off, wid);
+				sts_u64(wb.line_sa + part * 32u + (pos & (L - 1)) * 8u, off, wid);
 			else
-				wb.line[part * 8 + (pos & (L - 1))] = off;
-			if ((pos & (L - 1)) == L - 1) // the line is complete (earlier slots were filled in earlier rounds)
+				sts_u32(wb.line_sa + part * 32u + (pos & (L - 1)) * 4u, off);
+			// the item that completes a line stores it: its other slots were filled in earlier rounds (at
+			// most one item per partition is placed per round, and two warp barriers separate the rounds)
+			if ((pos & (L - 1)) == L - 1)
 				bin_flush_line<QUERY>(P, wb, part, pos - (L - 1));
 			pending = false;
 		}
-		__syncwarp(); // line contents are visible to whoever completes the line next
 	}
 }
 
@@ -169,8 +188,9 @@ __global__ void __launch_bounds__(kTPB) bin_kernel_warp(const __grid_constant__ 
 	WarpBins wb;
 	wb.cursor = cur_all + warp * nb8;
 	wb.line = line_all + (size_t)warp * nb8 * 8;
+	wb.cursor_sa = (uint32_t)__cvta_generic_to_shared(wb.cursor);
+	wb.line_sa = (uint32_t)__cvta_generic_to_shared(wb.line);
 	wb.writer = blockIdx.x * (kTPB / 32) + warp;
-	wb.nbits = 32 - __clz(nb > 1 ? nb - 1 : 1);
 	for (uint32_t i = lane; i < nb; i += 32)
 		wb.cursor[i] = 0;
 	__syncwarp();
@@ -187,8 +207,9 @@ __global__ void __launch_bounds__(kTPB) bin_kernel_warp(const __grid_constant__ 
 		const uint32_t p0 = (uint32_t)tid * kWPT;
 		roll_windows(P, sm, t0, tid, [&](uint32_t s, bool ok, uint64_t F, uint64_t RC) {
 			validw |= (uint32_t)ok << s;
+			const uint32_t wid = (uint32_t)t0 + p0 + s;
 			for_each_hash<SPACED>(P, sm, p0 + s, F, RC, [&](uint32_t, uint64_t hv, bool) {
-				warp_bin_emit<QUERY>(P, wb, fastmod<POW2>(hv, P.fm), (uint32_t)t0 + p0 + s, ok);
+				warp_bin_emit<QUERY>(P, wb, fastmod<POW2>(hv, P.fm), wid, ok);
 				return true;
 			});
 		});
@@ -204,7 +225,7 @@ __global__ void __launch_bounds__(kTPB) bin_kernel_warp(const __grid_constant__ 
 	// drain the partial lines and publish the cursors
 	__syncwarp();
 	for (uint32_t part = lane; part < nb; part += 32) {
-		const uint32_t c = wb.cursor[part] >> 5, start = c & ~(L - 1);
+		const uint32_t c = wb.cursor[part] >> kTagBits, start = c & ~(L - 1);
 		const uint64_t item0 = ((uint64_t)part * P.bin_writers + wb.writer) * P.bin_cap + start;
 		for (uint32_t i = 0; i < (c & (L - 1)); i++) {
 			if (QUERY) {
