@@ -373,12 +373,14 @@ def main():
               "peak": peak, "unit": "GB/s", "bytes_per_kmer": 32 * H + 1, "kmers_per_launch": k_qry / S,
               "launch_ms": qry_ms, "gkmers_s": k_qry / S / (qry_ms * 1e-3) / 1e9}
     roof_q["frac"] = roof_q["achieved"] / peak
-    prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(prof):
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this
+    # same command (profiles/r1_dram_bytes_per_launch.json, written by tools/summarize_ncu.py)
+    prof = os.path.join(ROOT, "profiles", "r1_dram_bytes_per_launch.json")
+    if os.path.exists(prof) and chunk == CHUNK and not args.opt:
         try:
             t = json.load(open(prof))
-            roof["traffic"] = t.get("bf_insert_dram_bytes_per_launch")
-            roof_q["traffic"] = t.get("bf_contains_dram_bytes_per_launch")
+            roof["traffic"] = t["void bin_kernel_warp<0, 0, 0>"] + t["apply_bins_kernel"]
+            roof_q["traffic"] = t["void bin_kernel_warp<0, 0, 1>"] + t["probe_bins_kernel"] + t["finalize_hits_kernel"]
         except Exception:
             pass
     line = {"metric": "k-mers/s inserted+queried", "value": (k_ins_all + k_qry_all) / (ms_total * 1e-3) / 1e9,

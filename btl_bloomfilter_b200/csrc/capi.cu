@@ -79,12 +79,12 @@ struct btlbf_ctx
 	int bin_slot = 0;
 	cudaEvent_t ev_aux_last = nullptr; // last event recorded on aux (one of ev_apply_done)
 	bool aux_pending = false;          // the active stream has not been ordered after ev_aux_last yet
-	int64_t overlap = 1;
+	int64_t overlap = 0; // 1: run pass 2 of the partitioned build on the background stream
 	uint64_t launches = 0;
 	unsigned long long* d_scalars = nullptr; // 16 device words: [0..1] stats, [2] popcount, [4..7] list counters
 	unsigned long long* h_scalars = nullptr; // pinned mirror
 	int64_t force_generic = 0, query_mode = 0;
-	int64_t chunk_bases = (int64_t)32 << 20; // windows per pipeline stage of the host-buffer calls
+	int64_t chunk_bases = (int64_t)64 << 20; // windows per pipeline stage of the host-buffer calls
 	int64_t cbf_batch = (int64_t)1 << 20;    // windows per batch of the ordered (exact) updates
 	int64_t resv_log2 = 28, list_log2 = 22;
 	int64_t drain_threshold = 4096;

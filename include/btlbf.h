@@ -73,11 +73,11 @@ int btlbf_ctx_destroy(btlbf_ctx *ctx);
  * NULL restores the context's own stream. */
 int btlbf_ctx_set_stream(btlbf_ctx *ctx, void *cuda_stream);
 int btlbf_ctx_sync(btlbf_ctx *ctx);
-/* The second pass of the partitioned BloomFilter build runs on a background stream so that it overlaps
- * the next batch's first pass.  Every btlbf_* call that touches the filter orders itself after it, and so
- * does btlbf_ctx_sync.  btlbf_ctx_flush makes the ACTIVE stream wait for the background work without
- * blocking the host: call it before you let other work on that stream (or an event recorded on it) depend
- * on filter contents.  Option "overlap" = 0 keeps everything on the active stream. */
+/* With option "overlap" = 1 the second pass of the partitioned BloomFilter build runs on a background
+ * stream so that it can overlap the next batch's first pass (default 0: everything on the active stream).
+ * Every btlbf_* call that touches the filter orders itself after the background work, and so does
+ * btlbf_ctx_sync.  btlbf_ctx_flush makes the ACTIVE stream wait for it without blocking the host: call it
+ * before other work on that stream (or an event recorded on it) depends on filter contents. */
 int btlbf_ctx_flush(btlbf_ctx *ctx);
 int btlbf_ctx_aux_stream(btlbf_ctx *ctx, void **cuda_stream); /* the background cudaStream_t (for timing) */
 /* number of kernels this context has launched so far (for accounting / tests) */
