@@ -106,7 +106,15 @@ class Context:
         check(self.L.btlbf_ctx_set_option(self.handle, key.encode(), int(value)))
 
     def set_stream(self, cuda_stream):
-        check(self.L.btlbf_ctx_set_stream(self.handle, C.c_void_p(cuda_stream or 0)))
+        """Run the context's kernels on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream).
+        None restores the context's own stream; 0 means the legacy default stream (cudaStreamLegacy)."""
+        if cuda_stream is None:
+            ptr = 0
+        elif cuda_stream == 0:
+            ptr = 1  # cudaStreamLegacy: a NULL handle would mean "the context's own stream" to the C ABI
+        else:
+            ptr = cuda_stream
+        check(self.L.btlbf_ctx_set_stream(self.handle, C.c_void_p(ptr)))
 
     def sync(self):
         check(self.L.btlbf_ctx_sync(self.handle))

@@ -70,7 +70,7 @@ int btlbf_device_count(int *count);
 int btlbf_ctx_create(int device, btlbf_ctx **ctx);
 int btlbf_ctx_destroy(btlbf_ctx *ctx);
 /* Run all kernels of this context on a caller-owned cudaStream_t (e.g. torch's current stream);
- * NULL restores the context's own stream. */
+ * NULL restores the context's own stream (pass cudaStreamLegacy / cudaStreamPerThread for the default streams). */
 int btlbf_ctx_set_stream(btlbf_ctx *ctx, void *cuda_stream);
 int btlbf_ctx_sync(btlbf_ctx *ctx);
 /* With option "overlap" = 1 the second pass of the partitioned BloomFilter build runs on a background

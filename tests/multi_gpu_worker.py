@@ -1,0 +1,79 @@
+"""Worker of tests/test_multi_gpu.py (launched by torch.distributed.run, one rank per GPU): read-sharded
+build into per-GPU partial filters + NCCL merge, and read-sharded query against the replicated filter,
+checked against the oracle on every rank."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+import _oracle as O  # noqa: E402
+import btl_bloomfilter_b200 as B  # noqa: E402
+from btl_bloomfilter_b200 import parallel  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    orc = O.Oracle()
+    ctx = B.Context(local)
+    k, h = 25, 4
+    n_reads, rl, g_len = 6000, 150, 400_000
+    reads = orc.synth_reads(0, n_reads, rl, g_len, 42, 5)
+    off = (rl * np.arange(n_reads + 1)).astype(np.uint64)
+    lo, hi = parallel.shard_range(n_reads, rank, world)
+    my = (reads[lo * rl:hi * rl], off[lo:hi + 1] - off[lo])
+
+    # ---- BloomFilter: partial builds + OR merge == single build of all reads (bit-exact for any sharding)
+    bits = 8 * 300_007 * 8  # not a power of two, not a multiple of the slice size
+    nbytes = bits // 8
+    t = torch.zeros(parallel.padded_bytes(nbytes, world), dtype=torch.uint8, device=dev)
+    f = B.BloomFilter.from_device_memory(t, bits, h, k, ctx=ctx)
+    f.insertSeqs(my)
+    parallel.merge_filter(f)
+    torch.cuda.synchronize()
+    filt = np.zeros(nbytes, np.uint8)
+    orc.bf_insert_seqs(filt, bits, h, k, reads, off)
+    got = f.to_numpy()
+    assert np.array_equal(got, filt), "rank %d: merged BloomFilter differs from the single-build oracle" % rank
+    assert not t[nbytes:].any()
+
+    # ---- query: filter replicated (after the merge), reads sharded, no collective
+    r = f.containsSeqs(my)
+    nq, nh, hits, valid = orc.bf_contains_seqs(filt, bits, h, k, my[0], my[1])
+    assert (r.n_kmers, r.n_hits) == (nq, nh) and np.array_equal(r.hit_bits, hits)
+    miss = orc.synth_genome(rank * 50_000, 50_000, 43 << 40)
+    r = f.containsSeqs((miss, np.array([0, miss.size], np.uint64)))
+    e = orc.bf_contains_seqs(filt, bits, h, k, miss, np.array([0, miss.size], np.uint64))
+    assert (r.n_kmers, r.n_hits) == e[:2] and np.array_equal(r.hit_bits, e[2])
+
+    # ---- CountingBloomFilter: partial incrementMin builds + saturating add; oracle = the same sharded algorithm
+    m = 100_008
+    tc = torch.zeros(parallel.padded_bytes(m, world), dtype=torch.uint8, device=dev)
+    c = B.CountingBloomFilter.from_device_memory(tc, m, h, k, threshold=2, ctx=ctx)
+    c.insertSeqs(my)
+    parallel.merge_filter(c)
+    torch.cuda.synchronize()
+    exp = np.zeros(m, np.int32)
+    for rr in range(world):
+        a, b = parallel.shard_range(n_reads, rr, world)
+        part = np.zeros(m, np.uint8)
+        orc.cbf_insert_seqs(part, m, h, k, reads[a * rl:b * rl], off[a:b + 1] - off[a])
+        exp += part
+    exp = np.minimum(exp, 255).astype(np.uint8)
+    assert np.array_equal(c.to_numpy(), exp), "rank %d: merged counters differ" % rank
+    dist.barrier()
+    if rank == 0:
+        print("MULTI-GPU OK world=%d" % world)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
