@@ -134,6 +134,17 @@ BTL_HD uint64_t fastmod(uint64_t x, const FastMod& f)
 {
 	if (POW2)
 		return x & f.magic;
+	if ((f.magic >> 32) == 0) {
+		// m > 2^32 (every filter beyond 512 MiB): the reciprocal and the quotient fit in 32 bits, so the
+		// 64x64 high product and q*m shrink to three 32x32->64 multiplies
+		const uint32_t mg = (uint32_t)f.magic;
+		uint64_t lo = (uint64_t)(uint32_t)x * mg;
+		uint64_t hi = (uint64_t)(uint32_t)(x >> 32) * mg + (lo >> 32);
+		uint32_t q = (uint32_t)(hi >> 32);
+		uint64_t qm = (uint64_t)q * (uint32_t)f.m + ((uint64_t)(q * (uint32_t)(f.m >> 32)) << 32);
+		uint64_t r = x - qm;
+		return r >= f.m ? r - f.m : r;
+	}
 	uint64_t q = mulhi64(x, f.magic);
 	uint64_t r = x - q * f.m;
 	return r >= f.m ? r - f.m : r;

@@ -286,3 +286,17 @@ int emu_seq_op(int pub_op, int kind, uint64_t size, unsigned h, unsigned k, unsi
 }
 
 } // extern "C"
+
+// ---- arithmetic helpers of nthash_dev.cuh exposed for tests/test_host_arith.py
+extern "C" {
+uint64_t emu_fastmod(uint64_t x, uint64_t m)
+{
+	FastMod f = make_fastmod(m);
+	return f.pow2 ? fastmod<true>(x, f) : fastmod<false>(x, f);
+}
+uint64_t emu_srol(uint64_t v) { return srol(v); }
+uint64_t emu_sror(uint64_t v) { return sror(v); }
+uint64_t emu_srol_n(uint64_t v, unsigned n) { return srol_n(v, n); }
+uint64_t emu_multi_mix(uint64_t b, unsigned i, unsigned k) { return multi_mix(b, multi_mult(i, k)); }
+uint64_t emu_class_seeds(unsigned c, int rev) { uint8_t cls = base_class(c); return rev ? class_rseed(cls) : class_fseed(cls); }
+}
