@@ -295,6 +295,10 @@ def main():
     assert k_hit == k_qry, "a k-mer of an inserted chunk was not found (%d of %d)" % (k_hit, k_qry)
 
     # ---- end to end through the host-buffer C ABI (pinned inputs; H2D, kernels and D2H inside the timed region)
+    # Streaming form (btlbf_insert_seqs_async / btlbf_contains_seqs_async): every step copies its genome chunk
+    # and reads host->device, runs the kernels and copies the hit bits + counts device->host; the calls are
+    # queued back to back, so the copies of one step overlap the kernels of another, and the results are
+    # checked after the final btlbf_ctx_sync.  "e2e_sync" is the same with the blocking calls.
     e2e = None
     if not args.no_e2e:
         n_host = min(n_buf, 4)
@@ -303,46 +307,68 @@ def main():
         for j in range(n_host):
             h_genome[j].copy_(d_genome[j][: g_lens[j]])
             h_reads[j].copy_(d_reads[j][:read_bases])
-        h_hits = torch.zeros((read_bases + 31) // 32 * 4, dtype=torch.uint8).pin_memory()
-        h_roff = np.arange(0, read_bases + 1, READ_LEN, dtype=np.uint64)
+        h_hits = [torch.zeros((read_bases + 31) // 32 * 4, dtype=torch.uint8).pin_memory() for _ in range(n_host)]
+        t_roff = torch.arange(0, read_bases + 1, READ_LEN, dtype=torch.int64).pin_memory()
+        h_roff = t_roff.numpy().view(np.uint64)
+        t_goff = [torch.tensor([0, g_lens[j]], dtype=torch.int64).pin_memory() for j in range(n_host)]
+        h_goff = [t.numpy().view(np.uint64) for t in t_goff]
+        S2 = min(S, 16)
+        h_counts = torch.zeros((S2 + 4, 4), dtype=torch.int64).pin_memory()
+        counts = h_counts.numpy().view(np.uint64)
         torch.cuda.synchronize()
 
-        def step_host(i):
+        def step_host_sync(i):
             j = i % n_host
-            gl = g_lens[j]
-            a = filt.insertSeqs((h_genome[j].numpy(), np.array([0, gl], np.uint64)))
-            r = filt.containsSeqs((h_reads[j].numpy(), h_roff), hit_out=h_hits.numpy(), want_valid=False)
+            a = filt.insertSeqs((h_genome[j].numpy(), h_goff[j]))
+            r = filt.containsSeqs((h_reads[j].numpy(), h_roff), hit_out=h_hits[j].numpy(), want_valid=False)
             return a, r.n_kmers, r.n_hits
 
+        def step_host_async(i, slot):
+            j = i % n_host
+            filt.insertSeqsAsync((h_genome[j].numpy(), h_goff[j]), counts[slot, 0:2])
+            filt.containsSeqsAsync((h_reads[j].numpy(), h_roff), h_hits[j].numpy(), counts[slot, 2:4])
+
         for i in range(min(W, 2)):
-            step_host(i)
-        S2 = min(S, 12)
+            step_host_sync(i)
+        for i in range(2):
+            step_host_async(i, S2 + i)
+        ctx.sync()
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        ke = 0
         for i in range(S2):
-            a, q, hq = step_host(i)
-            assert hq == q
-            ke += a + q
-        torch.cuda.synchronize()
+            step_host_async(i, i)
+        ctx.sync()
         dt = time.perf_counter() - t0
         barrier()
-        e2e = {"kmers": ke, "seconds": dt, "steps": S2,
+        ke = int(counts[:S2, 0].sum() + counts[:S2, 2].sum())
+        assert np.array_equal(counts[:S2, 2], counts[:S2, 3]) and counts[:S2, 2].all(), "e2e: a queried k-mer was not found"
+        S3 = min(S, 6)
+        t0 = time.perf_counter()
+        ks = 0
+        for i in range(S3):
+            a, q, hq = step_host_sync(i)
+            assert hq == q
+            ks += a + q
+        dts = time.perf_counter() - t0
+        barrier()
+        e2e = {"kmers": ke, "seconds": dt, "steps": S2, "kmers_sync": ks, "seconds_sync": dts, "steps_sync": S3,
                "h2d": int(np.mean(g_lens[:n_host])) + read_bases + (n_reads + 1) * 8 + 16,
-               "d2h": int(h_hits.numel()) + 32}
+               "d2h": int(h_hits[0].numel()) + 32}
 
     # ---- reductions over ranks (max time, summed work)
     if world > 1:
-        t = torch.tensor([ms_total, ms_insert, ms_query, e2e["seconds"] if e2e else 0.0], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms_total, ms_insert, ms_query, e2e["seconds"] if e2e else 0.0,
+                          e2e["seconds_sync"] if e2e else 0.0], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, ms_insert, ms_query = float(t[0]), float(t[1]), float(t[2])
-        w = torch.tensor([k_ins, k_qry, e2e["kmers"] if e2e else 0, launches], dtype=torch.int64, device=dev)
+        w = torch.tensor([k_ins, k_qry, e2e["kmers"] if e2e else 0, launches, e2e["kmers_sync"] if e2e else 0],
+                         dtype=torch.int64, device=dev)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        k_ins_all, k_qry_all, ke_all, launches_all = [int(x) for x in w]
+        k_ins_all, k_qry_all, ke_all, launches_all, ks_all = [int(x) for x in w]
         if e2e:
-            e2e["seconds"] = float(t[3])
-            e2e["kmers"] = ke_all
+            e2e["seconds"], e2e["seconds_sync"] = float(t[3]), float(t[4])
+            e2e["kmers"], e2e["kmers_sync"] = ke_all, ks_all
     else:
         k_ins_all, k_qry_all, launches_all = k_ins, k_qry, launches
 
@@ -391,7 +417,10 @@ def main():
             "roofline": roof, "roofline_query": roof_q, "gpu_launches": launches_all, "clocks": clocks}
     if e2e:
         line["e2e"] = {"value": e2e["kmers"] / e2e["seconds"] / 1e9, "unit": "Gk-mer/s", "steps": e2e["steps"],
-                       "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"]}
+                       "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                       "api": "btlbf_insert_seqs_async + btlbf_contains_seqs_async (streaming), pinned host buffers"}
+        line["e2e_sync"] = {"value": e2e["kmers_sync"] / e2e["seconds_sync"] / 1e9, "unit": "Gk-mer/s",
+                            "steps": e2e["steps_sync"], "api": "btlbf_insert_seqs + btlbf_contains_seqs (blocking)"}
     if merge:
         line["merge"] = merge
     if world == 1 and not args.no_cpu_baseline:

@@ -47,6 +47,8 @@ SIGNATURES = {
     "btlbf_filter_ordered_stats": [vp, u64p, u64p],
     "btlbf_insert_seqs": [vp, vp, u64p, u64, u64p],
     "btlbf_contains_seqs": [vp, vp, u64p, u64, vp, vp, u64p, u64p],
+    "btlbf_insert_seqs_async": [vp, vp, u64p, u64, vp],
+    "btlbf_contains_seqs_async": [vp, vp, u64p, u64, vp, vp, vp],
     "btlbf_insert_and_check_seqs": [vp, vp, u64p, u64, vp, vp, u64p],
     "btlbf_mincount_seqs": [vp, vp, u64p, u64, vp, vp, u64p],
     "btlbf_increment_all_seqs": [vp, vp, u64p, u64, u64p],

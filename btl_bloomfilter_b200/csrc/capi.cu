@@ -57,6 +57,15 @@ struct Slot // one stage of the host-buffer pipeline (H2D copy | kernel | D2H co
 	bool used = false;
 };
 
+struct Ticket // per-call state of the host-buffer pipeline (several calls may be in flight)
+{
+	DevBuf offsets;
+	unsigned long long* d_stats = nullptr; // {n_kmers, n_hits}
+	cudaEvent_t done = nullptr;
+	bool in_use = false;
+};
+constexpr int kTickets = 4;
+
 struct HashCfg // everything the kernels need to turn a window into its hashes
 {
 	uint32_t k = 0, h = 0, n_seeds = 0, h2 = 0;
@@ -93,7 +102,9 @@ struct btlbf_ctx
 	int64_t bin_slack_pct = 20;
 	int64_t bin_query_mode = 0; // partitioned query: 0 auto, 1 always (when supported), -1 never
 	Slot slot[2];
-	DevBuf offsets, ibin_items[2], ibin_counts[2], qbin_items, qbin_counts, q_hit, q_valid;
+	Ticket ticket[kTickets];
+	uint64_t slot_seq = 0, ticket_seq = 0;
+	DevBuf ibin_items[2], ibin_counts[2], qbin_items, qbin_counts, q_hit, q_valid;
 	uint64_t binned_launches = 0;
 };
 
@@ -276,6 +287,11 @@ extern "C" int btlbf_ctx_create(int device, btlbf_ctx** out)
 		e = cudaMemset(ctx->d_scalars, 0, 16 * sizeof(unsigned long long));
 	if (e == cudaSuccess)
 		e = cudaHostAlloc(&ctx->h_scalars, 16 * sizeof(unsigned long long), cudaHostAllocDefault);
+	for (int i = 0; i < kTickets && e == cudaSuccess; i++) {
+		e = cudaEventCreateWithFlags(&ctx->ticket[i].done, cudaEventDisableTiming);
+		if (e == cudaSuccess)
+			e = cudaMalloc(&ctx->ticket[i].d_stats, 16);
+	}
 	for (int i = 0; i < 2 && e == cudaSuccess; i++) {
 		e = cudaEventCreateWithFlags(&ctx->slot[i].ev_h2d, cudaEventDisableTiming);
 		if (e == cudaSuccess)
@@ -305,7 +321,11 @@ extern "C" int btlbf_ctx_destroy(btlbf_ctx* ctx)
 		if (s.ev_kernel) cudaEventDestroy(s.ev_kernel);
 		if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
 	}
-	release(ctx->offsets);
+	for (int i = 0; i < kTickets; i++) {
+		release(ctx->ticket[i].offsets);
+		if (ctx->ticket[i].d_stats) cudaFree(ctx->ticket[i].d_stats);
+		if (ctx->ticket[i].done) cudaEventDestroy(ctx->ticket[i].done);
+	}
 	for (int i = 0; i < 2; i++) {
 		release(ctx->ibin_items[i]);
 		release(ctx->ibin_counts[i]);
@@ -340,7 +360,11 @@ extern "C" int btlbf_ctx_set_stream(btlbf_ctx* ctx, void* cuda_stream)
 extern "C" int btlbf_ctx_sync(btlbf_ctx* ctx)
 {
 	TRY(use(ctx));
+	CU(cudaStreamSynchronize(ctx->copy_in));
 	CU(cudaStreamSynchronize(joined(ctx)));
+	CU(cudaStreamSynchronize(ctx->copy_out));
+	for (int i = 0; i < kTickets; i++)
+		ctx->ticket[i].in_use = false;
 	return BTLBF_OK;
 }
 
@@ -1083,15 +1107,30 @@ struct HostIO
 	uint64_t* n_hits = nullptr;
 };
 
+// grows a pipeline buffer; since that frees the old allocation, nothing may be in flight when it happens
+static int ensure_idle(btlbf_ctx* ctx, DevBuf& b, size_t bytes)
+{
+	if (bytes <= b.cap)
+		return BTLBF_OK;
+	CU(cudaStreamSynchronize(ctx->copy_in));
+	CU(cudaStreamSynchronize(ctx->active));
+	CU(cudaStreamSynchronize(ctx->copy_out));
+	return ensure(b, bytes);
+}
+
 // Streams the flat batch through the GPU in chunks of ctx->chunk_bases windows: chunk i+1 is copied
 // in (copy_in stream) and chunk i-1's results are copied out (copy_out stream) while chunk i runs.
-static int host_pipeline(btlbf_ctx* ctx, btlbf_filter* f, const HashCfg* hash_only, PublicOp op, const HostIO& h)
+// async: return once everything is queued; counts_out (host, 2 words) receives {n_kmers, n_hits} when the
+// call completes, and up to kTickets calls may be in flight (H2D of one call overlaps kernels of another).
+static int host_pipeline(btlbf_ctx* ctx, btlbf_filter* f, const HashCfg* hash_only, PublicOp op, const HostIO& h,
+                         bool async = false, uint64_t* counts_out = nullptr)
 {
 	TRY(use(ctx));
 	if (h.n_seqs && !h.offsets)
 		return fail(BTLBF_ERR_ARG, "null offsets");
 	if (h.n_kmers) *h.n_kmers = 0;
 	if (h.n_hits) *h.n_hits = 0;
+	if (counts_out) counts_out[0] = counts_out[1] = 0;
 	uint64_t n_bases = h.n_seqs ? h.offsets[h.n_seqs] : 0;
 	if (h.n_seqs && h.offsets[0] != 0)
 		return fail(BTLBF_ERR_ARG, "offsets[0] must be 0");
@@ -1113,37 +1152,43 @@ static int host_pipeline(btlbf_ctx* ctx, btlbf_filter* f, const HashCfg* hash_on
 		if (lim < (uint64_t)kTile) lim = kTile;
 		if (chunk > lim) chunk = lim;
 	}
-	if (chunk > n_bases)
-		chunk = (n_bases + kTile - 1) / kTile * kTile;
+	{
+		// near-equal chunks (a batch slightly larger than chunk_bases is not split into one big and one tiny
+		// chunk: every chunk of a large filter costs a pass over the whole filter)
+		uint64_t n_chunks = (n_bases + chunk + chunk / 4 - 1) / (chunk + chunk / 4);
+		if (n_chunks < 1) n_chunks = 1;
+		uint64_t per = (n_bases + n_chunks - 1) / n_chunks;
+		chunk = (per + kTile - 1) / kTile * kTile;
+	}
 
-	TRY(ensure(ctx->offsets, (h.n_seqs + 1) * 8));
-	CU(cudaMemcpyAsync(ctx->offsets.p, h.offsets, (h.n_seqs + 1) * 8, cudaMemcpyHostToDevice, s));
-	CU(cudaMemsetAsync(ctx->d_scalars, 0, 16, s));
-	CU(cudaEventRecord(ctx->slot[0].ev_d2h, s)); // orders the copy streams after the setup above
-	CU(cudaStreamWaitEvent(ctx->copy_in, ctx->slot[0].ev_d2h, 0));
-	ctx->slot[0].used = ctx->slot[1].used = false;
-
+	Ticket& tk = ctx->ticket[ctx->ticket_seq++ % kTickets];
+	if (tk.in_use) {
+		CU(cudaEventSynchronize(tk.done));
+		tk.in_use = false;
+	}
 	const bool want_hit = h.hit_bits != nullptr, want_valid = h.valid_bits != nullptr;
 	const bool need_hit_dev = want_hit || op == PUB_INSERT_CHECK; // list rounds OR into hit words
 	auto run_chunks = [&]() -> int {
-		uint64_t idx = 0;
-		for (uint64_t c0 = 0; c0 < n_bases; c0 += chunk, idx++) {
-			Slot& sl = ctx->slot[idx & 1];
+		TRY(ensure_idle(ctx, tk.offsets, (h.n_seqs + 1) * 8));
+		CU(cudaMemcpyAsync(tk.offsets.p, h.offsets, (h.n_seqs + 1) * 8, cudaMemcpyHostToDevice, ctx->copy_in));
+		CU(cudaMemsetAsync(tk.d_stats, 0, 16, s));
+		for (uint64_t c0 = 0; c0 < n_bases; c0 += chunk) {
+			Slot& sl = ctx->slot[ctx->slot_seq++ & 1];
 			uint64_t cw = n_bases - c0 < chunk ? n_bases - c0 : chunk;
 			uint64_t cb = n_bases - c0 < cw + k - 1 ? n_bases - c0 : cw + k - 1; // chunk + halo
 			uint64_t words = (cw + 31) / 32;
-			TRY(ensure(sl.bases, (size_t)chunk + k + 64));
-			if (need_hit_dev) TRY(ensure(sl.hit, (size_t)(chunk / 32 + 1) * 4));
-			if (want_valid) TRY(ensure(sl.valid, (size_t)(chunk / 32 + 1) * 4));
-			if (h.counts) TRY(ensure(sl.counts, (size_t)chunk));
-			if (h.hashes) TRY(ensure(sl.hashes, (size_t)chunk * H * 8));
-			if (h.strands) TRY(ensure(sl.strands, (size_t)chunk * H));
+			TRY(ensure_idle(ctx, sl.bases, (size_t)chunk + k + 64));
+			if (need_hit_dev) TRY(ensure_idle(ctx, sl.hit, (size_t)(chunk / 32 + 1) * 4));
+			if (want_valid) TRY(ensure_idle(ctx, sl.valid, (size_t)(chunk / 32 + 1) * 4));
+			if (h.counts) TRY(ensure_idle(ctx, sl.counts, (size_t)chunk));
+			if (h.hashes) TRY(ensure_idle(ctx, sl.hashes, (size_t)chunk * H * 8));
+			if (h.strands) TRY(ensure_idle(ctx, sl.strands, (size_t)chunk * H));
 			// the slot is free once its previous results have left the device
 			if (sl.used)
 				CU(cudaStreamWaitEvent(ctx->copy_in, sl.ev_d2h, 0));
 			CU(cudaMemcpyAsync(sl.bases.p, h.bases + c0, cb, cudaMemcpyHostToDevice, ctx->copy_in));
 			CU(cudaEventRecord(sl.ev_h2d, ctx->copy_in));
-			CU(cudaStreamWaitEvent(s, sl.ev_h2d, 0));
+			CU(cudaStreamWaitEvent(s, sl.ev_h2d, 0)); // also orders the offsets upload before the kernels
 			if (sl.used)
 				CU(cudaStreamWaitEvent(s, sl.ev_d2h, 0));
 			ChunkIO io;
@@ -1151,14 +1196,14 @@ static int host_pipeline(btlbf_ctx* ctx, btlbf_filter* f, const HashCfg* hash_on
 			io.n_bases = cb;
 			io.base0 = c0;
 			io.n_windows = cw;
-			io.d_offsets = (const uint64_t*)ctx->offsets.p;
+			io.d_offsets = (const uint64_t*)tk.offsets.p;
 			io.n_seqs = h.n_seqs;
 			io.d_hit = need_hit_dev ? (uint32_t*)sl.hit.p : nullptr;
 			io.d_valid = want_valid ? (uint32_t*)sl.valid.p : nullptr;
 			io.d_counts = h.counts ? (uint8_t*)sl.counts.p : nullptr;
 			io.d_hashes = h.hashes ? (uint64_t*)sl.hashes.p : nullptr;
 			io.d_strands = h.strands ? (uint8_t*)sl.strands.p : nullptr;
-			io.d_stats = (uint64_t*)ctx->d_scalars;
+			io.d_stats = (uint64_t*)tk.d_stats;
 			if (io.d_counts) CU(cudaMemsetAsync(io.d_counts, 0, cw, s));
 			if (io.d_hashes) CU(cudaMemsetAsync(io.d_hashes, 0, cw * H * 8, s));
 			if (io.d_strands) CU(cudaMemsetAsync(io.d_strands, 0, cw * H, s));
@@ -1186,19 +1231,27 @@ static int host_pipeline(btlbf_ctx* ctx, btlbf_filter* f, const HashCfg* hash_on
 			CU(cudaEventRecord(sl.ev_d2h, ctx->copy_out));
 			sl.used = true;
 		}
+		// copy_out is ordered after the last kernel: the call's statistics follow its results
+		CU(cudaMemcpyAsync(async ? (void*)counts_out : (void*)ctx->h_scalars, tk.d_stats, 16, cudaMemcpyDeviceToHost,
+		                   ctx->copy_out));
+		CU(cudaEventRecord(tk.done, ctx->copy_out));
+		tk.in_use = true;
 		return BTLBF_OK;
 	};
 	int rc = run_chunks();
+	if (async && rc == BTLBF_OK)
+		return BTLBF_OK;
 	// drain: everything queued on the three streams must finish before the caller reads its buffers
 	cudaError_t e1 = cudaStreamSynchronize(ctx->copy_in);
 	cudaError_t e2 = cudaStreamSynchronize(s);
 	cudaError_t e3 = cudaStreamSynchronize(ctx->copy_out);
+	for (int i = 0; i < kTickets; i++)
+		ctx->ticket[i].in_use = false;
 	if (rc != BTLBF_OK)
 		return rc;
 	CU(e1);
 	CU(e2);
 	CU(e3);
-	CU(cudaMemcpy(ctx->h_scalars, ctx->d_scalars, 16, cudaMemcpyDeviceToHost));
 	if (h.n_kmers) *h.n_kmers = ctx->h_scalars[0];
 	if (h.n_hits) *h.n_hits = ctx->h_scalars[1];
 	return BTLBF_OK;
@@ -1223,6 +1276,29 @@ extern "C" int btlbf_contains_seqs(btlbf_filter* f, const char* bases, const uin
 	h.bases = bases; h.offsets = offsets; h.n_seqs = n_seqs; h.hit_bits = hit_bits; h.valid_bits = valid_bits;
 	h.n_kmers = n_kmers; h.n_hits = n_hits;
 	return host_pipeline(f->ctx, f, nullptr, PUB_CONTAINS, h);
+}
+
+extern "C" int btlbf_insert_seqs_async(btlbf_filter* f, const char* bases, const uint64_t* offsets, uint64_t n_seqs,
+                                       uint64_t* counts_out)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	HostIO h;
+	h.bases = bases; h.offsets = offsets; h.n_seqs = n_seqs;
+	uint64_t dummy[2];
+	return host_pipeline(f->ctx, f, nullptr, PUB_INSERT, h, counts_out != nullptr, counts_out ? counts_out : dummy);
+}
+
+extern "C" int btlbf_contains_seqs_async(btlbf_filter* f, const char* bases, const uint64_t* offsets, uint64_t n_seqs,
+                                         uint8_t* hit_bits, uint8_t* valid_bits, uint64_t* counts_out)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	if (!counts_out)
+		return fail(BTLBF_ERR_ARG, "counts_out is required (2 host words: n_kmers, n_hits)");
+	HostIO h;
+	h.bases = bases; h.offsets = offsets; h.n_seqs = n_seqs; h.hit_bits = hit_bits; h.valid_bits = valid_bits;
+	return host_pipeline(f->ctx, f, nullptr, PUB_CONTAINS, h, true, counts_out);
 }
 
 extern "C" int btlbf_insert_and_check_seqs(btlbf_filter* f, const char* bases, const uint64_t* offsets,

@@ -284,6 +284,21 @@ class _DeviceFilter:
                                           C.byref(nk), C.byref(nh)))
         return QueryResult(n, off, self.getKmerSize(), hits, valid, nk.value, nh.value)
 
+    # -- streaming (asynchronous) forms: all arrays must stay alive and untouched until Context.sync()
+    def insertSeqsAsync(self, seqs, counts_out):
+        """Queue insertSeqs; counts_out: uint64[2] (ideally pinned) that receives {n_kmers, n_hits}."""
+        bases, off = as_batch(seqs)
+        check(self._L.btlbf_insert_seqs_async(self._h, _ptr(bases), _p64(off), off.size - 1, _ptr(counts_out)))
+        return bases, off  # the caller keeps these alive until sync()
+
+    def containsSeqsAsync(self, seqs, hit_out, counts_out, valid_out=None):
+        bases, off = as_batch(seqs)
+        if hit_out.size < bit_bytes(bases.size):
+            raise ValueError("hit_out needs %d bytes" % bit_bytes(bases.size))
+        check(self._L.btlbf_contains_seqs_async(self._h, _ptr(bases), _p64(off), off.size - 1, _ptr(hit_out),
+                                                _ptr(valid_out), _ptr(counts_out)))
+        return bases, off
+
     # -- device-resident batches (asynchronous on the context's stream; pointers are raw device addresses)
     def insertSeqsDevice(self, d_bases, n_bases, d_offsets, n_seqs, d_stats=0):
         check(self._L.btlbf_insert_seqs_dev(self._h, C.c_void_p(d_bases), n_bases, C.c_void_p(d_offsets), n_seqs,

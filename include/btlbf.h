@@ -140,6 +140,15 @@ int btlbf_insert_seqs(btlbf_filter *f, const char *bases, const uint64_t *offset
 int btlbf_contains_seqs(btlbf_filter *f, const char *bases, const uint64_t *offsets,
                         uint64_t n_seqs, uint8_t *hit_bits, uint8_t *valid_bits, uint64_t *n_kmers,
                         uint64_t *n_hits);
+/* Asynchronous forms for streaming callers: return once the work is queued, so the H2D copy of the next
+ * call overlaps the kernels of this one.  All host buffers (bases, offsets, outputs, counts_out) must stay
+ * valid and untouched until btlbf_ctx_sync(); pinned memory makes the copies truly asynchronous.
+ * counts_out: 2 host words that receive {n_kmers, n_hits} when the call completes (insert: may be NULL, in
+ * which case the call is synchronous).  Up to 4 calls may be in flight; a fifth waits for the oldest. */
+int btlbf_insert_seqs_async(btlbf_filter *f, const char *bases, const uint64_t *offsets, uint64_t n_seqs,
+                            uint64_t *counts_out);
+int btlbf_contains_seqs_async(btlbf_filter *f, const char *bases, const uint64_t *offsets, uint64_t n_seqs,
+                              uint8_t *hit_bits, uint8_t *valid_bits, uint64_t *counts_out);
 int btlbf_insert_and_check_seqs(btlbf_filter *f, const char *bases, const uint64_t *offsets,
                                 uint64_t n_seqs, uint8_t *found_bits, uint8_t *valid_bits,
                                 uint64_t *n_kmers);

@@ -362,3 +362,27 @@ def test_binned_build_full_size_equals_direct_build(gpu, oracle):
     assert np.array_equal(head, g[:200_000].cpu().numpy())
     r = arrays[1][0].containsSeqs((head, np.array([0, head.size], np.uint64)))
     assert r.n_kmers == r.n_hits == head.size - 24
+
+
+def test_async_host_calls_match_blocking_calls(gpu, oracle):
+    """btlbf_insert_seqs_async / btlbf_contains_seqs_async queued back to back (more calls than tickets),
+    results read after one btlbf_ctx_sync: same filter, hit vectors and counts as the oracle."""
+    import btl_bloomfilter_b200 as B
+    rng = np.random.default_rng(21)
+    bits, h, k = 8 * 50_021, 3, 21
+    f = B.BloomFilter(bits, h, k, ctx=gpu.ctx)
+    filt = np.zeros(bits // 8, np.uint8)
+    batches = [S.rand_batch(rng, 30, 400) for _ in range(7)]
+    counts = np.zeros((14, 2), np.uint64)
+    hits = [np.zeros(O.nbits_bytes(b.size), np.uint8) for b, _ in batches]
+    keep = []
+    for i, (b, off) in enumerate(batches):
+        keep.append(f.insertSeqsAsync((b, off), counts[2 * i]))
+        keep.append(f.containsSeqsAsync((b, off), hits[i], counts[2 * i + 1]))
+    gpu.ctx.sync()
+    for i, (b, off) in enumerate(batches):
+        n = oracle.bf_insert_seqs(filt, bits, h, k, b, off)
+        assert int(counts[2 * i, 0]) == n
+        assert (int(counts[2 * i + 1, 0]), int(counts[2 * i + 1, 1])) == (n, n)
+        assert np.array_equal(O.bits_to_bool(hits[i], b.size), O.bits_to_bool(oracle.hash_seqs(h, k, b, off)[2], b.size))
+    assert np.array_equal(f.to_numpy(), filt)

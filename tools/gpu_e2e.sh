@@ -4,6 +4,6 @@ for a in "$@"; do
   python - "$a" <<'PY'
 import json,sys
 d=json.load(open("gpurun_out/sweep.json"))
-print("%-44s value %.2f e2e %.2f insert %.2f query %.2f" % (sys.argv[1], d["value"], d["e2e"]["value"], d["insert_gkmers_s"], d["query_gkmers_s"]))
+print("%-44s value %.2f e2e %.2f e2e_sync %.2f insert %.2f query %.2f" % (sys.argv[1], d["value"], d["e2e"]["value"], d["e2e_sync"]["value"], d["insert_gkmers_s"], d["query_gkmers_s"]))
 PY
 done
