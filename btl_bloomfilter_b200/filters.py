@@ -479,6 +479,26 @@ class BloomFilter(_DeviceFilter):
         self.m_tEntry = int(v)
 
 
+class KmerBloomFilter(BloomFilter):
+    """KmerBloomFilter.hpp:17-74 (what swig/BloomFilter.i exports as "BloomFilter"): insert / contains also take
+    one k-mer as text.  The k-mer is hashed on the GPU with the iterator-consistent canonical ntHash (equal to the
+    reference's NTC64(kmer,k) for k % 4 != 0; for k % 4 == 0 the reference's value is undefined behaviour)."""
+
+    def _is_text(self, x):
+        return isinstance(x, (str, bytes, bytearray))
+
+    def insert(self, kmer_or_hashes):
+        if self._is_text(kmer_or_hashes):
+            self.insertSeqs([kmer_or_hashes[: self.getKmerSize()]])
+        else:
+            super().insert(kmer_or_hashes)
+
+    def contains(self, kmer_or_hashes):
+        if self._is_text(kmer_or_hashes):
+            return self.containsSeqs([kmer_or_hashes[: self.getKmerSize()]]).n_hits == 1
+        return super().contains(kmer_or_hashes)
+
+
 def insertSeq(bloom, seq, hashNum=None, kmerSize=None):
     """BloomFilterUtil.h:10-17: load every k-mer of one sequence into the filter."""
     if hashNum is not None and hashNum != bloom.getHashNum():

@@ -197,6 +197,21 @@ def main():
                     "n_hits": int(nh.value), "hit_hex": hits.tobytes().hex(), "valid_hex": valid.tobytes().hex()}
     R.L.ref_bf_free(f)
 
+    # ---- KmerBloomFilter::insert/contains(const char*) (table-driven NTC64 + NTE64), k % 4 != 0 only:
+    # for k % 4 == 0 the reference's value is undefined behaviour
+    kbf = []
+    for k, h, bits in ((5, 4, 8 * 997), (25, 4, 8 * 4099), (31, 3, 1 << 15), (22, 6, 8 * 1237)):
+        kmers = [rand_seq(rng, k, p_lower=0.2) for _ in range(40)]
+        f = R.L.ref_kbf_new(bits, h, k)
+        for km in kmers:
+            R.L.ref_kbf_insert(f, km.encode())
+        data = np.ctypeslib.as_array(R.L.ref_kbf_data(f), shape=(bits // 8,)).copy()
+        probes = kmers[:5] + [rand_seq(rng, k) for _ in range(20)]
+        kbf.append({"k": k, "h": h, "bits": bits, "kmers": kmers, "filter_hex": data.tobytes().hex(),
+                    "probes": probes, "contains": [int(R.L.ref_kbf_contains(f, p_.encode())) for p_ in probes]})
+        R.L.ref_kbf_free(f)
+    out["kmer_bloom_filter"] = kbf
+
     # ---- cfg1 (BASELINE.json configs[0]): 1 Mbp synthetic genome (seed 42), k=25, h=4, 2^23-bit filter
     orc = O.Oracle()
     g = orc.synth_genome(0, 1_000_000, 42)

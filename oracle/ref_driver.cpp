@@ -11,7 +11,7 @@
  * insert/contains), README.md:86-113 (counting filter), BloomFilterUtil.h:10-17 (insertSeq),
  * Tests/AdHoc/ParallelFilter.cpp:104-122 (OpenMP over reads).
  */
-#include "BloomFilter.hpp"
+#include "KmerBloomFilter.hpp"
 #include "CountingBloomFilter.hpp"
 #include "vendor/ntHashIterator.hpp"
 #include "vendor/stHashIterator.hpp"
@@ -294,6 +294,40 @@ ref_st_bf_contains_seqs(void* f, const char* const* seeds, unsigned n_seeds, uns
 	if (n_hits)
 		*n_hits = hits;
 	return n;
+}
+
+/* ---------- KmerBloomFilter (KmerBloomFilter.hpp:47-74): one k-mer as text, table-driven NTC64/NTE64 ---------- */
+struct RefKBF : public KmerBloomFilter
+{
+	RefKBF(size_t bits, unsigned h, unsigned k)
+	  : KmerBloomFilter(bits, h, k)
+	{}
+	uint8_t* data() { return m_filter; }
+};
+void*
+ref_kbf_new(uint64_t bits, unsigned h, unsigned k)
+{
+	return new RefKBF(bits, h, k);
+}
+void
+ref_kbf_free(void* f)
+{
+	delete (RefKBF*)f;
+}
+uint8_t*
+ref_kbf_data(void* f)
+{
+	return ((RefKBF*)f)->data();
+}
+void
+ref_kbf_insert(void* f, const char* kmer)
+{
+	((RefKBF*)f)->insert(kmer);
+}
+int
+ref_kbf_contains(void* f, const char* kmer)
+{
+	return ((RefKBF*)f)->contains(kmer) ? 1 : 0;
 }
 
 /* ---------- CountingBloomFilter<uint8_t> ---------- */

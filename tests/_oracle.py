@@ -293,6 +293,14 @@ class Ref:
         L.ref_cbf_contains_seqs.argtypes = [vp, u8p, u64p, u64, u8p, u8p, u64p]
         L.ref_st_cbf_insert_seqs.argtypes = [vp, cpp, u32, u32, u8p, u64p, u64]
         L.ref_st_cbf_mincount_seqs.argtypes = [vp, cpp, u32, u32, u8p, u64p, u64, u8p, u8p]
+        L.ref_kbf_new.restype = vp
+        L.ref_kbf_new.argtypes = [u64, u32, u32]
+        L.ref_kbf_free.argtypes = [vp]
+        L.ref_kbf_data.restype = u8p
+        L.ref_kbf_data.argtypes = [vp]
+        L.ref_kbf_insert.argtypes = [vp, C.c_char_p]
+        L.ref_kbf_contains.argtypes = [vp, C.c_char_p]
+        L.ref_kbf_contains.restype = C.c_int
         L.ref_bench_bf.restype = C.c_double
         L.ref_bench_bf.argtypes = [vp, u8p, u64p, u64, C.c_int, C.c_int, u64p, u64p]
         L.ref_bench_cbf.restype = C.c_double

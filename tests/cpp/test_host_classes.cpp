@@ -13,6 +13,7 @@
 #include "btlbf/BloomFilter.hpp"
 #include "btlbf/BloomFilterUtil.h"
 #include "btlbf/CountingBloomFilter.hpp"
+#include "btlbf/KmerBloomFilter.hpp"
 
 extern "C" {
 #include "../../oracle/btl_oracle.h"
@@ -103,6 +104,23 @@ bloomScenario(const std::string& tmp)
 	for (size_t s = 0; s < seqs.size(); s++)
 		for (ora_nt_iter_init(&it, seqs[s].data(), seqs[s].size(), 4, 7); it.pos != ORA_END; ora_nt_iter_next(&it))
 			CHECK(h.valid(batch.offsets[s] + it.pos) && h.hit(batch.offsets[s] + it.pos));
+	// KmerBloomFilter: text k-mers, consistent with the iterator path (swig/test.pl scenario: 20-mers)
+	KmerBloomFilter kb(8 * 4099, 4, 21), kb2(8 * 4099, 4, 21);
+	const char* kmers[4] = { "ATCGGGTCATCAACCAATATA", "ATCGGGTCATCAACCAATATT", "ATCGGGTCATCAACCAATAAA", "ATCGGGTCATCAACCAATAGG" };
+	for (int i = 0; i < 4; i++) {
+		kb.insert(kmers[i]);
+		ora_nt_iter_init(&it, kmers[i], 21, 4, 21);
+		kb2.insert(it.hv);
+	}
+	std::ostringstream ka, kb_;
+	ka << kb;
+	kb_ << kb2;
+	CHECK(ka.str() == kb_.str());
+	for (int i = 0; i < 4; i++)
+		CHECK(kb.contains(kmers[i]));
+	CHECK(!kb.contains("ATCGGGTCATCAACCAATACC"));
+	insertSeq(kb, "ATCGGGTCATCAACCAATACCGG", 4, 21);
+	CHECK(kb.contains("ATCGGGTCATCAACCAATACC"));
 	printf("bloom scenario ok (%llu k-mers)\n", (unsigned long long)n);
 }
 

@@ -386,3 +386,87 @@ def test_async_host_calls_match_blocking_calls(gpu, oracle):
         assert (int(counts[2 * i + 1, 0]), int(counts[2 * i + 1, 1])) == (n, n)
         assert np.array_equal(O.bits_to_bool(hits[i], b.size), O.bits_to_bool(oracle.hash_seqs(h, k, b, off)[2], b.size))
     assert np.array_equal(f.to_numpy(), filt)
+
+
+# ---------------------------------------------------------------- BASELINE-size property tests (cfg4, cfg5)
+def test_cfg4_counting_filter_full_size_properties(gpu, oracle):
+    """CountingBloomFilter<uint8_t> with 16e9 counters (BASELINE configs[3]): exact counts on a sample the
+    oracle can replay sparsely (every touched counter), threshold-2 query semantics, idempotent queries."""
+    import btl_bloomfilter_b200 as B
+    m, h, k = 16_000_000_000, 4, 25
+    f = B.CountingBloomFilter(m, h, k, 2, ctx=gpu.ctx)
+    assert f.size() == f.sizeInBytes() == m
+    reads = oracle.synth_reads(0, 4000, 150, 3_000_000_000, 42, 11)
+    off = (150 * np.arange(4001)).astype(np.uint64)
+    n = f.insertSeqs((reads, off))
+    assert n == 4000 * 126
+    r1 = f.containsSeqs((reads, off))
+    assert r1.n_kmers == n
+    # sparse replay: sequential min-increment over a dict of touched counters
+    _, hs, valid = oracle.hash_seqs(h, k, reads, off)
+    idx = (hs % np.uint64(m))
+    vmask = O.bits_to_bool(valid, reads.size)
+    cnt = {}
+    for p in np.nonzero(vmask)[0]:
+        slots = [int(x) for x in idx[p]]
+        mn = min(cnt.get(s_, 0) for s_ in slots)
+        if mn < 255:
+            for s_ in slots:
+                if cnt.get(s_, 0) == mn:
+                    cnt[s_] = mn + 1
+    exp_min = np.array([min(cnt.get(int(x), 0) for x in idx[p]) if vmask[p] else 0 for p in range(reads.size)], np.uint8)
+    q = f.minCountSeqs((reads, off))
+    assert np.array_equal(q.counts, exp_min)
+    assert r1.n_hits == int((exp_min[vmask] >= 2).sum())
+    assert f.popCount() == len(cnt)
+    n2 = f.insertSeqs((reads, off))
+    q2 = f.minCountSeqs((reads, off))
+    assert n2 == n and (q2.counts[vmask] >= 2).all()  # second pass: every k-mer now has count >= 2
+    r2 = f.containsSeqs((reads, off))
+    assert r2.n_hits == n
+    del f
+
+
+@pytest.mark.parametrize("bits", [1 << 29, 1 << 37])
+def test_cfg5_spaced_seed_filters_properties(gpu, oracle, bits):
+    """stHashIterator, k=31, two symmetric seeds (BASELINE configs[4]) on the L2-resident 64 MB filter and the
+    16 GB filter: inserted => contained, bit positions equal the oracle's hashes, idempotent inserts."""
+    import btl_bloomfilter_b200 as B
+    left = ["111101110111001", "111110110100111"]
+    seeds = [x + "1" + x[::-1] for x in left]
+    assert all(s == s[::-1] and len(s) == 31 for s in seeds)
+    k = 31
+    f = B.BloomFilter(bits, 2, k, ctx=gpu.ctx)
+    f.setSeeds(seeds, 1)
+    reads = oracle.synth_reads(0, 3000, 150, 3_000_000_000, 42, 13)
+    off = (150 * np.arange(3001)).astype(np.uint64)
+    n = f.insertSeqs((reads, off))
+    assert n == 3000 * 120
+    _, hs, _, valid = oracle.st_hash_seqs(seeds, 1, k, reads, off)
+    vm = O.bits_to_bool(valid, reads.size)
+    idx = np.unique((hs[vm] % np.uint64(bits)).reshape(-1))
+    assert f.getPop() == idx.size
+    r = f.containsSeqs((reads, off))
+    assert r.n_kmers == r.n_hits == n
+    assert f.insertSeqs((reads, off)) == n and f.getPop() == idx.size
+    miss = oracle.synth_genome(0, 200_000, 43 << 40)
+    r = f.containsSeqs((miss, np.array([0, miss.size], np.uint64)))
+    _, mh, _, mv = oracle.st_hash_seqs(seeds, 1, k, miss, np.array([0, miss.size], np.uint64))
+    mvm = O.bits_to_bool(mv, miss.size)
+    exp = np.isin(mh % np.uint64(bits), idx).all(axis=1) & mvm
+    assert r.n_hits == int(exp.sum())
+    assert np.array_equal(O.bits_to_bool(r.hit_bits, miss.size), exp)
+    del f
+
+
+def test_kmer_bloom_filter_matches_reference(gpu, golden):
+    """KmerBloomFilter::insert/contains(const char*) (the class SWIG exports as BloomFilter)."""
+    import btl_bloomfilter_b200 as B
+    for c in golden["kmer_bloom_filter"]:
+        f = B.KmerBloomFilter(c["bits"], c["h"], c["k"], ctx=gpu.ctx)
+        for km in c["kmers"][:10]:
+            f.insert(km)                      # one k-mer per call, as the Perl callers do
+        f.insertSeqs(c["kmers"][10:])         # the rest in one batch
+        assert f.to_numpy().tobytes().hex() == c["filter_hex"]
+        assert [int(f.contains(p)) for p in c["probes"]] == c["contains"]
+        assert f.contains("N" * c["k"]) is False
