@@ -97,6 +97,7 @@ struct btlbf_ctx
 	int64_t cbf_batch = (int64_t)1 << 20;    // windows per batch of the ordered (exact) updates
 	int64_t resv_log2 = 28, list_log2 = 22;
 	int64_t drain_threshold = 4096;
+	int64_t ordered_coop = 1; // residual rounds of the ordered updates: 1 cooperative grid kernel, 0 host-driven rounds
 	int64_t bin_mode = 0;       // partitioned BloomFilter build: 0 auto, 1 always, -1 never
 	int64_t bin_part_log2 = 27; // bits per filter partition (2^27 bits = 16 MiB: two of them resident in L2)
 	int64_t bin_slack_pct = 20;
@@ -126,6 +127,7 @@ struct btlbf_filter
 	uint64_t* d_list_resv = nullptr;
 	uint32_t list_log2 = 0;
 	uint32_t epoch = 0;
+	uint32_t* d_ord = nullptr; // device words of the cooperative path: [0..1] list counters, [2] epoch, [3] rounds, [4] deferred
 	uint64_t deferred_total = 0, rounds_total = 0;
 };
 
@@ -441,6 +443,8 @@ extern "C" int btlbf_ctx_set_option(btlbf_ctx* ctx, const char* key, int64_t val
 		if (value < 0 || value > 1000)
 			return fail(BTLBF_ERR_ARG, "bin_slack_pct out of range");
 		ctx->bin_slack_pct = value;
+	} else if (k == "ordered_coop") {
+		ctx->ordered_coop = value != 0;
 	} else if (k == "drain_threshold") {
 		if (value < 0)
 			return fail(BTLBF_ERR_ARG, "drain_threshold out of range");
@@ -531,6 +535,7 @@ extern "C" int btlbf_filter_destroy(btlbf_filter* f)
 	if (f->d_pending[0]) cudaFree(f->d_pending[0]);
 	if (f->d_pending[1]) cudaFree(f->d_pending[1]);
 	if (f->d_list_resv) cudaFree(f->d_list_resv);
+	if (f->d_ord) cudaFree(f->d_ord);
 	delete f;
 	return BTLBF_OK;
 }
@@ -740,6 +745,12 @@ static int ordered_state(btlbf_filter* f, uint32_t batch)
 		CU(cudaMemsetAsync(f->d_list_resv, 0xff, bytes, ctx->active));
 		f->list_log2 = want_list;
 		f->epoch = 0;
+		if (f->d_ord)
+			CU(cudaMemsetAsync(f->d_ord, 0, 32, ctx->active));
+	}
+	if (!f->d_ord) {
+		CU(cudaMalloc(&f->d_ord, 32));
+		CU(cudaMemsetAsync(f->d_ord, 0, 32, ctx->active));
 	}
 	return BTLBF_OK;
 }
@@ -754,6 +765,9 @@ static int ordered_apply(btlbf_filter* f, const SeqParams& chunk, int kind, cuda
 	TRY(ordered_state(f, (uint32_t)batch));
 	uint32_t* d_cnt = reinterpret_cast<uint32_t*>(ctx->d_scalars + 4); // [0],[1]: list counters, [2]: rounds
 	volatile uint32_t* h_cnt = reinterpret_cast<volatile uint32_t*>(ctx->h_scalars + 4);
+	const bool coop = ctx->ordered_coop != 0;
+	if (coop)
+		d_cnt = f->d_ord;
 	for (uint64_t b0 = 0; b0 < chunk.n_windows; b0 += batch) {
 		SeqParams P = chunk;
 		uint64_t bw = chunk.n_windows - b0 < batch ? chunk.n_windows - b0 : batch;
@@ -769,7 +783,8 @@ static int ordered_apply(btlbf_filter* f, const SeqParams& chunk, int kind, cuda
 		P.resv_log2 = f->resv_log2;
 		P.pending = f->d_pending[0];
 		P.pending_count = d_cnt;
-		CU(cudaMemsetAsync(d_cnt, 0, 16, s));
+		if (!coop)
+			CU(cudaMemsetAsync(d_cnt, 0, 16, s));
 		// pass 1 carries no outputs; pass 2 writes valid/hit words and the k-mer statistics
 		SeqParams T = P;
 		T.hit_bits = T.valid_bits = nullptr;
@@ -777,6 +792,26 @@ static int ordered_apply(btlbf_filter* f, const SeqParams& chunk, int kind, cuda
 		TRY(launch(ctx, OP_RESV_TOUCH, T, s));
 		TRY(launch(ctx, kind == 0 ? OP_CBF_COMMIT : OP_BFCHK_COMMIT, P, s));
 		TRY(launch(ctx, OP_RESV_CLEAR, T, s));
+		if (coop) {
+			// the residual rounds run to completion on the device (grid-wide barriers): nothing to wait for
+			ListParams L;
+			memset(&L, 0, sizeof L);
+			L.list_in = f->d_pending[0];
+			L.list_out = f->d_pending[1];
+			L.counts = d_cnt;
+			L.count_in = d_cnt;
+			L.count_out = d_cnt + 1;
+			L.resv = f->d_list_resv;
+			L.resv_log2 = f->list_log2;
+			L.kind = (uint32_t)kind;
+			L.d_epoch = d_cnt + 2;
+			L.rounds_out = d_cnt + 3;
+			cudaError_t e = launch_list_drain_coop(P, L, s);
+			if (e != cudaSuccess)
+				return fail(BTLBF_ERR_CUDA, "cooperative drain launch failed: %s", cudaGetErrorString(e));
+			ctx->launches++;
+			continue;
+		}
 		CU(cudaMemcpyAsync((void*)h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
 		CU(cudaStreamSynchronize(s));
 		uint32_t n = h_cnt[0];
@@ -1361,8 +1396,17 @@ extern "C" int btlbf_filter_ordered_stats(btlbf_filter* f, uint64_t* deferred, u
 {
 	if (!f)
 		return fail(BTLBF_ERR_ARG, "null filter");
-	if (deferred) *deferred = f->deferred_total;
-	if (rounds) *rounds = f->rounds_total;
+	uint64_t d = f->deferred_total, r = f->rounds_total;
+	if (f->d_ord) { // the cooperative path keeps its counters on the device
+		TRY(use(f->ctx));
+		uint32_t w[8];
+		CU(cudaStreamSynchronize(joined(f->ctx)));
+		CU(cudaMemcpy(w, f->d_ord, 32, cudaMemcpyDeviceToHost));
+		r += w[3];
+		d += w[4];
+	}
+	if (deferred) *deferred = d;
+	if (rounds) *rounds = r;
 	return BTLBF_OK;
 }
 

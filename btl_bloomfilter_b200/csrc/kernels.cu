@@ -10,6 +10,8 @@
 // queries, RED.OR / byte update for inserts), so the kernels are bound by HBM random-sector rate.
 #include "tile_core.cuh"
 
+#include <cooperative_groups.h>
+
 namespace btl {
 
 // one tile: stage -> classify/pack -> roll + fused operation -> per-window result words + statistics
@@ -628,6 +630,84 @@ __global__ void __launch_bounds__(kDrainThreads) list_drain_kernel(const __grid_
 		if (L.rounds_out)
 			*L.rounds_out = rounds;
 	}
+}
+
+// Cooperative variant: every round is [reserve | grid barrier | commit or re-queue | grid barrier].
+// L.counts[0] is the length of list_in on entry; the epoch counter is read from and written back to
+// L.d_epoch, and the reservation table is re-armed here when the 32-bit epoch space runs low.
+constexpr int kCoopThreads = 256;
+
+template<bool POW2, int KIND>
+__global__ void __launch_bounds__(kCoopThreads) list_drain_coop_kernel(const __grid_constant__ SeqParams P,
+                                                                       const __grid_constant__ ListParams L)
+{
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+	const uint64_t emask = ((uint64_t)1 << L.resv_log2) - 1;
+	uint32_t epoch = *L.d_epoch;
+	uint32_t n = L.counts[0];
+	if (n == 0)
+		return; // uniform across the grid
+	if (gtid == 0)
+		L.counts[4] += n; // statistics: k-mers that had to wait for the residual rounds
+	if (epoch > 0xf0000000u) {
+		for (uint64_t i = gtid; i <= emask; i += gthreads)
+			L.resv[i] = ~0ull;
+		epoch = 0;
+		grid.sync();
+	}
+	const uint32_t* in = L.list_in;
+	uint32_t* out = L.list_out;
+	uint32_t cur = 0, rounds = 0;
+	while (n > 0) {
+		++epoch;
+		for (uint32_t i = gtid; i < n; i += gthreads)
+			list_round_reserve<POW2>(P, L.resv, emask, epoch, in[i]);
+		grid.sync();
+		for (uint32_t i = gtid; i < n; i += gthreads) {
+			uint32_t w = in[i];
+			if (!list_round_commit<POW2, KIND>(P, L.resv, emask, epoch, w))
+				out[atomicAdd(L.counts + (cur ^ 1u), 1u)] = w;
+		}
+		grid.sync();
+		n = ld_cg(L.counts + (cur ^ 1u));
+		if (gtid == 0)
+			L.counts[cur] = 0; // becomes the output counter of the next round (ordered by its first barrier)
+		const uint32_t* t = out;
+		out = const_cast<uint32_t*>(in);
+		in = t;
+		cur ^= 1u;
+		rounds++;
+	}
+	if (gtid == 0) {
+		*L.d_epoch = epoch;
+		L.counts[0] = 0;
+		L.counts[1] = 0;
+		if (L.rounds_out)
+			atomicAdd(L.rounds_out, rounds);
+	}
+}
+
+cudaError_t launch_list_drain_coop(const SeqParams& P, const ListParams& L, cudaStream_t stream)
+{
+	const void* kern;
+	if (P.fm.pow2)
+		kern = L.kind == 0 ? (const void*)list_drain_coop_kernel<true, 0> : (const void*)list_drain_coop_kernel<true, 1>;
+	else
+		kern = L.kind == 0 ? (const void*)list_drain_coop_kernel<false, 0> : (const void*)list_drain_coop_kernel<false, 1>;
+	int occ = 0, dev = 0, sms = 0;
+	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCoopThreads, 0);
+	if (e != cudaSuccess)
+		return e;
+	if ((e = cudaGetDevice(&dev)) != cudaSuccess)
+		return e;
+	if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
+		return e;
+	if (occ < 1)
+		return cudaErrorLaunchOutOfResources;
+	int per_sm = occ < 2 ? occ : 2; // a few hundred thousand items at most: two CTAs per SM are plenty
+	void* args[2] = { (void*)&P, (void*)&L };
+	return cudaLaunchCooperativeKernel(kern, dim3((unsigned)(sms * per_sm)), dim3(kCoopThreads), args, 0, stream);
 }
 
 cudaError_t launch_list_drain(const SeqParams& P, const ListParams& L, cudaStream_t stream)

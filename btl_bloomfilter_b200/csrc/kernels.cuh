@@ -105,12 +105,17 @@ struct ListParams
 	uint32_t epoch;       // strictly increasing across rounds
 	uint32_t max_items;   // upper bound of *count_in (sizes the grid)
 	uint32_t kind;        // 0: incrementMin, 1: insertAndCheck
-	uint32_t* rounds_out; // serial kernel: number of rounds it ran
+	uint32_t* rounds_out; // drain kernels: number of rounds they ran (added)
+	uint32_t* d_epoch;    // cooperative drain: the epoch counter lives on the device
+	uint32_t* counts;     // cooperative drain: the two ping-pong list counters {count(list_in), count(list_out)}
 };
 // phase 0: reserve, phase 1: commit or re-queue (one grid-wide launch each)
 cudaError_t launch_list_round(int phase, const SeqParams& P, const ListParams& L, cudaStream_t stream);
 // one CTA loops reserve/commit rounds until the list is empty (short lists, long dependency chains)
 cudaError_t launch_list_drain(const SeqParams& P, const ListParams& L, cudaStream_t stream);
+// the whole GPU loops reserve/commit rounds (grid-wide barriers) until the list is empty: no host round
+// trip at all, so batches of ordered updates can be queued back to back.  Cooperative launch.
+cudaError_t launch_list_drain_coop(const SeqParams& P, const ListParams& L, cudaStream_t stream);
 
 // Legacy per-k-mer interface of the reference classes (caller supplies the h hash values of each k-mer,
 // BloomFilter.hpp:185-262, CountingBloomFilter.hpp:53-64,134-214): hashes = n x h values.

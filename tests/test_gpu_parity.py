@@ -93,6 +93,15 @@ def test_random_cbf(gpu, oracle, k, h, m):
     S.check_random_cbf(gpu, oracle, k, h, m, seed=m + k)
 
 
+def test_random_cbf_host_driven_rounds(oracle, golden):
+    """the non-cooperative residual path (host-driven rounds + single-CTA drain)"""
+    from _backends import GpuBackend
+    be = GpuBackend(chunk=4096, batch=4096, resv_log2=10, list_log2=6, drain_threshold=16, ordered_coop=0)
+    S.check_random_cbf(be, oracle, 9, 4, 256, seed=1, n_seqs=80, max_len=200)
+    S.check_golden_cbf(be, golden)
+    S.check_golden_bf(be, golden)
+
+
 def test_random_cbf_small_tables(gpu_small, oracle):
     S.check_random_cbf(gpu_small, oracle, 9, 4, 256, seed=1, n_seqs=80, max_len=200)
     f = gpu_small.filter(1, 64, 3, 5)
