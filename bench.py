@@ -4,7 +4,9 @@
 Workload (BASELINE.json configs[1], "cfg2"): 3 Gbp synthetic genome, k=25, 4 hashes, 31,568,113,856-bit
 filter (the reference's calcOptimalSize(3e9, 0.01), 3.95 GB), built in chunks, then 150 bp read queries.
 One STEP = one pass of the hot path over one batch: insert one 64 Mi-window genome chunk into the filter
-and query one batch of 150 bp reads sampled from that chunk (all k-mers present: no early exit).
+and query one batch of 150 bp reads (4 x 64 MiB of bases by default) sampled from that chunk (all k-mers
+present: no early exit).  Like the workload itself (build the filter, then query reads), the timed region
+runs the K build batches first and the K query batches after them; both are inside the timed region.
 
   value     whole-job Gk-mer/s (inserted + queried) with the batches already resident in HBM
             (btlbf_insert_seqs_dev / btlbf_contains_seqs_dev), CUDA events, max over ranks
@@ -169,6 +171,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--chunk", type=int, default=CHUNK)
+    ap.add_argument("--query-factor", type=int, default=4, help="read bases per query batch, in units of --chunk")
     ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity (0: leave as is)")
     ap.add_argument("--stream-priority", type=int, default=0)
     ap.add_argument("--opt", action="append", default=[], help="context option key=value (tuning experiments)")
@@ -177,8 +180,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": WORKLOAD, "k": K, "hashes": H, "filter_bits": FILTER_BITS, "genome_bp": G_LEN,
-              "read_len": READ_LEN, "chunk_windows": args.chunk,
-              "l2": "inputs larger than L2 (64 MiB per batch, 3.95 GB filter); no flush needed"}
+              "read_len": READ_LEN, "chunk_windows": args.chunk, "query_bases_per_step": args.chunk * args.query_factor,
+              "step": "K build batches, then K query batches, all inside the timed region",
+              "l2": "inputs larger than L2 (64 MiB / 256 MiB per batch, 3.95 GB filter); no flush needed"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -219,7 +223,7 @@ def main():
     chunk = args.chunk // 4096 * 4096
     n_chunks = (G_LEN + chunk - 1) // chunk
     W, S = args.warmup, args.steps
-    n_reads = chunk // READ_LEN
+    n_reads = chunk * args.query_factor // READ_LEN
     read_bases = n_reads * READ_LEN
     filt = B.BloomFilter(FILTER_BITS, H, K, ctx=ctx)
 
@@ -244,31 +248,28 @@ def main():
     d_stats = torch.zeros(4, dtype=torch.int64, device=dev)
     torch.cuda.synchronize()
 
-    aux = torch.cuda.ExternalStream(ctx.aux_stream, device=dev)
-
-    def step_dev(i, evs=None):
+    def build_dev(i):
         j = i % n_buf
-        if evs:
-            evs[0].record(stream)
         filt.insertSeqsDevice(d_genome[j].data_ptr(), g_lens[j], goff_of[g_lens[j]].data_ptr(), 1, d_stats.data_ptr())
-        if evs:
-            evs[1].record(stream)  # end of the build's pass 1 (or of the whole build when it is not partitioned)
-            evs[3].record(aux)     # end of the build's pass 2 on the background stream
+
+    def query_dev(i):
+        j = i % n_buf
         filt.containsSeqsDevice(d_reads[j].data_ptr(), read_bases, d_roff.data_ptr(), n_reads, d_hits.data_ptr(), 0,
                                 d_stats[2:].data_ptr())
-        if evs:
-            evs[2].record(stream)
 
     def barrier():
         if world > 1:
             dist.barrier()
 
     for i in range(W):
-        step_dev(i)
+        build_dev(i)
+    for i in range(W):
+        query_dev(i)
     torch.cuda.synchronize()
     d_stats.zero_()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(S)]
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(S)]
+    ev_q = [torch.cuda.Event(enable_timing=True) for _ in range(S)]
+    t_start, t_mid, t_end = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -277,19 +278,26 @@ def main():
     torch.cuda.synchronize()
     t_start.record(stream)
     for i in range(S):
-        step_dev(W + i, evs[i])
-    ctx.flush()  # the active stream (and t_end) waits for the background pass of the last build
+        build_dev(W + i)
+        ev_b[i].record(stream)
+    ctx.flush()  # every k-mer parked in the partition buckets reaches the filter (pass 2) before t_mid
+    t_mid.record(stream)
+    for i in range(S):
+        query_dev(W + i)
+        ev_q[i].record(stream)
     t_end.record(stream)
     torch.cuda.synchronize()
     barrier()
     launches = ctx.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_total = t_start.elapsed_time(t_end)
-    # build = pass 1 on the active stream + pass 2 on the background stream (which starts when pass 1 ends
-    # and overlaps the query's pass 1); the two durations are added as if they ran back to back
-    ms_insert = sum(e[0].elapsed_time(e[1]) + max(0.0, e[1].elapsed_time(e[3])) for e in evs)
-    ms_insert_pass1 = sum(e[0].elapsed_time(e[1]) for e in evs)
-    ms_query = sum(e[1].elapsed_time(e[2]) for e in evs)
+    ms_insert = t_start.elapsed_time(t_mid)
+    ms_query = t_mid.elapsed_time(t_end)
+    # per-call durations on the stream: a build call is pass 1 of its batch, plus pass 2 of the whole
+    # accumulation when that call filled the partition buckets (the median is therefore pass 1 alone)
+    d_b = [(t_start if i == 0 else ev_b[i - 1]).elapsed_time(ev_b[i]) for i in range(S)]
+    d_q = [(t_mid if i == 0 else ev_q[i - 1]).elapsed_time(ev_q[i]) for i in range(S)]
+    ms_insert_pass1 = float(np.median(d_b)) * S
     st = d_stats.cpu().numpy()
     k_ins, k_qry, k_hit = int(st[0]), int(st[2]), int(st[3])
     assert k_hit == k_qry, "a k-mer of an inserted chunk was not found (%d of %d)" % (k_hit, k_qry)
@@ -323,21 +331,28 @@ def main():
             r = filt.containsSeqs((h_reads[j].numpy(), h_roff), hit_out=h_hits[j].numpy(), want_valid=False)
             return a, r.n_kmers, r.n_hits
 
-        def step_host_async(i, slot):
+        def build_host_async(i, slot):
             j = i % n_host
             filt.insertSeqsAsync((h_genome[j].numpy(), h_goff[j]), counts[slot, 0:2])
+
+        def query_host_async(i, slot):
+            j = i % n_host
             filt.containsSeqsAsync((h_reads[j].numpy(), h_roff), h_hits[j].numpy(), counts[slot, 2:4])
 
         for i in range(min(W, 2)):
             step_host_sync(i)
         for i in range(2):
-            step_host_async(i, S2 + i)
+            build_host_async(i, S2 + i)
+        for i in range(2):
+            query_host_async(i, S2 + i)
         ctx.sync()
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(S2):
-            step_host_async(i, i)
+            build_host_async(i, i)
+        for i in range(S2):
+            query_host_async(i, i)
         ctx.sync()
         dt = time.perf_counter() - t0
         barrier()
@@ -389,24 +404,26 @@ def main():
     ins_ms = ms_insert / S
     qry_bytes = (32 * H + 1) * (k_qry / S)
     qry_ms = ms_query / S
-    roof = {"bound": "hbm", "kernel": "BloomFilter build: bin_kernel_warp + apply_bins_kernel (durations added)", "achieved": ins_bytes / (ins_ms * 1e-3) / 1e9,
+    roof = {"bound": "hbm", "kernel": "BloomFilter build: bin_kernel_sort per batch + apply_bins_kernel per accumulation "
+                                      "(all durations of the build phase added)", "achieved": ins_bytes / (ins_ms * 1e-3) / 1e9,
             "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None,
             "bytes_per_kmer": 64 * H + 1, "kmers_per_launch": k_ins / S, "launch_ms": ins_ms,
             "pass1_ms": ms_insert_pass1 / S, "pass2_ms": (ms_insert - ms_insert_pass1) / S,
             "gkmers_s": k_ins / S / (ins_ms * 1e-3) / 1e9}
     roof["frac"] = roof["achieved"] / peak
-    roof_q = {"bound": "hbm", "kernel": "BloomFilter query: bin_kernel_warp + probe_bins_kernel + finalize_hits_kernel", "achieved": qry_bytes / (qry_ms * 1e-3) / 1e9,
+    roof_q = {"bound": "hbm", "kernel": "BloomFilter query: bin_kernel_sort + probe_bins_kernel + finalize_hits_kernel", "achieved": qry_bytes / (qry_ms * 1e-3) / 1e9,
               "peak": peak, "unit": "GB/s", "bytes_per_kmer": 32 * H + 1, "kmers_per_launch": k_qry / S,
-              "launch_ms": qry_ms, "gkmers_s": k_qry / S / (qry_ms * 1e-3) / 1e9}
+              "launch_ms": qry_ms, "call_ms_median": float(np.median(d_q)),
+              "gkmers_s": k_qry / S / (qry_ms * 1e-3) / 1e9}
     roof_q["frac"] = roof_q["achieved"] / peak
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this
     # same command (profiles/r1_dram_bytes_per_launch.json, written by tools/summarize_ncu.py)
-    prof = os.path.join(ROOT, "profiles", "r1_dram_bytes_per_launch.json")
-    if os.path.exists(prof) and chunk == CHUNK and not args.opt:
+    prof = os.path.join(ROOT, "profiles", "r1_dram_bytes_per_step.json")
+    if os.path.exists(prof) and chunk == CHUNK and args.query_factor == 4 and not args.opt:
         try:
             t = json.load(open(prof))
-            roof["traffic"] = t["void bin_kernel_warp<0, 0, 0>"] + t["apply_bins_kernel"]
-            roof_q["traffic"] = t["void bin_kernel_warp<0, 0, 1>"] + t["probe_bins_kernel"] + t["finalize_hits_kernel"]
+            roof["traffic"] = t["build_bytes_per_step"]
+            roof_q["traffic"] = t["query_bytes_per_step"]
         except Exception:
             pass
     line = {"metric": "k-mers/s inserted+queried", "value": (k_ins_all + k_qry_all) / (ms_total * 1e-3) / 1e9,

@@ -107,6 +107,19 @@ struct btlbf_ctx
 	uint64_t slot_seq = 0, ticket_seq = 0;
 	DevBuf ibin_items[2], ibin_counts[2], qbin_items, qbin_counts, q_hit, q_valid;
 	uint64_t binned_launches = 0;
+	// Accumulation of the partitioned build: pass 1 of successive batches appends to the same sub-buckets and
+	// pass 2 runs once they are full or the filter contents are needed (settle()).
+	struct
+	{
+		btlbf_filter* f = nullptr; // filter whose k-mers are parked in the sub-buckets (nullptr: none)
+		SeqParams P;               // geometry of the sub-buckets + the filter they belong to
+		uint64_t windows = 0, capacity = 0, tiles = 0;
+		int slot = 0;
+	} acc;
+	int64_t bin_accum_bytes = (int64_t)8 << 30; // sub-bucket storage one accumulation may use
+	int64_t bin_kernel = 0;                     // 0 auto (sort-bin kernel when the shape allows), 1 legacy kernels only
+	int64_t bin_max_parts = 512;                // the sort-bin path widens the partitions until there are at most this many
+	int settle_error = 0;
 };
 
 struct btlbf_filter
@@ -142,8 +155,12 @@ static int use(btlbf_ctx* ctx)
 
 // The active stream, ordered after all background (aux-stream) work: every operation that reads or
 // writes filter contents on the active stream goes through this.
+static int settle(btlbf_ctx* ctx);
+
 static cudaStream_t joined(btlbf_ctx* ctx)
 {
+	if (ctx->acc.f)
+		settle(ctx);
 	if (ctx->aux_pending) {
 		cudaStreamWaitEvent(ctx->active, ctx->ev_aux_last, 0);
 		ctx->aux_pending = false;
@@ -443,6 +460,16 @@ extern "C" int btlbf_ctx_set_option(btlbf_ctx* ctx, const char* key, int64_t val
 		if (value < 0 || value > 1000)
 			return fail(BTLBF_ERR_ARG, "bin_slack_pct out of range");
 		ctx->bin_slack_pct = value;
+	} else if (k == "bin_accum_bytes") {
+		if (value < 0)
+			return fail(BTLBF_ERR_ARG, "bin_accum_bytes out of range");
+		ctx->bin_accum_bytes = value;
+	} else if (k == "bin_kernel") {
+		ctx->bin_kernel = value != 0;
+	} else if (k == "bin_max_parts") {
+		if (value < 1 || value > 1024)
+			return fail(BTLBF_ERR_ARG, "bin_max_parts out of range [1,1024]");
+		ctx->bin_max_parts = value;
 	} else if (k == "ordered_coop") {
 		ctx->ordered_coop = value != 0;
 	} else if (k == "drain_threshold") {
@@ -526,6 +553,8 @@ extern "C" int btlbf_filter_destroy(btlbf_filter* f)
 	if (!f)
 		return BTLBF_OK;
 	cudaSetDevice(f->ctx->device);
+	if (f->ctx->acc.f == f)
+		f->ctx->acc.f = nullptr; // parked k-mers of a filter that is going away
 	cudaStreamSynchronize(joined(f->ctx));
 	if (f->owned && f->d_data)
 		cudaFree(f->d_data);
@@ -604,6 +633,10 @@ extern "C" int btlbf_filter_device_ptr(btlbf_filter* f, void** device_ptr, uint6
 {
 	if (!f)
 		return fail(BTLBF_ERR_ARG, "null filter");
+	if (f->ctx->acc.f == f || f->ctx->aux_pending) { // parked k-mers reach the filter now, in stream order
+		TRY(use(f->ctx));
+		joined(f->ctx);
+	}
 	if (device_ptr) *device_ptr = f->d_data;
 	if (nbytes) *nbytes = f->bytes;
 	return BTLBF_OK;
@@ -879,26 +912,53 @@ static bool want_binned(const btlbf_filter* f, const SeqParams& P)
 	return f->bytes >= ((uint64_t)96 << 20) && P.n_windows * P.h >= f->bytes / 64;
 }
 
-// partition geometry + sub-bucket storage shared by the partitioned build and query
-static int bin_setup(btlbf_filter* f, SeqParams& P, bool query, uint32_t* grid, DevBuf& items, DevBuf& counts)
+// log2(bits per partition) for filter f hashed as P describes (P.bin_legacy set); false: too many partitions
+static bool bin_geometry(const btlbf_filter* f, const SeqParams& P, uint32_t* shift_out)
+{
+	const btlbf_ctx* ctx = f->ctx;
+	auto parts_at = [&](uint32_t sh) { return (f->size + (((uint64_t)1 << sh) - 1)) >> sh; };
+	uint32_t shift = (uint32_t)ctx->bin_part_log2;
+	while (parts_at(shift) > 4096 && shift < 31)
+		shift++;
+	if (parts_at(shift) > 4096)
+		return false;
+	// the sort-bin kernel wants few partitions (long runs per partition and round); widen them when that
+	// makes the filter eligible
+	if (!P.bin_legacy) {
+		uint32_t sh2 = shift;
+		while (parts_at(sh2) > (uint64_t)ctx->bin_max_parts && sh2 < 31)
+			sh2++;
+		if (sh2 != shift && parts_at(sh2) <= (uint64_t)ctx->bin_max_parts && bin_sort_eligible(P, (uint32_t)parts_at(sh2)))
+			shift = sh2;
+	}
+	*shift_out = shift;
+	return true;
+}
+
+// partition geometry + sub-bucket storage shared by the partitioned build and query.
+// capacity_windows: windows the sub-buckets are sized for (>= P.n_windows).
+static int bin_setup(btlbf_filter* f, SeqParams& P, bool query, uint64_t capacity_windows, uint32_t* grid, int* mode,
+                     DevBuf& items, DevBuf& counts)
 {
 	btlbf_ctx* ctx = f->ctx;
-	uint32_t shift = (uint32_t)ctx->bin_part_log2;
-	while (((f->size + (((uint64_t)1 << shift) - 1)) >> shift) > 4096 && shift < 31)
-		shift++;
-	uint64_t n_bins = (f->size + (((uint64_t)1 << shift) - 1)) >> shift;
-	if (n_bins > 4096)
+	P.bin_legacy = (uint32_t)ctx->bin_kernel;
+	P.bin_rot = 0;
+	uint32_t shift = 0;
+	if (!bin_geometry(f, P, &shift))
 		return fail(BTLBF_ERR_ARG, "filter too large for the partitioned path");
+	auto parts_at = [&](uint32_t sh) { return (f->size + (((uint64_t)1 << sh) - 1)) >> sh; };
+	uint64_t n_bins = parts_at(shift);
 	P.n_bins = (uint32_t)n_bins;
 	P.bin_shift = shift;
 	P.bin_mask = (uint32_t)(((uint64_t)1 << shift) - 1);
 	uint32_t writers = 0;
-	cudaError_t e = bin_plan(P, P.n_bins, query, &writers, grid);
+	cudaError_t e = bin_plan(P, P.n_bins, query, &writers, grid, mode);
 	if (e != cudaSuccess)
 		return fail(BTLBF_ERR_CUDA, "planning the partitioned pass failed: %s", cudaGetErrorString(e));
 	P.bin_writers = writers;
+	P.bin_segs = writers >= 2048 ? 1u : (4096u + writers - 1) / writers;
 	double parts = (double)f->size / (double)((uint64_t)1 << shift); // fractional: the last one is partial
-	double expect = (double)P.n_windows * P.h / parts / writers;
+	double expect = (double)capacity_windows * P.h / parts / writers;
 	uint64_t cap = (uint64_t)(expect * (1.0 + ctx->bin_slack_pct / 100.0)) + 96;
 	cap = (cap + 7) / 8 * 8; // whole 32-byte lines
 	if (cap > 0x7ffffff8ULL)
@@ -916,27 +976,16 @@ static int bin_setup(btlbf_filter* f, SeqParams& P, bool query, uint32_t* grid, 
 	return BTLBF_OK;
 }
 
-static int binned_insert(btlbf_filter* f, SeqParams P, cudaStream_t s)
+// pass 2 of the partitioned build for the sub-buckets described by P: on the background stream when
+// overlapping (it then runs under the next batches' pass 1), else on s
+static int apply_pass(btlbf_ctx* ctx, const SeqParams& P, int slot, cudaStream_t s)
 {
-	btlbf_ctx* ctx = f->ctx;
-	uint32_t grid = 0;
-	const int slot = ctx->bin_slot;
-	ctx->bin_slot ^= 1;
-	TRY(bin_setup(f, P, false, &grid, ctx->ibin_items[slot], ctx->ibin_counts[slot]));
-	// pass 1 (hash + bin) on the active stream; it may not overwrite sub-buckets pass 2 is still reading
-	if (ctx->slot_used[slot])
-		CU(cudaStreamWaitEvent(s, ctx->ev_apply_done[slot], 0));
-	cudaError_t e = launch_bin(P, false, grid, s);
-	if (e != cudaSuccess)
-		return fail(BTLBF_ERR_CUDA, "partitioned build (pass 1) launch failed: %s", cudaGetErrorString(e));
-	// pass 2 (OR into the L2-resident partitions): in the background when overlapping, so that it runs
-	// under the next batch's pass 1; anything that touches the filter later waits for it (joined()).
 	cudaStream_t s2 = ctx->overlap ? ctx->aux : s;
 	if (ctx->overlap) {
 		CU(cudaEventRecord(ctx->ev_bin_done[slot], s));
 		CU(cudaStreamWaitEvent(s2, ctx->ev_bin_done[slot], 0));
 	}
-	e = launch_apply_bins(P, s2);
+	cudaError_t e = launch_apply_bins(P, s2);
 	if (e != cudaSuccess)
 		return fail(BTLBF_ERR_CUDA, "partitioned build (pass 2) launch failed: %s", cudaGetErrorString(e));
 	CU(cudaEventRecord(ctx->ev_apply_done[slot], s2));
@@ -945,9 +994,92 @@ static int binned_insert(btlbf_filter* f, SeqParams P, cudaStream_t s)
 		ctx->ev_aux_last = ctx->ev_apply_done[slot];
 		ctx->aux_pending = true;
 	}
-	ctx->launches += 2;
-	ctx->binned_launches++;
+	ctx->launches++;
 	return BTLBF_OK;
+}
+
+// Runs pass 2 for the k-mers parked in the accumulation, if any.  Everything that reads or writes filter
+// contents goes through joined(), which calls this first.
+static int settle(btlbf_ctx* ctx)
+{
+	if (!ctx->acc.f)
+		return BTLBF_OK;
+	ctx->acc.f = nullptr;
+	int rc = apply_pass(ctx, ctx->acc.P, ctx->acc.slot, ctx->active);
+	if (rc != BTLBF_OK)
+		ctx->settle_error = rc;
+	return rc;
+}
+
+static int binned_insert(btlbf_filter* f, SeqParams P, cudaStream_t s)
+{
+	btlbf_ctx* ctx = f->ctx;
+	uint32_t grid = 0;
+	int mode = 0;
+	// accumulation target in windows: the storage budget, but no more than makes pass 2's one sweep over
+	// the filter a small part of the item traffic, and never less than this batch
+	uint64_t budget = (uint64_t)ctx->bin_accum_bytes;
+	if (budget > 8 * f->bytes)
+		budget = 8 * f->bytes;
+	uint64_t target = (uint64_t)((double)budget / (4.0 * P.h * (1.0 + ctx->bin_slack_pct / 100.0)));
+	if (target < P.n_windows)
+		target = P.n_windows;
+
+	if (ctx->acc.f) {
+		// append to the running accumulation when it is this filter's and there is room
+		SeqParams Q = P;
+		const SeqParams& A = ctx->acc.P;
+		Q.bin_legacy = (uint32_t)ctx->bin_kernel;
+		uint32_t w = 0, g = 0;
+		int m = -1;
+		bool same = ctx->acc.f == f && A.filter == P.filter && A.fm.m == P.fm.m && !Q.bin_legacy &&
+		            ctx->acc.windows + P.n_windows <= ctx->acc.capacity &&
+		            bin_plan(Q, A.n_bins, false, &w, &g, &m) == cudaSuccess && m == BIN_SORT && w == A.bin_writers;
+		if (same) {
+			P.n_bins = A.n_bins; P.bin_shift = A.bin_shift; P.bin_mask = A.bin_mask; P.bin_cap = A.bin_cap;
+			P.bin_writers = A.bin_writers; P.bin_segs = A.bin_segs; P.bin_items = A.bin_items; P.bin_counts = A.bin_counts;
+			P.bin_legacy = 0;
+			P.bin_rot = (uint32_t)(ctx->acc.tiles % A.bin_writers);
+			cudaError_t e = launch_bin(P, false, A.bin_writers, s);
+			if (e != cudaSuccess)
+				return fail(BTLBF_ERR_CUDA, "partitioned build (pass 1) launch failed: %s", cudaGetErrorString(e));
+			ctx->acc.windows += P.n_windows;
+			ctx->acc.tiles += (P.n_windows + bin_sort_tile() - 1) / bin_sort_tile();
+			ctx->launches++;
+			ctx->binned_launches++;
+			return BTLBF_OK;
+		}
+		TRY(settle(ctx));
+	}
+
+	const int slot = ctx->bin_slot;
+	if (ctx->overlap)
+		ctx->bin_slot ^= 1;
+	TRY(bin_setup(f, P, false, target, &grid, &mode, ctx->ibin_items[slot], ctx->ibin_counts[slot]));
+	// pass 1 (hash + bin) on the active stream; it may not overwrite sub-buckets pass 2 is still reading
+	if (ctx->slot_used[slot])
+		CU(cudaStreamWaitEvent(s, ctx->ev_apply_done[slot], 0));
+	if (mode == BIN_SORT) {
+		CU(cudaMemsetAsync(P.bin_counts, 0, (size_t)P.n_bins * P.bin_writers * 4, s));
+		grid = P.bin_writers; // every writer runs (idle ones just keep their cursors)
+	}
+	cudaError_t e = launch_bin(P, false, grid, s);
+	if (e != cudaSuccess)
+		return fail(BTLBF_ERR_CUDA, "partitioned build (pass 1) launch failed: %s", cudaGetErrorString(e));
+	ctx->launches++;
+	ctx->binned_launches++;
+	if (mode == BIN_SORT) {
+		ctx->acc.f = f;
+		ctx->acc.P = P;
+		ctx->acc.windows = P.n_windows;
+		ctx->acc.tiles = (P.n_windows + bin_sort_tile() - 1) / bin_sort_tile();
+		ctx->acc.capacity = target;
+		ctx->acc.slot = slot;
+		if (ctx->acc.windows >= ctx->acc.capacity)
+			TRY(settle(ctx));
+		return BTLBF_OK;
+	}
+	return apply_pass(ctx, P, slot, s);
 }
 
 // Partitioned query: bin (offset, window) pairs by filter partition, test them while the partition is
@@ -957,10 +1089,12 @@ static bool want_binned_query(const btlbf_filter* f, const SeqParams& P)
 	const btlbf_ctx* ctx = f->ctx;
 	if (ctx->bin_query_mode < 0 || f->kind != BTLBF_BLOOM || f->size % 32 != 0 || P.n_windows > 0xffffffffULL)
 		return false;
-	uint32_t shift = (uint32_t)ctx->bin_part_log2;
-	if (!bin_query_supported((uint32_t)((f->size + (((uint64_t)1 << shift) - 1)) >> shift)))
-		return false;
 	if (((uintptr_t)P.hit_bits | (uintptr_t)P.valid_bits) & 3u)
+		return false;
+	SeqParams Q = P;
+	Q.bin_legacy = (uint32_t)ctx->bin_kernel;
+	uint32_t shift = 0;
+	if (!bin_geometry(f, Q, &shift) || !bin_query_supported(Q, (uint32_t)((f->size + (((uint64_t)1 << shift) - 1)) >> shift)))
 		return false;
 	if (ctx->bin_query_mode > 0)
 		return true;
@@ -971,7 +1105,9 @@ static int binned_query(btlbf_filter* f, SeqParams P, cudaStream_t s)
 {
 	btlbf_ctx* ctx = f->ctx;
 	uint32_t grid = 0;
-	TRY(bin_setup(f, P, true, &grid, ctx->qbin_items, ctx->qbin_counts));
+	int mode = 0;
+	joined(ctx); // parked k-mers first: the probes (and pass 1's overflow path) read the filter
+	TRY(bin_setup(f, P, true, P.n_windows, &grid, &mode, ctx->qbin_items, ctx->qbin_counts));
 	const uint64_t words = P.out_words;
 	if (!P.hit_bits) {
 		TRY(ensure(ctx->q_hit, words * 4));
@@ -983,11 +1119,11 @@ static int binned_query(btlbf_filter* f, SeqParams P, cudaStream_t s)
 	}
 	uint64_t* stats = P.stats;
 	CU(cudaMemsetAsync(P.hit_bits, 0xff, words * 4, s));
-	cudaError_t e = launch_bin(P, true, grid, s); // does not read the filter (bar overflow): may run under a pending pass 2
-	if (e == cudaSuccess) {
-		joined(ctx);
+	if (mode == BIN_SORT)
+		CU(cudaMemsetAsync(P.bin_counts, 0, (size_t)P.n_bins * P.bin_writers * 4, s));
+	cudaError_t e = launch_bin(P, true, grid, s);
+	if (e == cudaSuccess)
 		e = launch_probe_bins(P, s);
-	}
 	if (e == cudaSuccess)
 		e = launch_finalize_hits(P.hit_bits, P.valid_bits, words, stats ? (unsigned long long*)(stats + 1) : nullptr, s);
 	if (e != cudaSuccess)

@@ -8,7 +8,7 @@
 // Memory behaviour: the input is read once with coalesced 16-byte loads and lives in
 // shared memory as 2-bit codes; the filter traffic is one random 32-byte sector per hash (gather for
 // queries, RED.OR / byte update for inserts), so the kernels are bound by HBM random-sector rate.
-#include "tile_core.cuh"
+#include "sort_bin.cuh"
 
 #include <cooperative_groups.h>
 
@@ -97,20 +97,6 @@ __device__ __forceinline__ void sts_u32(uint32_t sa, uint32_t v)
 __device__ __forceinline__ void sts_u64(uint32_t sa, uint32_t lo, uint32_t hi)
 {
 	asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sa), "r"(lo), "r"(hi) : "memory");
-}
-
-__device__ __forceinline__ void bin_direct_or(const SeqParams& P, uint32_t part, uint32_t off)
-{
-	uint64_t n = ((uint64_t)part << P.bin_shift) | off;
-	atomicOr((uint32_t*)P.filter + (n >> 5), 1u << (uint32_t)(n & 31));
-}
-
-// query flavour: the bit is tested right away; a miss clears the window's hit bit
-__device__ __forceinline__ void bin_direct_probe(const SeqParams& P, uint32_t part, uint32_t off, uint32_t wid)
-{
-	uint64_t n = ((uint64_t)part << P.bin_shift) | off;
-	if (!((__ldg((const uint32_t*)P.filter + (n >> 5)) >> (uint32_t)(n & 31)) & 1u))
-		atomicAnd(P.hit_bits + (wid >> 5), ~(1u << (wid & 31)));
 }
 
 // Stores one full 32-byte staging line at sub-bucket item position `start`: 8 offsets (build), or 4
@@ -295,12 +281,21 @@ __global__ void __launch_bounds__(kApplyThreads) apply_bins_kernel(const __grid_
 		for (uint64_t l = (uint64_t)sub * kApplyThreads + threadIdx.x; l < lines; l += (uint64_t)blocks_per_part * kApplyThreads)
 			asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (l << 7)));
 	}
+	// work unit = one segment of one sub-bucket (bin_segs segments each, so that a partition keeps the whole
+	// GPU busy even when there are only a few hundred writers)
 	const uint32_t warps = kApplyThreads / 32, lane = threadIdx.x & 31;
-	for (uint32_t w = sub * warps + (threadIdx.x >> 5); w < P.bin_writers; w += blocks_per_part * warps) {
+	const uint32_t units = P.bin_writers * P.bin_segs;
+	for (uint32_t u = sub * warps + (threadIdx.x >> 5); u < units; u += blocks_per_part * warps) {
+		const uint32_t w = u / P.bin_segs, sg = u - w * P.bin_segs;
 		uint32_t n = __ldg(P.bin_counts + (uint64_t)part * P.bin_writers + w);
 		n = n < P.bin_cap ? n : P.bin_cap;
-		const uint32_t* items = P.bin_items + ((uint64_t)part * P.bin_writers + w) * P.bin_cap;
-		const uint4* v = reinterpret_cast<const uint4*>(items); // bin_cap is a multiple of 8
+		const uint32_t seg = ((n + P.bin_segs - 1) / P.bin_segs + 3u) & ~3u; // whole 16-byte vectors
+		const uint32_t lo = sg * seg;
+		if (lo >= n)
+			continue;
+		n = n - lo < seg ? n - lo : seg;
+		const uint32_t* items = P.bin_items + ((uint64_t)part * P.bin_writers + w) * P.bin_cap + lo;
+		const uint4* v = reinterpret_cast<const uint4*>(items); // bin_cap and lo are multiples of 4
 		const uint32_t nv = n / 4;
 		for (uint32_t i = lane; i < nv; i += 32) {
 			uint4 x = __ldcs(v + i);
@@ -340,10 +335,17 @@ __global__ void __launch_bounds__(kApplyThreads) probe_bins_kernel(const __grid_
 			asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (l << 7)));
 	}
 	const uint32_t warps = kApplyThreads / 32, lane = threadIdx.x & 31;
-	for (uint32_t w = sub * warps + (threadIdx.x >> 5); w < P.bin_writers; w += blocks_per_part * warps) {
+	const uint32_t units = P.bin_writers * P.bin_segs;
+	for (uint32_t u = sub * warps + (threadIdx.x >> 5); u < units; u += blocks_per_part * warps) {
+		const uint32_t w = u / P.bin_segs, sg = u - w * P.bin_segs;
 		uint32_t n = __ldg(P.bin_counts + (uint64_t)part * P.bin_writers + w);
 		n = n < P.bin_cap ? n : P.bin_cap;
-		const uint32_t* items = P.bin_items + ((uint64_t)part * P.bin_writers + w) * P.bin_cap * 2;
+		const uint32_t seg = ((n + P.bin_segs - 1) / P.bin_segs + 3u) & ~3u;
+		const uint32_t lo = sg * seg;
+		if (lo >= n)
+			continue;
+		n = n - lo < seg ? n - lo : seg;
+		const uint32_t* items = P.bin_items + (((uint64_t)part * P.bin_writers + w) * P.bin_cap + lo) * 2;
 		const uint4* v = reinterpret_cast<const uint4*>(items); // two items per 16 bytes
 		const uint32_t nv = n / 2;
 		for (uint32_t i = lane; i < nv; i += 32) {
@@ -374,51 +376,94 @@ __global__ void __launch_bounds__(256) finalize_hits_kernel(uint32_t* hit, const
 		atomicAdd(hits_out, acc);
 }
 
-template<bool SPACED, bool POW2>
-static cudaError_t bin_occupancy(const SeqParams& P, uint32_t n_bins, bool query, bool* warp_mode, size_t* smem_out,
-                                 int* blocks_per_sm)
+// ---------------------------------------------------------------- pass-1 kernel selection
+// BIN_SORT: bin_kernel_sort (sort_bin.cuh); BIN_WARP / BIN_CTA: the general-shape kernels above.
+struct BinKernel
 {
-	*warp_mode = n_bins <= kMaxWarpBins;
-	if (query && !*warp_mode)
-		return cudaErrorNotSupported;
-	size_t smem = *warp_mode ? bin_warp_smem_bytes(P.k, SPACED, n_bins) : tile_smem_bytes(P.k, SPACED, n_bins);
-	const void* kern = !*warp_mode ? (const void*)bin_kernel_cta<SPACED, POW2>
-	                   : query    ? (const void*)bin_kernel_warp<SPACED, POW2, true>
-	                              : (const void*)bin_kernel_warp<SPACED, POW2, false>;
-	if (smem > 48 * 1024) {
-		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	const void* fn;
+	size_t smem;
+	int threads;
+	int mode;
+	uint32_t tile; // windows per CTA pass
+};
+
+template<bool QUERY>
+static const void* warp_fn(bool spaced, bool pow2)
+{
+	if (spaced)
+		return pow2 ? (const void*)bin_kernel_warp<true, true, QUERY> : (const void*)bin_kernel_warp<true, false, QUERY>;
+	return pow2 ? (const void*)bin_kernel_warp<false, true, QUERY> : (const void*)bin_kernel_warp<false, false, QUERY>;
+}
+
+static const void* cta_fn(bool spaced, bool pow2)
+{
+	if (spaced)
+		return pow2 ? (const void*)bin_kernel_cta<true, true> : (const void*)bin_kernel_cta<true, false>;
+	return pow2 ? (const void*)bin_kernel_cta<false, true> : (const void*)bin_kernel_cta<false, false>;
+}
+
+bool bin_sort_eligible(const SeqParams& P, uint32_t n_bins)
+{
+	if (P.bin_legacy || P.h > (uint32_t)kMaxSortHashes || n_bins > kMaxSortBins)
+		return false;
+	if (P.n_seeds && P.h2 != 1)
+		return false;
+	return sort_smem_bytes(P.k, P.n_seeds != 0, n_bins, (int)P.h) <= 110 * 1024;
+}
+
+static cudaError_t bin_select(const SeqParams& P, uint32_t n_bins, bool query, BinKernel* K, int* occ)
+{
+	const bool spaced = P.n_seeds != 0, pow2 = P.fm.pow2 != 0;
+	if (bin_sort_eligible(P, n_bins)) {
+		K->mode = BIN_SORT;
+		K->threads = kSortThreads;
+		K->tile = kSortTile;
+		K->smem = sort_smem_bytes(P.k, spaced, n_bins, (int)P.h);
+		K->fn = query ? bin_sort_kernel_query((int)P.h, spaced, pow2) : bin_sort_kernel_build((int)P.h, spaced, pow2);
+	} else if (n_bins <= kMaxWarpBins) {
+		K->mode = BIN_WARP;
+		K->threads = kTPB;
+		K->tile = kTile;
+		K->smem = bin_warp_smem_bytes(P.k, spaced, n_bins);
+		K->fn = query ? warp_fn<true>(spaced, pow2) : warp_fn<false>(spaced, pow2);
+	} else {
+		if (query)
+			return cudaErrorNotSupported;
+		K->mode = BIN_CTA;
+		K->threads = kTPB;
+		K->tile = kTile;
+		K->smem = tile_smem_bytes(P.k, spaced, n_bins);
+		K->fn = cta_fn(spaced, pow2);
+	}
+	if (K->smem > 48 * 1024) {
+		cudaError_t e = cudaFuncSetAttribute(K->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K->smem);
 		if (e != cudaSuccess)
 			return e;
 	}
 	// same L1/shared split as the pass-2 kernels, so that the two passes can share an SM (kernels that ask
 	// for different carve-outs cannot be co-resident)
-	cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-	*smem_out = smem;
-	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, kTPB, smem);
+	cudaFuncSetAttribute(K->fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, K->fn, K->threads, K->smem);
 }
 
-static cudaError_t bin_dispatch(const SeqParams& P, uint32_t n_bins, bool query, bool* warp_mode, size_t* smem, int* occ)
+uint32_t bin_sort_tile()
 {
-	bool spaced = P.n_seeds != 0, pow2 = P.fm.pow2 != 0;
-	if (spaced)
-		return pow2 ? bin_occupancy<true, true>(P, n_bins, query, warp_mode, smem, occ)
-		            : bin_occupancy<true, false>(P, n_bins, query, warp_mode, smem, occ);
-	return pow2 ? bin_occupancy<false, true>(P, n_bins, query, warp_mode, smem, occ)
-	            : bin_occupancy<false, false>(P, n_bins, query, warp_mode, smem, occ);
+	return (uint32_t)kSortTile;
 }
 
-bool bin_query_supported(uint32_t n_bins)
+bool bin_query_supported(const SeqParams& P, uint32_t n_bins)
 {
-	return n_bins <= kMaxWarpBins;
+	return n_bins <= kMaxWarpBins || bin_sort_eligible(P, n_bins);
 }
 
-// number of sub-bucket writers (warps or CTAs) the bin kernel will run with, and its grid size
-cudaError_t bin_plan(const SeqParams& P, uint32_t n_bins, bool query, uint32_t* writers, uint32_t* grid)
+// number of sub-bucket writers (CTAs or warps) the bin kernel will run with, its grid size and flavour.
+// BIN_SORT: the writer count does not depend on the batch (so that launches can append to the same
+// sub-buckets); only the first `grid` writers run when the batch has fewer tiles than that.
+cudaError_t bin_plan(const SeqParams& P, uint32_t n_bins, bool query, uint32_t* writers, uint32_t* grid, int* mode)
 {
-	size_t smem;
-	bool warp_mode;
+	BinKernel K;
 	int occ = 0, dev = 0, sms = 0;
-	cudaError_t e = bin_dispatch(P, n_bins, query, &warp_mode, &smem, &occ);
+	cudaError_t e = bin_select(P, n_bins, query, &K, &occ);
 	if (e != cudaSuccess)
 		return e;
 	if ((e = cudaGetDevice(&dev)) != cudaSuccess)
@@ -427,47 +472,30 @@ cudaError_t bin_plan(const SeqParams& P, uint32_t n_bins, bool query, uint32_t* 
 		return e;
 	if (occ < 1)
 		return cudaErrorLaunchOutOfResources;
-	uint64_t tiles = (P.n_windows + kTile - 1) / kTile;
-	uint64_t g = (uint64_t)sms * (uint64_t)occ;
-	g = tiles < g ? (tiles ? tiles : 1) : g;
+	uint64_t tiles = (P.n_windows + K.tile - 1) / K.tile;
+	uint64_t full = (uint64_t)sms * (uint64_t)occ;
+	uint64_t g = tiles < full ? (tiles ? tiles : 1) : full;
 	*grid = (uint32_t)g;
-	*writers = (uint32_t)(warp_mode ? g * (kTPB / 32) : g);
+	*mode = K.mode;
+	*writers = (uint32_t)(K.mode == BIN_SORT ? full : K.mode == BIN_WARP ? g * (kTPB / 32) : g);
 	return cudaSuccess;
 }
 
 cudaError_t launch_bin(const SeqParams& P, bool query, uint32_t grid, cudaStream_t stream)
 {
-	size_t smem;
-	bool warp_mode;
+	BinKernel K;
 	int occ = 0;
-	cudaError_t e = bin_dispatch(P, P.n_bins, query, &warp_mode, &smem, &occ);
+	cudaError_t e = bin_select(P, P.n_bins, query, &K, &occ);
 	if (e != cudaSuccess)
 		return e;
-	bool spaced = P.n_seeds != 0, pow2 = P.fm.pow2 != 0;
-#define BTL_LAUNCH_BIN(KERN, ...)                                                         \
-	do {                                                                                  \
-		if (spaced) {                                                                     \
-			if (pow2) KERN<true, true, ##__VA_ARGS__><<<grid, kTPB, smem, stream>>>(P);   \
-			else KERN<true, false, ##__VA_ARGS__><<<grid, kTPB, smem, stream>>>(P);       \
-		} else {                                                                          \
-			if (pow2) KERN<false, true, ##__VA_ARGS__><<<grid, kTPB, smem, stream>>>(P);  \
-			else KERN<false, false, ##__VA_ARGS__><<<grid, kTPB, smem, stream>>>(P);      \
-		}                                                                                 \
-	} while (0)
-	if (!warp_mode)
-		BTL_LAUNCH_BIN(bin_kernel_cta);
-	else if (query)
-		BTL_LAUNCH_BIN(bin_kernel_warp, true);
-	else
-		BTL_LAUNCH_BIN(bin_kernel_warp, false);
-#undef BTL_LAUNCH_BIN
-	return cudaGetLastError();
+	void* args[1] = { (void*)&P };
+	return cudaLaunchKernel(K.fn, dim3(grid), dim3((unsigned)K.threads), args, K.smem, stream);
 }
 
 static uint32_t blocks_per_partition(const SeqParams& P)
 {
 	// enough blocks per partition to fill the GPU, never more warps than sub-buckets
-	uint32_t want = (P.bin_writers + (kApplyThreads / 32) - 1) / (kApplyThreads / 32);
+	uint32_t want = (P.bin_writers * P.bin_segs + (kApplyThreads / 32) - 1) / (kApplyThreads / 32);
 	return want < 592u ? (want ? want : 1u) : 592u;
 }
 

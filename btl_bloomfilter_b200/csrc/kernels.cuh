@@ -63,6 +63,9 @@ struct SeqParams
 	uint32_t bin_cap;
 	uint32_t bin_writers;
 	uint32_t n_bins;
+	uint32_t bin_segs;    // pass 2 splits every sub-bucket into this many segments (work units)
+	uint32_t bin_legacy;  // knob: never use the sort-bin kernel
+	uint32_t bin_rot;     // sort-bin kernel: tile t goes to writer (t + bin_rot) % bin_writers
 	// outputs (chunk-local indexing by window)
 	uint32_t* hit_bits;
 	uint32_t* valid_bits;
@@ -85,13 +88,16 @@ cudaError_t launch_seq(SeqOp op, const SeqParams& P, cudaStream_t stream);
 // launch_apply_bins: pass 2 (per partition, OR the binned offsets into the L2-resident filter region).
 // query == true: the partitioned QUERY (items are (offset, window) pairs; pass 2 = launch_probe_bins, then
 // launch_finalize_hits ANDs the hit words with the valid words and counts the hits).
-cudaError_t bin_plan(const SeqParams& P, uint32_t n_bins, bool query, uint32_t* writers, uint32_t* grid);
+enum BinMode { BIN_SORT = 0, BIN_WARP = 1, BIN_CTA = 2 };
+cudaError_t bin_plan(const SeqParams& P, uint32_t n_bins, bool query, uint32_t* writers, uint32_t* grid, int* mode);
 cudaError_t launch_bin(const SeqParams& P, bool query, uint32_t grid, cudaStream_t stream);
 cudaError_t launch_apply_bins(const SeqParams& P, cudaStream_t stream);
 cudaError_t launch_probe_bins(const SeqParams& P, cudaStream_t stream);
 cudaError_t launch_finalize_hits(uint32_t* hit, const uint32_t* valid, uint64_t n_words, unsigned long long* hits_out,
                                  cudaStream_t stream);
-bool bin_query_supported(uint32_t n_bins);
+bool bin_query_supported(const SeqParams& P, uint32_t n_bins);
+bool bin_sort_eligible(const SeqParams& P, uint32_t n_bins); // the sort-bin kernel (sort_bin.cuh) serves this shape
+uint32_t bin_sort_tile();                                    // windows per CTA pass of the sort-bin kernel
 
 // residual rounds of the ordered updates on the compacted list of deferred windows
 struct ListParams

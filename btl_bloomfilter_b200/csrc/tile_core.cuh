@@ -85,14 +85,15 @@ struct TileSmem
 	uint32_t nb;       // staged bytes (multiple of 32)
 };
 
-BTL_HD uint32_t tile_bytes(uint32_t k)
+BTL_HD uint32_t tile_bytes(uint32_t k, uint32_t tile = (uint32_t)kTile)
 {
-	return ((uint32_t)kTile + k - 1 + 31u) / 32u * 32u + 32u;
+	return (tile + k - 1 + 31u) / 32u * 32u + 32u;
 }
 
-BTL_HD size_t tile_smem_bytes(uint32_t k, bool spaced, uint32_t nbins = 0)
+// tile: windows staged per CTA pass (kTile for the kTPB-thread kernels, kSortTile for the sort-bin kernel)
+BTL_HD size_t tile_smem_bytes(uint32_t k, bool spaced, uint32_t nbins = 0, uint32_t tile = (uint32_t)kTile)
 {
-	uint32_t nb = tile_bytes(k);
+	uint32_t nb = tile_bytes(k, tile);
 	size_t s = nb;                       // tile
 	s += (nb / 16 + 4) * 4;              // codes
 	s += (nb / 32 + 4) * 4 * 2;          // badw, startw
@@ -104,10 +105,10 @@ BTL_HD size_t tile_smem_bytes(uint32_t k, bool spaced, uint32_t nbins = 0)
 	return (s + 15) / 16 * 16;
 }
 
-BTL_HD TileSmem carve_smem(uint8_t* raw, uint32_t k, bool spaced, uint32_t nbins = 0)
+BTL_HD TileSmem carve_smem(uint8_t* raw, uint32_t k, bool spaced, uint32_t nbins = 0, uint32_t tile = (uint32_t)kTile)
 {
 	TileSmem sm;
-	sm.nb = tile_bytes(k);
+	sm.nb = tile_bytes(k, tile);
 	uint8_t* p = raw;
 	sm.gtab = (uint64_t*)p;    p += 64 * 8;
 	sm.scratch = (uint64_t*)p; p += 16 * 8;

@@ -318,10 +318,12 @@ def test_errors_are_reported_not_fatal(gpu):
 
 
 # ---------------------------------------------------------------- partitioned (binned) BloomFilter build
+@pytest.mark.parametrize("legacy", [0, 1])
 @pytest.mark.parametrize("shift", [8, 12, 20])
-def test_binned_build_equals_oracle(oracle, golden, shift):
+def test_binned_build_equals_oracle(oracle, golden, shift, legacy):
+    """legacy=0: the sort-bin kernel (sort_bin.cuh) wherever the shape allows; 1: the general-shape kernels"""
     from _backends import GpuBackend
-    be = GpuBackend(bin_shift=shift)
+    be = GpuBackend(bin_shift=shift, bin_kernel=legacy)
     S.check_golden_bf(be, golden)
     S.check_random_bf(be, oracle, 25, 4, 1 << 16, seed=3)
     S.check_random_bf(be, oracle, 32, 6, 32 * 1237, seed=4)
@@ -329,15 +331,48 @@ def test_binned_build_equals_oracle(oracle, golden, shift):
     S.check_cfg1(be, oracle, golden)
 
 
-def test_binned_build_skewed_input(oracle):
+@pytest.mark.parametrize("legacy", [0, 1])
+def test_binned_build_skewed_input(oracle, legacy):
+    """sub-buckets without slack + repetitive input: the overflow path (direct atomics / direct probes)"""
     from _backends import GpuBackend
-    be = GpuBackend(bin_shift=8, bin_slack_pct=0)
+    be = GpuBackend(bin_shift=8, bin_slack_pct=0, bin_kernel=legacy)
     f = be.filter(0, 1 << 14, 4, 11)
     seqs = ["A" * 30000, "ACGT" * 5000, "ACGTTGCA" * 3000]
     b, off = O.as_batch(seqs)
     filt = np.zeros((1 << 14) // 8, np.uint8)
     assert f.insert(seqs) == oracle.bf_insert_seqs(filt, 1 << 14, 4, 11, b, off)
     assert np.array_equal(f.bytes(), filt)
+    q = seqs + ["ACGTTGCATTGACCA" * 2000, "C" * 20000]
+    qb, qoff = O.as_batch(q)
+    nk, nh, hit, valid = f.contains(q)
+    onk, onh, ohit, ovalid = oracle.bf_contains_seqs(filt, 1 << 14, 4, 11, qb, qoff)
+    assert (nk, nh) == (onk, onh)
+    assert np.array_equal(hit, ohit) and np.array_equal(valid, ovalid)
+
+
+@pytest.mark.parametrize("accum_bytes", [1 << 33, 1 << 16, 0])
+def test_binned_build_accumulates_across_calls(oracle, accum_bytes):
+    """Pass 1 of successive insert calls appends to the same sub-buckets; pass 2 runs when they are full or the
+    filter is read.  Two filters are interleaved, one of them re-hashed with spaced seeds half way."""
+    from _backends import GpuBackend
+    be = GpuBackend(bin_shift=10, bin_accum_bytes=accum_bytes)
+    bits, h, k = 1 << 18, 4, 21
+    f1, f2 = be.filter(0, bits, h, k), be.filter(0, 3 * 32 * 1031, 3, 15)
+    a1, a2 = np.zeros(bits // 8, np.uint8), np.zeros(3 * 32 * 1031 // 8, np.uint8)
+    rng = np.random.default_rng(11)
+    for i in range(7):
+        b, off = S.rand_batch(rng, 5 + i, 3000 + 500 * i, p_n=0.002)
+        assert f1.insert((b, off)) == oracle.bf_insert_seqs(a1, bits, h, k, b, off)
+        if i % 3 == 2:
+            assert f2.insert((b, off)) == oracle.bf_insert_seqs(a2, 3 * 32 * 1031, 3, 15, b, off)
+        if i == 4:
+            assert np.array_equal(f1.bytes(), a1)  # a read in the middle settles the accumulation
+    assert np.array_equal(f1.bytes(), a1)
+    assert np.array_equal(f2.bytes(), a2)
+    qb, qoff = S.rand_batch(rng, 6, 4000)
+    nk, nh, hit, valid = f1.contains((qb, qoff))
+    onk, onh, ohit, ovalid = oracle.bf_contains_seqs(a1, bits, h, k, qb, qoff)
+    assert (nk, nh) == (onk, onh) and np.array_equal(hit, ohit) and np.array_equal(valid, ovalid)
 
 
 def test_binned_build_full_size_equals_direct_build(gpu, oracle):
