@@ -44,6 +44,11 @@ SIGNATURES = {
     "btlbf_filter_set_seeds": [vp, cpp, u32, u32],
     "btlbf_filter_merge_from_device": [vp, vp, u64],
     "btlbf_merge_device_buffers": [vp, C.c_int, vp, vp, u64],
+    "btlbf_merge_slice": [u64, C.c_int, C.c_int, u64p, u64p],
+    "btlbf_ipc_export": [vp, vp, vp, u64p],
+    "btlbf_ipc_open": [vp, vp, C.POINTER(vp)],
+    "btlbf_ipc_close": [vp, vp],
+    "btlbf_merge_peers": [vp, C.c_int, C.POINTER(vp), C.c_int, C.c_int, u64],
     "btlbf_filter_ordered_stats": [vp, u64p, u64p],
     "btlbf_insert_seqs": [vp, vp, u64p, u64, u64p],
     "btlbf_contains_seqs": [vp, vp, u64p, u64, vp, vp, u64p, u64p],

@@ -739,6 +739,97 @@ extern "C" int btlbf_merge_device_buffers(btlbf_ctx* ctx, int kind, void* dst_de
 	return BTLBF_OK;
 }
 
+// ---------------------------------------------------------------- fused multi-GPU merge (peer memory)
+extern "C" int btlbf_merge_slice(uint64_t nbytes, int world, int rank, uint64_t* lo, uint64_t* hi)
+{
+	if (world < 1 || rank < 0 || rank >= world || !lo || !hi)
+		return fail(BTLBF_ERR_ARG, "bad world / rank");
+	uint64_t nvec = (nbytes + 15) / 16;
+	uint64_t per = (nvec + (uint64_t)world - 1) / (uint64_t)world;
+	uint64_t a = (uint64_t)rank * per, b = a + per;
+	a = a > nvec ? nvec : a;
+	b = b > nvec ? nvec : b;
+	*lo = a * 16;
+	*hi = b * 16;
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_ipc_export(btlbf_ctx* ctx, const void* device_ptr, void* handle64, uint64_t* offset)
+{
+	if (!device_ptr || !handle64 || !offset)
+		return fail(BTLBF_ERR_ARG, "null argument");
+	TRY(use(ctx));
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+	// the handle names a whole cudaMalloc allocation: find its base (the pointer may sit inside a block of
+	// a caching allocator)
+	cudaPointerAttributes attr;
+	CU(cudaPointerGetAttributes(&attr, device_ptr));
+	if (attr.type != cudaMemoryTypeDevice)
+		return fail(BTLBF_ERR_ARG, "not a device pointer");
+	// (driver entry point fetched through the runtime: the library does not link libcuda)
+	typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+	void* fn = nullptr;
+	cudaDriverEntryPointQueryResult qr;
+	CU(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+	if (!fn || qr != cudaDriverEntryPointSuccess)
+		return fail(BTLBF_ERR_CUDA, "cuMemGetAddressRange is not available");
+	unsigned long long base = 0;
+	size_t size = 0;
+	int r = ((range_fn)fn)(&base, &size, (unsigned long long)(uintptr_t)device_ptr);
+	if (r != 0)
+		return fail(BTLBF_ERR_CUDA, "cuMemGetAddressRange failed (%d)", r);
+	cudaIpcMemHandle_t h;
+	CU(cudaIpcGetMemHandle(&h, (void*)(uintptr_t)base));
+	memcpy(handle64, &h, 64);
+	*offset = (uint64_t)((unsigned long long)(uintptr_t)device_ptr - base);
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_ipc_open(btlbf_ctx* ctx, const void* handle64, void** mapped_base)
+{
+	if (!handle64 || !mapped_base)
+		return fail(BTLBF_ERR_ARG, "null argument");
+	TRY(use(ctx));
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, 64);
+	CU(cudaIpcOpenMemHandle(mapped_base, h, cudaIpcMemLazyEnablePeerAccess));
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_ipc_close(btlbf_ctx* ctx, void* mapped_base)
+{
+	TRY(use(ctx));
+	if (mapped_base)
+		CU(cudaIpcCloseMemHandle(mapped_base));
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_merge_peers(btlbf_ctx* ctx, int kind, void* const* bases, int world, int rank, uint64_t nbytes)
+{
+	if (!bases || world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+		return fail(BTLBF_ERR_ARG, "bad peer list (world %d, rank %d; at most %d peers)", world, rank, kMaxPeers);
+	if (kind != BTLBF_BLOOM && kind != BTLBF_COUNTING8)
+		return fail(BTLBF_ERR_ARG, "bad filter kind");
+	TRY(use(ctx));
+	PeerMergeParams M;
+	memset(&M, 0, sizeof M);
+	// start with the local copy, then the peers in ring order so that the ranks do not all hit one GPU at once
+	for (int i = 0; i < world; i++) {
+		void* b = bases[(rank + i) % world];
+		if (!b || ((uintptr_t)b & 15u))
+			return fail(BTLBF_ERR_ARG, "peer base %d is null or not 16-byte aligned", (rank + i) % world);
+		M.base[i] = (uint8_t*)b;
+	}
+	M.world = (uint32_t)world;
+	M.sat_add = kind == BTLBF_COUNTING8;
+	TRY(btlbf_merge_slice(nbytes, world, rank, &M.lo, &M.hi));
+	cudaError_t e = launch_peer_merge(M, joined(ctx));
+	if (e != cudaSuccess)
+		return fail(BTLBF_ERR_CUDA, "peer merge launch failed: %s", cudaGetErrorString(e));
+	ctx->launches++;
+	return BTLBF_OK;
+}
+
 // ---------------------------------------------------------------- ordered (exact) updates
 static int ordered_state(btlbf_filter* f, uint32_t batch)
 {

@@ -917,6 +917,71 @@ __global__ void __launch_bounds__(256) merge_kernel(uint8_t* __restrict__ dst, c
 	}
 }
 
+// ---------------------------------------------------------------- K7 fused: reduce-scatter + all-gather over peer memory
+// One kernel per GPU replaces  all-to-all of 1/N slices -> local reduce -> all-gather:  this rank owns
+// the byte range [lo, hi) of the filter; every 16-byte vector of it is loaded from all N partial filters
+// (its own HBM and the peers' memory mapped over NVLink), reduced (OR / saturating add) in registers and
+// stored into all N filters.  No staging buffer, one pass; the NVLink loads of one vector overlap the
+// stores of the previous ones.  Ranges of different ranks are disjoint, so the kernels of all ranks run
+// concurrently; the host brackets them with barriers.
+template<int WORLD>
+__global__ void __launch_bounds__(256) peer_merge_kernel(const __grid_constant__ PeerMergeParams M)
+{
+	const uint64_t nvec = (M.hi - M.lo) / 16;
+	const int world = WORLD ? WORLD : (int)M.world;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (uint64_t)gridDim.x * blockDim.x) {
+		const uint64_t o = M.lo + i * 16;
+		uint4 v[WORLD ? WORLD : 1];
+		uint4 acc;
+		if (WORLD) {
+#pragma unroll
+			for (int p = 0; p < WORLD; p++)
+				v[p] = *reinterpret_cast<const uint4*>(M.base[p] + o);
+			acc = v[0];
+#pragma unroll
+			for (int p = 1; p < WORLD; p++) {
+				if (M.sat_add) {
+					acc.x = __vaddus4(acc.x, v[p].x); acc.y = __vaddus4(acc.y, v[p].y);
+					acc.z = __vaddus4(acc.z, v[p].z); acc.w = __vaddus4(acc.w, v[p].w);
+				} else {
+					acc.x |= v[p].x; acc.y |= v[p].y; acc.z |= v[p].z; acc.w |= v[p].w;
+				}
+			}
+		} else {
+			acc = *reinterpret_cast<const uint4*>(M.base[0] + o);
+			for (int p = 1; p < world; p++) {
+				uint4 b = *reinterpret_cast<const uint4*>(M.base[p] + o);
+				if (M.sat_add) {
+					acc.x = __vaddus4(acc.x, b.x); acc.y = __vaddus4(acc.y, b.y);
+					acc.z = __vaddus4(acc.z, b.z); acc.w = __vaddus4(acc.w, b.w);
+				} else {
+					acc.x |= b.x; acc.y |= b.y; acc.z |= b.z; acc.w |= b.w;
+				}
+			}
+		}
+		for (int p = 0; p < world; p++)
+			*reinterpret_cast<uint4*>(M.base[p] + o) = acc;
+	}
+}
+
+cudaError_t launch_peer_merge(const PeerMergeParams& M, cudaStream_t stream)
+{
+	if (M.world < 1 || M.world > (uint32_t)kMaxPeers || M.lo > M.hi || ((M.lo | M.hi) & 15u))
+		return cudaErrorInvalidValue;
+	uint64_t nvec = (M.hi - M.lo) / 16;
+	if (nvec == 0)
+		return cudaSuccess;
+	uint64_t want = (nvec + 255) / 256;
+	unsigned grid = (unsigned)(want > 148 * 8 ? 148 * 8 : want);
+	switch (M.world) {
+	case 2: peer_merge_kernel<2><<<grid, 256, 0, stream>>>(M); break;
+	case 4: peer_merge_kernel<4><<<grid, 256, 0, stream>>>(M); break;
+	case 8: peer_merge_kernel<8><<<grid, 256, 0, stream>>>(M); break;
+	default: peer_merge_kernel<0><<<grid, 256, 0, stream>>>(M); break;
+	}
+	return cudaGetLastError();
+}
+
 cudaError_t launch_merge(void* dst, const void* src, uint64_t nbytes, int saturating_add, cudaStream_t stream)
 {
 	uint64_t nvec = nbytes / 16;

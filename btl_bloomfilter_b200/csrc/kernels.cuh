@@ -134,6 +134,17 @@ cudaError_t launch_popcount(const void* data, uint64_t nbytes, int mode, unsigne
                             unsigned long long* d_out, cudaStream_t stream);
 cudaError_t launch_merge(void* dst, const void* src, uint64_t nbytes, int saturating_add,
                          cudaStream_t stream);
+// fused multi-GPU merge over peer-mapped memory: base[p] = rank p's partial filter (base[rank] is local);
+// this rank reduces bytes [lo, hi) of all of them and stores the result into all of them
+constexpr int kMaxPeers = 16;
+struct PeerMergeParams
+{
+	uint8_t* base[kMaxPeers];
+	uint32_t world;
+	int sat_add;
+	uint64_t lo, hi; // multiples of 16
+};
+cudaError_t launch_peer_merge(const PeerMergeParams& M, cudaStream_t stream);
 cudaError_t launch_synth_genome(uint8_t* out, uint64_t start, uint64_t n, uint64_t seed,
                                 cudaStream_t stream);
 cudaError_t launch_synth_reads(uint8_t* out, uint64_t first_read, uint64_t n_reads,

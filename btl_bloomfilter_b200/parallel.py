@@ -7,8 +7,17 @@ reference layout by   all-to-all of 1/N array slices  ->  local OR (BloomFilter)
 so the merged BloomFilter is bit-identical to a single-GPU build of the same sequences for any sharding.
 The counting merge (saturating add of per-shard incrementMin builds) is a different function from the
 sequential single-filter build; its oracle is "N sequential partial builds, then saturating add".
+
+Two implementations of that merge:
+  merge_partials / merge_filter   NCCL all-to-all + local reduce kernel + NCCL all-gather (also the gloo
+                                  path of the CPU tests)
+  PeerMerge / fused_merge_filter  ONE kernel per GPU over peer-mapped memory (CUDA IPC + NVLink loads and
+                                  stores): each rank reduces its 1/N byte range of all N partial filters
+                                  in registers and writes the result into all N of them -- no staging
+                                  buffer, no separate reduce pass (btlbf_merge_peers)
 """
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -129,6 +138,108 @@ def bench_merge(filt, ctx, dev, repeats=3):
     dist.all_gather(pops, pop)
     ms = float(tt[0])
     traffic = 2.0 * (world - 1) / world * pad  # bytes sent (= received) per GPU: all-to-all + all-gather
-    return {"ms": ms, "filter_bytes": int(nbytes), "bytes_per_gpu_each_way": int(traffic),
-            "GBps_per_gpu_each_way": traffic / (ms * 1e-3) / 1e9,
-            "identical_popcount_on_all_ranks": len({int(p) for p in pops}) == 1, "popcount": int(pops[0])}
+    out = {"nccl_ms": ms, "filter_bytes": int(nbytes), "bytes_per_gpu_each_way": int(traffic),
+           "nccl_GBps_per_gpu_each_way": traffic / (ms * 1e-3) / 1e9,
+           "identical_popcount_on_all_ranks": len({int(p) for p in pops}) == 1, "popcount": int(pops[0])}
+    # the fused kernel over peer memory, on the (already merged, hence idempotent under OR) filters
+    if filt.KIND == 0:
+        pm = PeerMerge(ctx, ptr, nbytes, filt.KIND)
+        times = []
+        for _ in range(repeats):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            dist.barrier()
+            a.record()
+            pm.launch()
+            b.record()
+            torch.cuda.synchronize()
+            dist.barrier()
+            times.append(a.elapsed_time(b))
+        pm.close()
+        tf = torch.tensor([min(times)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        pop2 = torch.tensor([filt.getPop()], dtype=torch.int64, device=dev)
+        pops2 = [torch.zeros_like(pop2) for _ in range(world)]
+        dist.all_gather(pops2, pop2)
+        out["fused_ms"] = float(tf[0])
+        out["fused_GBps_per_gpu_each_way"] = traffic / (float(tf[0]) * 1e-3) / 1e9
+        out["fused_popcount_unchanged"] = all(int(p) == int(pops[0]) for p in pops2)
+    out["ms"] = min(ms, out.get("fused_ms", ms))
+    return out
+
+
+def merge_slice(nbytes, rank, world):
+    """Byte range [lo, hi) of an nbytes filter that `rank` reduces in the fused merge (16-byte granules;
+    the same arithmetic as btlbf_merge_slice)."""
+    nvec = (int(nbytes) + 15) // 16
+    per = (nvec + world - 1) // world
+    lo, hi = min(rank * per, nvec), min((rank + 1) * per, nvec)
+    return lo * 16, hi * 16
+
+
+class PeerMerge:
+    """Peer mappings of one device array per rank (CUDA IPC), reusable for any number of fused merges.
+
+    ptr / nbytes: this rank's partial filter (raw device memory of identical size on every rank: the
+    library's own allocation, f.device_ptr(), or a torch tensor's storage).  Collective: every rank of
+    `group` must construct it, merge() and close() together."""
+
+    def __init__(self, ctx, ptr, nbytes, kind, group=None):
+        from ._capi import check
+        self.ctx, self.kind, self.nbytes, self.group = ctx, kind, int(nbytes), group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        L = ctx.L
+        handle = (C.c_uint8 * 64)()
+        off = C.c_uint64()
+        check(L.btlbf_ipc_export(ctx.handle, C.c_void_p(ptr), handle, C.byref(off)))
+        mine = (bytes(handle), int(off.value), int(nbytes), os.getpid())
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        assert all(e[2] == self.nbytes for e in everyone), "partial filters differ in size across ranks"
+        self._mapped = []
+        bases = (C.c_void_p * self.world)()
+        for p, (h, o, _, pid) in enumerate(everyone):
+            if p == self.rank:
+                bases[p] = ptr
+                continue
+            hb = (C.c_uint8 * 64).from_buffer_copy(h)
+            base = C.c_void_p()
+            check(L.btlbf_ipc_open(ctx.handle, hb, C.byref(base)))
+            self._mapped.append(base.value)
+            bases[p] = base.value + o
+        self._bases = bases
+
+    def merge(self):
+        """Every rank's array := reduce(all arrays).  Ranks are synchronised before and after."""
+        from ._capi import check
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)  # all partial builds are complete and visible
+        check(self.ctx.L.btlbf_merge_peers(self.ctx.handle, self.kind, self._bases, self.world, self.rank,
+                                           self.nbytes))
+        self.ctx.sync()
+        dist.barrier(group=self.group)  # all ranges have been written everywhere
+
+    def launch(self):
+        """The kernel alone (for timing): the caller brackets it with synchronize + barrier."""
+        from ._capi import check
+        check(self.ctx.L.btlbf_merge_peers(self.ctx.handle, self.kind, self._bases, self.world, self.rank,
+                                           self.nbytes))
+
+    def close(self):
+        from ._capi import check
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for b in self._mapped:
+            check(self.ctx.L.btlbf_ipc_close(self.ctx.handle, C.c_void_p(b)))
+        self._mapped = []
+
+
+def fused_merge_filter(filt, group=None):
+    """One-shot fused merge of the per-rank partial filters behind `filt` (any filter of the library)."""
+    ptr, nbytes = filt.device_ptr()
+    pm = PeerMerge(filt._ctx, ptr, nbytes, filt.KIND, group)
+    try:
+        pm.merge()
+    finally:
+        pm.close()

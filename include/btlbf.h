@@ -127,6 +127,22 @@ int btlbf_filter_merge_from_device(btlbf_filter *f, const void *src_device, uint
  * or dst = saturating dst + src (COUNTING8), asynchronous on the context's stream */
 int btlbf_merge_device_buffers(btlbf_ctx *ctx, int kind, void *dst_device, const void *src_device,
                                uint64_t nbytes);
+/* ---- fused multi-GPU merge over peer memory (one process per GPU; replaces the reference-side pattern
+ * "build one filter per thread/process, then OR them": BloomFilter.hpp has no merge, callers OR the
+ * arrays byte by byte) ----
+ * btlbf_merge_slice: the byte range [lo, hi) of an nbytes filter that rank reduces (16-byte granules).
+ * btlbf_ipc_export / _open / _close: CUDA IPC plumbing so that every process can map its peers' filter
+ * arrays (handle64 = 64 opaque bytes naming the allocation that contains device_ptr, offset = position
+ * of device_ptr inside it; exchange both through any host channel, e.g. torch.distributed).
+ * btlbf_merge_peers: ONE kernel on this GPU that reads range `rank` of all `world` partial filters
+ * (bases[p] = rank p's array as mapped in this process, bases[rank] the local one) over NVLink, reduces
+ * them (OR for BLOOM, saturating add for COUNTING8) and stores the result into all of them.  The caller
+ * synchronises the ranks before (all partial builds done) and after (all ranges written). */
+int btlbf_merge_slice(uint64_t nbytes, int world, int rank, uint64_t *lo, uint64_t *hi);
+int btlbf_ipc_export(btlbf_ctx *ctx, const void *device_ptr, void *handle64, uint64_t *offset);
+int btlbf_ipc_open(btlbf_ctx *ctx, const void *handle64, void **mapped_base);
+int btlbf_ipc_close(btlbf_ctx *ctx, void *mapped_base);
+int btlbf_merge_peers(btlbf_ctx *ctx, int kind, void *const *bases, int world, int rank, uint64_t nbytes);
 /* order-dependent updates (counting insert, insert_and_check): number of k-mers that had to wait for
  * the index-ordered residual rounds, and the number of such rounds, since the filter was created */
 int btlbf_filter_ordered_stats(btlbf_filter *f, uint64_t *deferred, uint64_t *rounds);

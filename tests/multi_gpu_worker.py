@@ -45,6 +45,20 @@ def main():
     assert np.array_equal(got, filt), "rank %d: merged BloomFilter differs from the single-build oracle" % rank
     assert not t[nbytes:].any()
 
+    # ---- the same merge as ONE kernel per GPU over peer-mapped memory (CUDA IPC + NVLink loads/stores)
+    t2 = torch.zeros(parallel.padded_bytes(nbytes, world), dtype=torch.uint8, device=dev)
+    f2 = B.BloomFilter.from_device_memory(t2, bits, h, k, ctx=ctx)
+    f2.insertSeqs(my)
+    parallel.fused_merge_filter(f2)
+    assert np.array_equal(f2.to_numpy(), filt), "rank %d: fused peer-memory merge differs from the oracle" % rank
+    f3 = B.BloomFilter(bits, h, k, ctx=ctx)  # the library's own allocation, merged twice (OR is idempotent)
+    f3.insertSeqs(my)
+    pm = parallel.PeerMerge(ctx, *f3.device_ptr(), f3.KIND)
+    pm.merge()
+    pm.merge()
+    pm.close()
+    assert np.array_equal(f3.to_numpy(), filt)
+
     # ---- query: filter replicated (after the merge), reads sharded, no collective
     r = f.containsSeqs(my)
     nq, nh, hits, valid = orc.bf_contains_seqs(filt, bits, h, k, my[0], my[1])
@@ -69,6 +83,10 @@ def main():
         exp += part
     exp = np.minimum(exp, 255).astype(np.uint8)
     assert np.array_equal(c.to_numpy(), exp), "rank %d: merged counters differ" % rank
+    c2 = B.CountingBloomFilter(m, h, k, 2, ctx=ctx)
+    c2.insertSeqs(my)
+    parallel.fused_merge_filter(c2)
+    assert np.array_equal(c2.to_numpy(), exp), "rank %d: fused saturating-add merge differs" % rank
     dist.barrier()
     if rank == 0:
         print("MULTI-GPU OK world=%d" % world)

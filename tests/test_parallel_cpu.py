@@ -87,3 +87,22 @@ def test_slice_geometry():
     assert cover[0][0] == 0 and cover[-1][1] == 45
     assert all(cover[i][1] == cover[i + 1][0] for i in range(7))
     assert max(b - a for a, b in cover) - min(b - a for a, b in cover) <= 1
+
+
+def test_fused_merge_slices_partition_the_filter():
+    """btlbf_merge_slice / parallel.merge_slice: the ranks' byte ranges are 16-byte granules, disjoint, and
+    cover the (16-byte padded) filter exactly; the C ABI and the Python mirror agree."""
+    import ctypes as C
+    from btl_bloomfilter_b200 import lib, parallel
+    L = lib()
+    for nbytes in (0, 1, 16, 17, 300_007 * 8, 3_946_014_232, 100_008):
+        for world in (1, 2, 3, 4, 8, 16):
+            end = 0
+            for rank in range(world):
+                lo, hi = C.c_uint64(), C.c_uint64()
+                assert L.btlbf_merge_slice(nbytes, world, rank, C.byref(lo), C.byref(hi)) == 0
+                assert (lo.value, hi.value) == parallel.merge_slice(nbytes, rank, world)
+                assert lo.value % 16 == 0 and hi.value % 16 == 0 and lo.value <= hi.value
+                assert lo.value == end
+                end = hi.value
+            assert end == (nbytes + 15) // 16 * 16
