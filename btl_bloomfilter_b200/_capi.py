@@ -50,6 +50,12 @@ SIGNATURES = {
     "btlbf_ipc_close": [vp, vp],
     "btlbf_merge_peers": [vp, C.c_int, C.POINTER(vp), C.c_int, C.c_int, u64],
     "btlbf_filter_ordered_stats": [vp, u64p, u64p],
+    "btlbf_insert_file": [vp, C.c_char_p, C.c_int, u64p, u64p],
+    "btlbf_query_file": [vp, C.c_char_p, C.c_int, u64p, u64p, u64p],
+    "btlbf_seqfile_open": [C.c_char_p, u32, C.c_int, C.c_int, C.POINTER(vp)],
+    "btlbf_seqfile_next": [vp, vp, u64, u64p, u64, u64p, u64p, u64p, C.POINTER(C.c_int)],
+    "btlbf_seqfile_close": [vp],
+    "btlbf_filter_ctx": [vp, C.POINTER(vp)],
     "btlbf_insert_seqs": [vp, vp, u64p, u64, u64p],
     "btlbf_contains_seqs": [vp, vp, u64p, u64, vp, vp, u64p, u64p],
     "btlbf_insert_seqs_async": [vp, vp, u64p, u64, vp],

@@ -94,8 +94,8 @@ struct btlbf_ctx
 	unsigned long long* h_scalars = nullptr; // pinned mirror
 	int64_t force_generic = 0, query_mode = 0;
 	int64_t chunk_bases = (int64_t)64 << 20; // windows per pipeline stage of the host-buffer calls
-	int64_t cbf_batch = (int64_t)1 << 20;    // windows per batch of the ordered (exact) updates
-	int64_t resv_log2 = 28, list_log2 = 22;
+	int64_t cbf_batch = (int64_t)4 << 20;    // windows per batch of the ordered (exact) updates
+	int64_t resv_log2 = 29, list_log2 = 24;  // reservation sketch bits per table / residual-round table entries
 	int64_t drain_threshold = 4096;
 	int64_t ordered_coop = 1; // residual rounds of the ordered updates: 1 cooperative grid kernel, 0 host-driven rounds
 	int64_t bin_mode = 0;       // partitioned BloomFilter build: 0 auto, 1 always, -1 never
@@ -120,6 +120,7 @@ struct btlbf_ctx
 	int64_t bin_kernel = 0;                     // 0 auto (sort-bin kernel when the shape allows), 1 legacy kernels only
 	int64_t bin_max_parts = 512;                // the sort-bin path widens the partitions until there are at most this many
 	int settle_error = 0;
+	int64_t query_chunk_factor = 4; // BloomFilter queries of the host-buffer calls run in chunks of this many chunk_bases
 };
 
 struct btlbf_filter
@@ -249,6 +250,19 @@ static SeqParams filter_params(btlbf_filter* f)
 }
 
 // ---------------------------------------------------------------- misc entry points
+extern "C" int btlbf_set_error(int code, const char* msg) // used by ingest.cu
+{
+	return fail(code, "%s", msg ? msg : "");
+}
+
+extern "C" int btlbf_filter_ctx(btlbf_filter* f, btlbf_ctx** ctx)
+{
+	if (!f || !ctx)
+		return fail(BTLBF_ERR_ARG, "null argument");
+	*ctx = f->ctx;
+	return BTLBF_OK;
+}
+
 extern "C" const char* btlbf_last_error(void)
 {
 	return g_err;
@@ -464,6 +478,10 @@ extern "C" int btlbf_ctx_set_option(btlbf_ctx* ctx, const char* key, int64_t val
 		if (value < 0)
 			return fail(BTLBF_ERR_ARG, "bin_accum_bytes out of range");
 		ctx->bin_accum_bytes = value;
+	} else if (k == "query_chunk_factor") {
+		if (value < 1 || value > 16)
+			return fail(BTLBF_ERR_ARG, "query_chunk_factor out of range [1,16]");
+		ctx->query_chunk_factor = value;
 	} else if (k == "bin_kernel") {
 		ctx->bin_kernel = value != 0;
 	} else if (k == "bin_max_parts") {
@@ -915,7 +933,14 @@ static int ordered_apply(btlbf_filter* f, const SeqParams& chunk, int kind, cuda
 		T.stats = nullptr;
 		TRY(launch(ctx, OP_RESV_TOUCH, T, s));
 		TRY(launch(ctx, kind == 0 ? OP_CBF_COMMIT : OP_BFCHK_COMMIT, P, s));
-		TRY(launch(ctx, OP_RESV_CLEAR, T, s));
+		// re-arm the sketch: a sweep over the tables when the batch touched a good part of them, else the
+		// clear pass (which re-derives the positions)
+		const size_t table_bytes = (((size_t)1 << f->resv_log2) + 7) / 8;
+		if ((double)bw * P.h * 64.0 >= (double)table_bytes) {
+			CU(cudaMemsetAsync(f->d_touched, 0, table_bytes < 4 ? 4 : table_bytes, s));
+			CU(cudaMemsetAsync(f->d_contended, 0, table_bytes < 4 ? 4 : table_bytes, s));
+		} else
+			TRY(launch(ctx, OP_RESV_CLEAR, T, s));
 		if (coop) {
 			// the residual rounds run to completion on the device (grid-wide barriers): nothing to wait for
 			ListParams L;
@@ -1408,6 +1433,9 @@ static int host_pipeline(btlbf_ctx* ctx, btlbf_filter* f, const HashCfg* hash_on
 	cudaStream_t s = ctx->active;
 
 	uint64_t chunk = (uint64_t)ctx->chunk_bases;
+	// the partitioned query streams the whole filter once per chunk: larger chunks for it
+	if (op == PUB_CONTAINS && f && f->kind == BTLBF_BLOOM && f->bytes >= ((uint64_t)96 << 20))
+		chunk *= (uint64_t)ctx->query_chunk_factor;
 	if (op == PUB_HASH) { // keep the per-chunk hash buffer around 256 MiB
 		uint64_t lim = ((uint64_t)256 << 20) / ((uint64_t)H * 9);
 		lim = lim / kTile * kTile;

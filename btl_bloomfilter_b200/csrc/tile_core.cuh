@@ -353,6 +353,26 @@ BTL_HD bool bfchk_commit_one(const SeqParams& P, const TileSmem& sm, uint32_t w,
 	return found;
 }
 
+// reservation sketch of the ordered updates: the two table positions of a slot, counting, reading
+BTL_HD uint32_t resv_pos1(uint64_t slot, uint32_t log2)
+{
+	return (uint32_t)(slot & (((uint64_t)1 << log2) - 1));
+}
+BTL_HD uint32_t resv_pos2(uint64_t slot, uint32_t log2)
+{
+	return (uint32_t)((slot * 0x9e3779b97f4a7c15ULL + 0x7f4a7c159e3779b9ULL) >> (64 - log2));
+}
+BTL_HD void resv_count(const SeqParams& P, uint32_t e)
+{
+	uint32_t bit = 1u << (e & 31);
+	if (mem_atomic_or(P.resv_touched + (e >> 5), bit) & bit)
+		mem_red_or(P.resv_contended + (e >> 5), bit);
+}
+BTL_HD bool resv_twice(const SeqParams& P, uint32_t e)
+{
+	return (ld_cg(P.resv_contended + (e >> 5)) >> (e & 31)) & 1u;
+}
+
 // ---------------------------------------------------------------- the fused per-window operation
 struct ThreadOut
 {
@@ -461,24 +481,24 @@ BTL_HD void window_op(const SeqParams& P, const TileSmem& sm, uint64_t t0, uint3
 			return true;
 		});
 	} else if (OP == OP_RESV_TOUCH) {
-		// ordered updates, pass 1: mark every (hashed) slot; a slot marked twice is contended
-		uint32_t mask = (1u << P.resv_log2) - 1u;
+		// ordered updates, pass 1: count-min sketch with two-valued counters.  Every slot is counted at two
+		// positions of the bit tables (touched = "at least once", contended = "at least twice").
 		for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t, uint64_t hv, bool) {
-			uint32_t e = (uint32_t)fastmod<POW2>(hv, P.fm) & mask;
-			uint32_t bit = 1u << (e & 31);
-			if (mem_atomic_or(P.resv_touched + (e >> 5), bit) & bit)
-				mem_red_or(P.resv_contended + (e >> 5), bit);
+			uint64_t slot = fastmod<POW2>(hv, P.fm);
+			resv_count(P, resv_pos1(slot, P.resv_log2));
+			resv_count(P, resv_pos2(slot, P.resv_log2));
 			return true;
 		});
 	} else if (OP == OP_CBF_COMMIT || OP == OP_BFCHK_COMMIT) {
-		// pass 2: a k-mer none of whose slots is contended shares no slot with any other k-mer of the
-		// batch, so its update commutes with all of them and is applied now; the others are deferred
-		// to the index-ordered residual rounds (list_round_*)
-		uint32_t mask = (1u << P.resv_log2) - 1u;
+		// pass 2: a slot that some other k-mer of the batch also uses was counted twice at BOTH of its
+		// positions.  A k-mer none of whose slots looks that way shares no slot with any other k-mer of the
+		// batch, so its update commutes with all of them and is applied now; the others (true sharers plus the
+		// few false alarms of the sketch) are deferred to the index-ordered residual rounds (list_round_*).
 		bool contended = false;
 		for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t, uint64_t hv, bool) {
-			uint32_t e = (uint32_t)fastmod<POW2>(hv, P.fm) & mask;
-			contended |= (ld_cg(P.resv_contended + (e >> 5)) >> (e & 31)) & 1u;
+			uint64_t slot = fastmod<POW2>(hv, P.fm);
+			if (resv_twice(P, resv_pos1(slot, P.resv_log2)) && resv_twice(P, resv_pos2(slot, P.resv_log2)))
+				contended = true;
 			return true;
 		});
 		if (!contended) {
@@ -494,11 +514,14 @@ BTL_HD void window_op(const SeqParams& P, const TileSmem& sm, uint64_t t0, uint3
 			P.pending[slot] = (uint32_t)(t0 + w);
 		}
 	} else if (OP == OP_RESV_CLEAR) {
-		uint32_t mask = (1u << P.resv_log2) - 1u;
+		// pass 3 (small batches; large ones clear the tables with a memset instead)
 		for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t, uint64_t hv, bool) {
-			uint32_t e = (uint32_t)fastmod<POW2>(hv, P.fm) & mask;
-			P.resv_touched[e >> 5] = 0;
-			P.resv_contended[e >> 5] = 0;
+			uint64_t slot = fastmod<POW2>(hv, P.fm);
+			uint32_t e1 = resv_pos1(slot, P.resv_log2), e2 = resv_pos2(slot, P.resv_log2);
+			P.resv_touched[e1 >> 5] = 0;
+			P.resv_contended[e1 >> 5] = 0;
+			P.resv_touched[e2 >> 5] = 0;
+			P.resv_contended[e2 >> 5] = 0;
 			return true;
 		});
 	}

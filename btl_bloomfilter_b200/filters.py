@@ -284,6 +284,19 @@ class _DeviceFilter:
                                           C.byref(nk), C.byref(nh)))
         return QueryResult(n, off, self.getKmerSize(), hits, valid, nk.value, nh.value)
 
+    # -- FASTA / FASTQ files (the record loop of swig/writeBloom_rolling.cpp:19-59, parsed by native threads)
+    def insertFile(self, path, threads=0):
+        """Insert every k-mer of every record of a FASTA / FASTQ file: (n_records, n_kmers)."""
+        ns, nk = C.c_uint64(), C.c_uint64()
+        check(self._L.btlbf_insert_file(self._h, str(path).encode(), int(threads), C.byref(ns), C.byref(nk)))
+        return ns.value, nk.value
+
+    def queryFile(self, path, threads=0):
+        """contains() of every k-mer of every record of a FASTA / FASTQ file: (n_records, n_kmers, n_hits)."""
+        ns, nk, nh = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(self._L.btlbf_query_file(self._h, str(path).encode(), int(threads), C.byref(ns), C.byref(nk), C.byref(nh)))
+        return ns.value, nk.value, nh.value
+
     # -- streaming (asynchronous) forms: all arrays must stay alive and untouched until Context.sync()
     def insertSeqsAsync(self, seqs, counts_out):
         """Queue insertSeqs; counts_out: uint64[2] (ideally pinned) that receives {n_kmers, n_hits}."""

@@ -172,6 +172,27 @@ int btlbf_mincount_seqs(btlbf_filter *f, const char *bases, const uint64_t *offs
                         uint64_t n_seqs, uint8_t *counts, uint8_t *valid_bits, uint64_t *n_kmers);
 int btlbf_increment_all_seqs(btlbf_filter *f, const char *bases, const uint64_t *offsets,
                              uint64_t n_seqs, uint64_t *n_kmers);
+/* ---- FASTA / FASTQ ingest (reference: the read-a-record / insertSeq loop of
+ * swig/writeBloom_rolling.cpp:19-59 and BloomFilterUtil.h:10-17) ----
+ * btlbf_insert_file / btlbf_query_file: parse the file with `threads` parser threads (0 = automatic; always
+ * one for the order-dependent counting insert), stream the records through the batched calls above and
+ * return the number of records, of k-mers inserted / queried and (query) of k-mers found.  Multi-line
+ * FASTA, four-line FASTQ, CRLF line ends; sequences of any length (long ones are cut into pieces that
+ * overlap by k-1 bases, so every k-mer is visited exactly once). */
+int btlbf_insert_file(btlbf_filter *f, const char *path, int threads, uint64_t *n_seqs, uint64_t *n_kmers);
+int btlbf_query_file(btlbf_filter *f, const char *path, int threads, uint64_t *n_seqs, uint64_t *n_kmers,
+                     uint64_t *n_hits);
+/* The parser alone (no GPU involved): region `region` of `n_regions` equal cuts of the file, aligned to
+ * line (FASTA) / record (FASTQ) starts.  btlbf_seqfile_next fills one flat batch: bases[0..*n_bases),
+ * offsets[0..*n_seqs] (pieces; a piece that continues a cut sequence starts with its previous `overlap`
+ * bases), *n_records = records that started in the batch, *done = 1 once the region is exhausted. */
+typedef struct btlbf_seqfile btlbf_seqfile;
+int btlbf_seqfile_open(const char *path, unsigned overlap, int n_regions, int region, btlbf_seqfile **reader);
+int btlbf_seqfile_next(btlbf_seqfile *reader, char *bases, uint64_t cap_bases, uint64_t *offsets,
+                       uint64_t cap_seqs, uint64_t *n_bases, uint64_t *n_seqs, uint64_t *n_records, int *done);
+int btlbf_seqfile_close(btlbf_seqfile *reader);
+int btlbf_filter_ctx(btlbf_filter *f, btlbf_ctx **ctx); /* the context a filter belongs to */
+
 /* raw iterator output: hashes[p*H + i]; strands[p*H + i] (spaced seeds only, else zero).
  * seeds == NULL / n_seeds == 0: ntHashIterator with H = hash_num;
  * else stHashIterator with H = n_seeds*h2 (hash_num is ignored). */

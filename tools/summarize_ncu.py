@@ -25,7 +25,10 @@ METRICS = [
 
 
 def raw_rows(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):  # already exported on the GPU box (ncu -i x.ncu-rep --page raw --csv)
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     return hdr, units, rows[2:]
@@ -68,22 +71,52 @@ def main():
     with open(os.path.join(ROOT, "profiles", "%s_dram_bytes_per_launch.json" % tag), "w") as fh:
         json.dump(tj, fh, indent=1)
     if launches:
-        rows = [r for r in csv.reader(open(launches)) if len(r) > 12 and r[0] != "ID"]
-        with open(os.path.join(ROOT, "profiles", "%s_launch_list.csv" % tag), "w") as fh:
-            fh.write("id,kernel,grid,block,gpu__time_duration_ns\n")
-            for r in rows:
-                fh.write("%s,\"%s\",\"%s\",\"%s\",%s\n" % (r[0], r[4].split("(")[0][:70], r[8], r[7], r[14]))
-        # share of the step per kernel
-        tot = {}
+        # one row per (launch, metric): ID, ..., kernel name [4], block [7], grid [8], metric [12], unit [13], value [14]
+        rows = [r for r in csv.reader(open(launches)) if len(r) > 14 and r[0] != "ID"]
+        per = {}
+        order = []
         for r in rows:
-            k = r[4].split("(")[0][:70]
-            if "btl::" in k and "synth" not in k:
-                tot[k] = tot.get(k, 0.0) + float(r[14])
+            i = int(r[0])
+            if i not in per:
+                per[i] = {"kernel": r[4].split("(")[0][:70], "grid": r[8], "block": r[7]}
+                order.append(i)
+            per[i][r[12]] = float(r[14].replace(",", ""))
+        with open(os.path.join(ROOT, "profiles", "%s_launch_list.csv" % tag), "w") as fh:
+            fh.write("id,kernel,grid,block,gpu__time_duration_ns,dram_bytes_read,dram_bytes_write\n")
+            for i in order:
+                d = per[i]
+                fh.write("%d,\"%s\",\"%s\",\"%s\",%.0f,%.0f,%.0f\n" % (
+                    i, d["kernel"], d["grid"], d["block"], d.get("gpu__time_duration.sum", 0),
+                    d.get("dram__bytes_read.sum", 0), d.get("dram__bytes_write.sum", 0)))
+        # the timed region of `bench.py --steps S --warmup W`: per kernel, the launches after the warm-up ones
+        W = int(os.environ.get("BENCH_WARMUP", "3"))
+        S = int(os.environ.get("BENCH_STEPS", "8"))
+        seen = {}
+        tot, dram = {}, {}
+        for i in order:
+            d = per[i]
+            k = d["kernel"]
+            if "btl::" not in k or "synth" in k:
+                continue
+            n = seen.get(k, 0)
+            seen[k] = n + 1
+            warm = 1 if "apply_bins" in k else W  # the warm-up builds are settled by one pass 2
+            if n < warm:
+                continue
+            tot[k] = tot.get(k, 0.0) + d.get("gpu__time_duration.sum", 0)
+            dram[k] = dram.get(k, 0.0) + d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0)
         s = sum(tot.values())
         with open(os.path.join(ROOT, "profiles", "%s_kernel_shares.md" % tag), "w") as fh:
-            fh.write("# share of the timed step per kernel (ncu launch list, cold-cache serialised times)\n\n")
+            fh.write("# share of the timed region per kernel (ncu launch list of `bench.py --steps %d --warmup %d`, "
+                     "cold-cache serialised times)\n\n" % (S, W))
             for k, v in sorted(tot.items(), key=lambda x: -x[1]):
-                fh.write("- %-60s %8.3f ms total  %5.1f %%\n" % (k, v / 1e6, 100 * v / s))
+                fh.write("- %-60s %8.3f ms total  %5.1f %%   DRAM %7.2f GB\n" % (k, v / 1e6, 100 * v / s, dram[k] / 1e9))
+        build = sum(v for k, v in dram.items() if "apply_bins" in k or ("bin_kernel" in k and ", 0>" in k[-6:]))
+        query = sum(v for k, v in dram.items() if "probe_bins" in k or "finalize" in k or ("bin_kernel" in k and ", 1>" in k[-6:]))
+        with open(os.path.join(ROOT, "profiles", "%s_dram_bytes_per_step.json" % tag), "w") as fh:
+            json.dump({"build_bytes_per_step": build / S, "query_bytes_per_step": query / S, "steps": S,
+                       "source": "ncu launch list, dram__bytes_read.sum + dram__bytes_write.sum of the timed launches"},
+                      fh, indent=1)
     print(json.dumps(tj, indent=1))
 
 
