@@ -131,6 +131,7 @@ struct btlbf_filter
 	unsigned threshold = 1;
 	uint8_t* d_data = nullptr;
 	bool owned = false;
+	bool bitvector = false; // BTLBF_BITVECTOR: a BLOOM filter of any size in 64-bit words, without a file format
 	HashCfg hc;
 	// ordered-update state (lazy)
 	uint32_t* d_touched = nullptr;
@@ -507,11 +508,14 @@ static int filter_make(btlbf_ctx* ctx, int kind, uint64_t size, unsigned h, unsi
 		return fail(BTLBF_ERR_ARG, "null argument");
 	*out = nullptr;
 	TRY(use(ctx));
-	if (kind != BTLBF_BLOOM && kind != BTLBF_COUNTING8)
+	if (kind != BTLBF_BLOOM && kind != BTLBF_COUNTING8 && kind != BTLBF_BITVECTOR)
 		return fail(BTLBF_ERR_ARG, "unknown filter kind %d", kind);
 	if (size == 0)
 		return fail(BTLBF_ERR_ARG, "filter size must be > 0");
-	if (kind == BTLBF_BLOOM && size % 8 != 0) // BloomFilter.hpp:389-394
+	const bool bitvector = kind == BTLBF_BITVECTOR;
+	if (bitvector)
+		kind = BTLBF_BLOOM; // same bits, same kernels
+	if (kind == BTLBF_BLOOM && !bitvector && size % 8 != 0) // BloomFilter.hpp:389-394
 		return fail(BTLBF_ERR_ARG, "Filter Size \"%llu\" is not a multiple of 8", (unsigned long long)size);
 	btlbf_filter* f = new (std::nothrow) btlbf_filter();
 	if (!f)
@@ -519,7 +523,8 @@ static int filter_make(btlbf_ctx* ctx, int kind, uint64_t size, unsigned h, unsi
 	f->ctx = ctx;
 	f->kind = kind;
 	f->size = size;
-	f->bytes = kind == BTLBF_BLOOM ? size / 8 : size;
+	f->bitvector = bitvector;
+	f->bytes = bitvector ? (size + 63) / 64 * 8 : kind == BTLBF_BLOOM ? size / 8 : size;
 	f->threshold = threshold;
 	int rc = hashcfg_init(f->hc, k, h, nullptr, 0, 0);
 	if (rc != BTLBF_OK) {
@@ -601,7 +606,7 @@ extern "C" int btlbf_filter_info(btlbf_filter* f, int* kind, uint64_t* size, uin
 {
 	if (!f)
 		return fail(BTLBF_ERR_ARG, "null filter");
-	if (kind) *kind = f->kind;
+	if (kind) *kind = f->bitvector ? BTLBF_BITVECTOR : f->kind;
 	if (size) *size = f->size;
 	if (size_bytes) *size_bytes = f->bytes;
 	if (hash_num) *hash_num = f->hc.h;
@@ -1020,12 +1025,13 @@ static int ordered_apply(btlbf_filter* f, const SeqParams& chunk, int kind, cuda
 static bool want_binned(const btlbf_filter* f, const SeqParams& P)
 {
 	const btlbf_ctx* ctx = f->ctx;
-	if (ctx->bin_mode < 0 || f->kind != BTLBF_BLOOM || f->size % 32 != 0)
+	if (ctx->bin_mode < 0 || f->kind != BTLBF_BLOOM)
 		return false;
 	if (ctx->bin_mode > 0)
 		return true;
-	// auto: the filter does not fit in L2 and the batch is large enough to amortise streaming it once
-	return f->bytes >= ((uint64_t)96 << 20) && P.n_windows * P.h >= f->bytes / 64;
+	// auto: the filter does not fit in L2 and the batch is large enough to amortise streaming it.  Pass 2 runs
+	// once per accumulation (several batches), hence the lower bar than for the partitioned query.
+	return f->bytes >= ((uint64_t)96 << 20) && P.n_windows * P.h >= f->bytes / 512;
 }
 
 // log2(bits per partition) for filter f hashed as P describes (P.bin_legacy set); false: too many partitions
@@ -1203,7 +1209,7 @@ static int binned_insert(btlbf_filter* f, SeqParams P, cudaStream_t s)
 static bool want_binned_query(const btlbf_filter* f, const SeqParams& P)
 {
 	const btlbf_ctx* ctx = f->ctx;
-	if (ctx->bin_query_mode < 0 || f->kind != BTLBF_BLOOM || f->size % 32 != 0 || P.n_windows > 0xffffffffULL)
+	if (ctx->bin_query_mode < 0 || f->kind != BTLBF_BLOOM || P.n_windows > 0xffffffffULL)
 		return false;
 	if (((uintptr_t)P.hit_bits | (uintptr_t)P.valid_bits) & 3u)
 		return false;
@@ -1907,6 +1913,8 @@ extern "C" int btlbf_filter_store(btlbf_filter* f, const char* path, double dFPR
 {
 	if (!f || !path)
 		return fail(BTLBF_ERR_ARG, "null argument");
+	if (f->bitvector)
+		return fail(BTLBF_ERR_STATE, "a BTLBF_BITVECTOR has no file format of its own (download the words instead)");
 	btlbf_ctx* ctx = f->ctx;
 	TRY(use(ctx));
 	FILE* fp = fopen(path, "wb");

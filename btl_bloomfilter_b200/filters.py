@@ -492,6 +492,42 @@ class BloomFilter(_DeviceFilter):
         self.m_tEntry = int(v)
 
 
+class BitVector(_DeviceFilter):
+    """Level-1 bit vector of a multi-index Bloom filter (MIBFConstructSupport.hpp:36-46: an sdsl::bit_vector of
+    `size` bits, any size): insertSeqs = insertBV (:76-87), insertBVColli (:55-74), containsSeqs, getPop.
+    to_numpy() returns the 64-bit words as bytes (little-endian), i.e. m_bv.data()."""
+    KIND = 2
+
+    def __init__(self, size, hashNum, kmerSize, ctx=None):
+        super().__init__()
+        self._create(ctx, int(size), hashNum, kmerSize, 0)
+
+    def insertBVColli(self, seqs):
+        """Insert every k-mer; returns (n_kmers, n_collisions): collisions = k-mers whose h bits were all set
+        already, in sequence order (the reference's single-threaded result)."""
+        bases, off = as_batch(seqs)
+        n = bases.size
+        found = np.zeros(bit_bytes(n), np.uint8)
+        nk = C.c_uint64()
+        check(self._L.btlbf_insert_and_check_seqs(self._h, _ptr(bases), _p64(off), off.size - 1, _ptr(found), None,
+                                                  C.byref(nk)))
+        return nk.value, int(np.unpackbits(found).sum())
+
+    def getPop(self):
+        n = C.c_uint64()
+        check(self._L.btlbf_filter_popcount(self._h, C.byref(n)))
+        return n.value
+
+    def size(self):
+        return self._info()[1]
+
+    def sizeInBytes(self):
+        return self._info()[2]
+
+    def getKmerSize(self):
+        return self._info()[4]
+
+
 class KmerBloomFilter(BloomFilter):
     """KmerBloomFilter.hpp:17-74 (what swig/BloomFilter.i exports as "BloomFilter"): insert / contains also take
     one k-mer as text.  The k-mer is hashed on the GPU with the iterator-consistent canonical ntHash (equal to the

@@ -56,7 +56,13 @@ enum {
 
 enum {
 	BTLBF_BLOOM = 0,       /* BloomFilter: size = number of bits (multiple of 8), BloomFilter.hpp:389-399 */
-	BTLBF_COUNTING8 = 1    /* CountingBloomFilter<uint8_t>: size = number of 8-bit counters */
+	BTLBF_COUNTING8 = 1,   /* CountingBloomFilter<uint8_t>: size = number of 8-bit counters */
+	BTLBF_BITVECTOR = 2    /* the level-1 bit vector of a multi-index Bloom filter (sdsl::bit_vector of `size`
+	                        * bits, any size, 64-bit words, bit pos -> word pos>>6, mask 1<<(pos&63)):
+	                        * insert_seqs = MIBFConstructSupport::insertBV (MIBFConstructSupport.hpp:76-87),
+	                        * insert_and_check_seqs = insertBVColli (:55-74; found bit = all h bits were set,
+	                        * the collision count is the number of found bits), contains_seqs, popcount.
+	                        * Same bit layout as BTLBF_BLOOM (little-endian); no file format. */
 };
 
 typedef struct btlbf_ctx btlbf_ctx;       /* one per GPU: streams, staging buffers, constants */

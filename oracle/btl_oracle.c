@@ -494,6 +494,34 @@ uint64_t ora_bf_insert_and_check_seqs(uint8_t *filter, uint64_t m, unsigned h, u
 	return n;
 }
 
+/* MIBFConstructSupport::insertBVColli (MIBFConstructSupport.hpp:55-74) over a batch: 64-bit words of an
+ * sdsl::bit_vector of m bits; *colli = k-mers all of whose h bits were already set; returns the k-mers.
+ * (insertBV, :76-87, is the same without the count.) */
+uint64_t ora_mibf_insert_bv_seqs(uint64_t *words, uint64_t m, unsigned h, unsigned k, const char *bases,
+                                 const uint64_t *off, uint64_t n_seqs, uint64_t *colli)
+{
+	uint64_t n = 0, count = 0;
+	ora_nt_iter it;
+	for (uint64_t s = 0; s < n_seqs; s++) {
+		ora_nt_iter_init(&it, bases + off[s], off[s + 1] - off[s], h, k);
+		for (; it.pos != ORA_END; ora_nt_iter_next(&it)) {
+			unsigned colliCount = 0;
+			for (unsigned i = 0; i < h; i++) {
+				uint64_t pos = it.hv[i] % m;
+				uint64_t *dataIndex = words + (pos >> 6);
+				uint64_t bitMaskValue = (uint64_t)1 << (pos & 0x3F);
+				colliCount += (unsigned)(__sync_fetch_and_or(dataIndex, bitMaskValue) >> (pos & 0x3F) & 1);
+			}
+			if (colliCount == h)
+				count++;
+			n++;
+		}
+	}
+	if (colli)
+		*colli = count;
+	return n;
+}
+
 uint64_t ora_cbf_insert_seqs(uint8_t *cnt, uint64_t m, unsigned h, unsigned k, const char *bases,
                              const uint64_t *off, uint64_t n_seqs)
 {

@@ -161,6 +161,14 @@ class Oracle:
                                                   off.size - 1, _p8(found), _p8(valid))
         return int(cnt), found, valid
 
+    def mibf_insert_bv_seqs(self, words, m, h, k, bases, off):
+        """(n_kmers, n_collisions); words: uint64 array of ceil(m/64) words, updated in place"""
+        colli = C.c_uint64()
+        self.L.ora_mibf_insert_bv_seqs.restype = C.c_uint64
+        n = self.L.ora_mibf_insert_bv_seqs(words.ctypes.data_as(C.c_void_p), C.c_uint64(m), C.c_uint(h), C.c_uint(k),
+                                           _p8(bases), _p64(off), C.c_uint64(off.size - 1), C.byref(colli))
+        return int(n), int(colli.value)
+
     def cbf_insert_seqs(self, cntr, m, h, k, bases, off):
         return int(self.L.ora_cbf_insert_seqs(_p8(cntr), m, h, k, _p8(bases), _p64(off), off.size - 1))
 

@@ -514,3 +514,37 @@ def test_kmer_bloom_filter_matches_reference(gpu, golden):
         assert f.to_numpy().tobytes().hex() == c["filter_hex"]
         assert [int(f.contains(p)) for p in c["probes"]] == c["contains"]
         assert f.contains("N" * c["k"]) is False
+
+
+# ---------------------------------------------------------------- MIBF level-1 bit vector
+@pytest.mark.parametrize("bits,forced", [(1_000_003, 0), (8 * 300_007, 1), (64 * 4099 + 17, 1)])
+def test_mibf_bit_vector_build(oracle, bits, forced):
+    """BTLBF_BITVECTOR: insertBV / insertBVColli (MIBFConstructSupport.hpp:55-87) on an sdsl-style bit vector of
+    any size; words, k-mer counts and collision counts against the oracle's restatement.  forced=1 runs the
+    partitioned build and query on a size that is not a multiple of 32."""
+    import btl_bloomfilter_b200 as B
+    ctx = B.Context(0)
+    if forced:
+        ctx.set_option("bin_mode", 1)
+        ctx.set_option("bin_query_mode", 1)
+        ctx.set_option("bin_part_log2", 12)
+    h, k = 3, 19
+    rng = np.random.default_rng(bits % 1000)
+    bv = B.BitVector(bits, h, k, ctx=ctx)
+    words = np.zeros((bits + 63) // 64, np.uint64)
+    b1, o1 = S.rand_batch(rng, 30, 900, p_n=0.01)
+    assert bv.insertSeqs((b1, o1)) == oracle.mibf_insert_bv_seqs(words, bits, h, k, b1, o1)[0]
+    assert np.array_equal(bv.to_numpy(), words.view(np.uint8))
+    # second batch shares k-mers with the first: collisions
+    b2 = np.concatenate([b1[: b1.size // 2], S.rand_batch(rng, 10, 500)[0]])
+    o2 = np.array([0, b2.size], np.uint64)
+    assert bv.insertBVColli((b2, o2)) == oracle.mibf_insert_bv_seqs(words, bits, h, k, b2, o2)
+    assert np.array_equal(bv.to_numpy(), words.view(np.uint8))
+    assert bv.getPop() == int(np.unpackbits(words.view(np.uint8)).sum())
+    r = bv.containsSeqs((b1, o1))
+    assert r.n_hits == r.n_kmers > 0
+    filt = words.view(np.uint8)
+    q, qo = S.rand_batch(rng, 20, 700)
+    r = bv.containsSeqs((q, qo))
+    nk, nh, hit, valid = oracle.bf_contains_seqs(filt, bits, h, k, q, qo)
+    assert (r.n_kmers, r.n_hits) == (nk, nh) and np.array_equal(r.hit_bits, hit)
