@@ -92,7 +92,7 @@ struct btlbf_ctx
 	uint64_t launches = 0;
 	unsigned long long* d_scalars = nullptr; // 16 device words: [0..1] stats, [2] popcount, [4..7] list counters
 	unsigned long long* h_scalars = nullptr; // pinned mirror
-	int64_t force_generic = 0, query_mode = 0;
+	int64_t force_generic = 0, query_mode = 0, ungrouped_commit = 0;
 	int64_t chunk_bases = (int64_t)64 << 20; // windows per pipeline stage of the host-buffer calls
 	int64_t cbf_batch = (int64_t)4 << 20;    // windows per batch of the ordered (exact) updates
 	int64_t resv_log2 = 29, list_log2 = 24;  // reservation sketch bits per table / residual-round table entries
@@ -139,6 +139,8 @@ struct btlbf_filter
 	uint32_t resv_log2 = 0;
 	uint32_t* d_pending[2] = { nullptr, nullptr };
 	uint32_t pending_cap = 0;
+	uint64_t* d_pending_slots = nullptr; // [pending_cap * h] slots of deferred windows (when that fits 1 GiB)
+	uint32_t pending_slots_h = 0, pending_slots_cap = 0;
 	uint64_t* d_list_resv = nullptr;
 	uint32_t list_log2 = 0;
 	uint32_t epoch = 0;
@@ -247,6 +249,7 @@ static SeqParams filter_params(btlbf_filter* f)
 	P.threshold = f->threshold;
 	P.force_generic = (uint32_t)f->ctx->force_generic;
 	P.query_mode = (uint32_t)f->ctx->query_mode;
+	P.ungrouped_commit = (uint32_t)f->ctx->ungrouped_commit;
 	return P;
 }
 
@@ -434,6 +437,8 @@ extern "C" int btlbf_ctx_set_option(btlbf_ctx* ctx, const char* key, int64_t val
 		ctx->force_generic = value != 0;
 	else if (k == "query_mode")
 		ctx->query_mode = value != 0;
+	else if (k == "ungrouped_commit")
+		ctx->ungrouped_commit = value != 0;
 	else if (k == "chunk_bases") {
 		if (value < kTile || value > ((int64_t)1 << 31))
 			return fail(BTLBF_ERR_ARG, "chunk_bases out of range");
@@ -586,6 +591,7 @@ extern "C" int btlbf_filter_destroy(btlbf_filter* f)
 	if (f->d_contended) cudaFree(f->d_contended);
 	if (f->d_pending[0]) cudaFree(f->d_pending[0]);
 	if (f->d_pending[1]) cudaFree(f->d_pending[1]);
+	if (f->d_pending_slots) cudaFree(f->d_pending_slots);
 	if (f->d_list_resv) cudaFree(f->d_list_resv);
 	if (f->d_ord) cudaFree(f->d_ord);
 	delete f;
@@ -881,6 +887,20 @@ static int ordered_state(btlbf_filter* f, uint32_t batch)
 		}
 		f->pending_cap = batch;
 	}
+	// slot cache of the deferred windows (h may change with btlbf_filter_set_seeds)
+	if (f->d_pending_slots && (f->pending_slots_h != f->hc.h || f->pending_slots_cap < batch)) {
+		CU(cudaFree(f->d_pending_slots));
+		f->d_pending_slots = nullptr;
+	}
+	if (!f->d_pending_slots && (f->pending_slots_h != f->hc.h || f->pending_slots_cap < batch) &&
+	    (uint64_t)batch * f->hc.h * 8 <= ((uint64_t)1 << 30)) {
+		if (cudaMalloc(&f->d_pending_slots, (size_t)batch * f->hc.h * 8) != cudaSuccess) {
+			cudaGetLastError();
+			f->d_pending_slots = nullptr; // optional: the rounds then re-derive the slots
+		}
+		f->pending_slots_h = f->hc.h;
+		f->pending_slots_cap = f->d_pending_slots ? batch : 0;
+	}
 	uint32_t want_list = (uint32_t)ctx->list_log2;
 	if (f->d_list_resv && f->list_log2 != want_list) {
 		CU(cudaFree(f->d_list_resv));
@@ -930,6 +950,7 @@ static int ordered_apply(btlbf_filter* f, const SeqParams& chunk, int kind, cuda
 		P.resv_log2 = f->resv_log2;
 		P.pending = f->d_pending[0];
 		P.pending_count = d_cnt;
+		P.pending_slots = f->d_pending_slots;
 		if (!coop)
 			CU(cudaMemsetAsync(d_cnt, 0, 16, s));
 		// pass 1 carries no outputs; pass 2 writes valid/hit words and the k-mer statistics

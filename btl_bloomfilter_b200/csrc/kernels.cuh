@@ -54,6 +54,8 @@ struct SeqParams
 	uint32_t resv_log2;
 	uint32_t* pending;       // deferred window list (chunk-local window indices)
 	uint32_t* pending_count;
+	uint64_t* pending_slots; // optional: the h slots of deferred window w at [w*h ..), written when it is deferred,
+	                         // so that the residual rounds need not re-derive them from the bases
 	// partitioned build: sub-bucket (partition p, writer w) holds up to bin_cap 32-bit offsets at
 	// bin_items[(p*bin_writers + w)*bin_cap ...]; bin_counts[p*bin_writers + w] = appended (may exceed cap)
 	uint32_t* bin_items;
@@ -77,6 +79,7 @@ struct SeqParams
 	// knobs
 	uint32_t force_generic;
 	uint32_t query_mode;
+	uint32_t ungrouped_commit; // ordered updates, pass 2: one window at a time (the general form) even where the grouped form applies
 };
 
 size_t seq_kernel_smem_bytes(uint32_t k, bool spaced);

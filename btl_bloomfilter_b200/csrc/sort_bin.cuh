@@ -52,102 +52,6 @@ __device__ __forceinline__ void bin_direct_probe(const SeqParams& P, uint32_t pa
 		atomicAnd(P.hit_bits + (wid >> 5), ~(1u << (wid & 31)));
 }
 
-// the rolling hash of roll_windows() (tile_core.cuh) as an explicit state machine: one step() per window
-struct Roller
-{
-	uint64_t F, RC, in_codes, out_codes;
-	uint32_t in_bad, in_start, g, p0, q1, nwin;
-	bool generic;
-
-	__device__ __forceinline__ void init(const SeqParams& P, const TileSmem& sm, uint64_t t0, int tid, uint32_t tile)
-	{
-		uint64_t nwin64 = P.n_windows > t0 ? P.n_windows - t0 : 0;
-		nwin = nwin64 > (uint64_t)tile ? tile : (uint32_t)nwin64;
-		p0 = (uint32_t)tid * kWPT;
-		const uint32_t k = P.k;
-		const uint64_t* Gf = sm.gtab;
-		const uint64_t* Gr = sm.gtab + 32;
-		F = 0;
-		RC = 0;
-		g = 0;
-		q1 = p0 + k - 1;
-		generic = P.force_generic || sm.scratch[1] != 0;
-		in_codes = out_codes = 0;
-		in_bad = in_start = 0;
-		if (generic) {
-			// byte-class path: exact for every byte value (self-complementary raw bytes included)
-			for (uint32_t i = 0; i + 1 < k; i++) {
-				uint32_t qa = p0 + i, qb = p0 + k - 2 - i;
-				uint32_t ca = sm.tile[qa], cb = sm.tile[qb];
-				F = srol(F) ^ Gf[ca];
-				RC = srol(RC) ^ Gr[cb];
-				bool st = (sm.startw[qa >> 5] >> (qa & 31)) & 1u;
-				g = (ca & kClsBad) ? 0u : (st ? 1u : g + 1u);
-			}
-			RC = srol(RC);
-			return;
-		}
-		for (uint32_t i = 0; i + 1 < k; i++) {
-			uint32_t qa = p0 + i, qb = p0 + k - 2 - i;
-			uint32_t ca = (sm.codes[qa >> 4] >> (2 * (qa & 15))) & 3u;
-			uint32_t cb = (sm.codes[qb >> 4] >> (2 * (qb & 15))) & 3u;
-			F = srol(F) ^ Gf[ca];
-			RC = srol(RC) ^ Gr[cb];
-			bool bad = (sm.badw[qa >> 5] >> (qa & 31)) & 1u;
-			bool st = (sm.startw[qa >> 5] >> (qa & 31)) & 1u;
-			g = bad ? 0u : (st ? 1u : g + 1u);
-		}
-		RC = srol(RC);
-		// register streams: 32 incoming bases from q1 (unaligned), 32 outgoing bases from p0 (aligned)
-		uint32_t a = q1 >> 4, sh2 = 2 * (q1 & 15);
-		uint32_t in_lo = funnel_r(sm.codes[a], sm.codes[a + 1], sh2);
-		uint32_t in_hi = funnel_r(sm.codes[a + 1], sm.codes[a + 2], sh2);
-		uint32_t bw = q1 >> 5, sh1 = q1 & 31;
-		in_bad = funnel_r(sm.badw[bw], sm.badw[bw + 1], sh1);
-		in_start = funnel_r(sm.startw[bw], sm.startw[bw + 1], sh1);
-		in_codes = ((uint64_t)in_hi << 32) | in_lo;
-		out_codes = ((uint64_t)sm.codes[(p0 >> 4) + 1] << 32) | sm.codes[p0 >> 4];
-	}
-
-	// advances to window p0+s (s = 0, 1, 2, ... in order); true when it is a k-mer the reference's
-	// iterator visits (ntHashIterator.hpp:59-86)
-	__device__ __forceinline__ bool step(const SeqParams& P, const TileSmem& sm, uint32_t s)
-	{
-		const uint64_t* Gf = sm.gtab;
-		const uint64_t* Gfk = sm.gtab + 16;
-		const uint64_t* Gr = sm.gtab + 32;
-		const uint64_t* Grk = sm.gtab + 48;
-		if (generic) {
-			uint32_t q = q1 + s;
-			uint32_t cin = sm.tile[q];
-			F = srol(F) ^ Gf[cin];
-			RC ^= Grk[cin];
-			if (s > 0) {
-				uint32_t cout = sm.tile[p0 + s - 1];
-				F ^= Gfk[cout];
-				RC ^= Gr[cout];
-			}
-			RC = sror(RC);
-			bool st = (sm.startw[q >> 5] >> (q & 31)) & 1u;
-			g = (cin & kClsBad) ? 0u : (st ? 1u : g + 1u);
-		} else {
-			uint32_t cin = (uint32_t)in_codes & 3u;
-			in_codes >>= 2;
-			F = srol(F) ^ Gf[cin];
-			RC ^= Grk[cin];
-			if (s > 0) {
-				uint32_t cout = (uint32_t)out_codes & 3u;
-				out_codes >>= 2;
-				F ^= Gfk[cout];
-				RC ^= Gr[cout];
-			}
-			RC = sror(RC);
-			g = ((in_bad >> s) & 1u) ? 0u : (((in_start >> s) & 1u) ? 1u : g + 1u);
-		}
-		return g >= P.k && p0 + s < nwin;
-	}
-};
-
 // the H hashes of one window, statically indexed (SPACED: H == n_seeds, one hash per seed mask;
 // nthash.hpp:684-690 and :820-878)
 template<int H, bool SPACED>

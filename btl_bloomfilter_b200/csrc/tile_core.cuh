@@ -512,6 +512,13 @@ BTL_HD void window_op(const SeqParams& P, const TileSmem& sm, uint64_t t0, uint3
 		} else {
 			uint32_t slot = mem_atomic_inc(P.pending_count);
 			P.pending[slot] = (uint32_t)(t0 + w);
+			if (P.pending_slots) {
+				uint64_t* dst = P.pending_slots + (t0 + w) * P.h;
+				for_each_hash<SPACED>(P, sm, w, F, RC, [&](uint32_t i, uint64_t hv, bool) {
+					dst[i] = fastmod<POW2>(hv, P.fm);
+					return true;
+				});
+			}
 		}
 	} else if (OP == OP_RESV_CLEAR) {
 		// pass 3 (small batches; large ones clear the tables with a memset instead)
@@ -616,9 +623,245 @@ BTL_HD void roll_windows(const SeqParams& P, const TileSmem& sm, uint64_t t0, in
 	}
 }
 
+// The rolling hash of roll_windows() as an explicit state machine: init() seeds the thread's first window
+// (O(k)), one step() per window after that.  Used where the windows are consumed in groups (sort_bin.cuh,
+// the grouped commit pass below).
+struct Roller
+{
+	uint64_t F, RC, in_codes, out_codes;
+	uint32_t in_bad, in_start, g, p0, q1, nwin;
+	bool generic;
+
+	BTL_HD void init(const SeqParams& P, const TileSmem& sm, uint64_t t0, int tid, uint32_t tile)
+	{
+		uint64_t nwin64 = P.n_windows > t0 ? P.n_windows - t0 : 0;
+		nwin = nwin64 > (uint64_t)tile ? tile : (uint32_t)nwin64;
+		p0 = (uint32_t)tid * kWPT;
+		const uint32_t k = P.k;
+		const uint64_t* Gf = sm.gtab;
+		const uint64_t* Gr = sm.gtab + 32;
+		F = 0;
+		RC = 0;
+		g = 0;
+		q1 = p0 + k - 1;
+		generic = P.force_generic || sm.scratch[1] != 0;
+		in_codes = out_codes = 0;
+		in_bad = in_start = 0;
+		if (generic) {
+			// byte-class path: exact for every byte value (self-complementary raw bytes included)
+			for (uint32_t i = 0; i + 1 < k; i++) {
+				uint32_t qa = p0 + i, qb = p0 + k - 2 - i;
+				uint32_t ca = sm.tile[qa], cb = sm.tile[qb];
+				F = srol(F) ^ Gf[ca];
+				RC = srol(RC) ^ Gr[cb];
+				bool st = (sm.startw[qa >> 5] >> (qa & 31)) & 1u;
+				g = (ca & kClsBad) ? 0u : (st ? 1u : g + 1u);
+			}
+			RC = srol(RC);
+			return;
+		}
+		for (uint32_t i = 0; i + 1 < k; i++) {
+			uint32_t qa = p0 + i, qb = p0 + k - 2 - i;
+			uint32_t ca = (sm.codes[qa >> 4] >> (2 * (qa & 15))) & 3u;
+			uint32_t cb = (sm.codes[qb >> 4] >> (2 * (qb & 15))) & 3u;
+			F = srol(F) ^ Gf[ca];
+			RC = srol(RC) ^ Gr[cb];
+			bool bad = (sm.badw[qa >> 5] >> (qa & 31)) & 1u;
+			bool st = (sm.startw[qa >> 5] >> (qa & 31)) & 1u;
+			g = bad ? 0u : (st ? 1u : g + 1u);
+		}
+		RC = srol(RC);
+		// register streams: 32 incoming bases from q1 (unaligned), 32 outgoing bases from p0 (aligned)
+		uint32_t a = q1 >> 4, sh2 = 2 * (q1 & 15);
+		uint32_t in_lo = funnel_r(sm.codes[a], sm.codes[a + 1], sh2);
+		uint32_t in_hi = funnel_r(sm.codes[a + 1], sm.codes[a + 2], sh2);
+		uint32_t bw = q1 >> 5, sh1 = q1 & 31;
+		in_bad = funnel_r(sm.badw[bw], sm.badw[bw + 1], sh1);
+		in_start = funnel_r(sm.startw[bw], sm.startw[bw + 1], sh1);
+		in_codes = ((uint64_t)in_hi << 32) | in_lo;
+		out_codes = ((uint64_t)sm.codes[(p0 >> 4) + 1] << 32) | sm.codes[p0 >> 4];
+	}
+
+	// advances to window p0+s (s = 0, 1, 2, ... in order); true when it is a k-mer the reference's
+	// iterator visits (ntHashIterator.hpp:59-86)
+	BTL_HD bool step(const SeqParams& P, const TileSmem& sm, uint32_t s)
+	{
+		const uint64_t* Gf = sm.gtab;
+		const uint64_t* Gfk = sm.gtab + 16;
+		const uint64_t* Gr = sm.gtab + 32;
+		const uint64_t* Grk = sm.gtab + 48;
+		if (generic) {
+			uint32_t q = q1 + s;
+			uint32_t cin = sm.tile[q];
+			F = srol(F) ^ Gf[cin];
+			RC ^= Grk[cin];
+			if (s > 0) {
+				uint32_t cout = sm.tile[p0 + s - 1];
+				F ^= Gfk[cout];
+				RC ^= Gr[cout];
+			}
+			RC = sror(RC);
+			bool st = (sm.startw[q >> 5] >> (q & 31)) & 1u;
+			g = (cin & kClsBad) ? 0u : (st ? 1u : g + 1u);
+		} else {
+			uint32_t cin = (uint32_t)in_codes & 3u;
+			in_codes >>= 2;
+			F = srol(F) ^ Gf[cin];
+			RC ^= Grk[cin];
+			if (s > 0) {
+				uint32_t cout = (uint32_t)out_codes & 3u;
+				out_codes >>= 2;
+				F ^= Gfk[cout];
+				RC ^= Gr[cout];
+			}
+			RC = sror(RC);
+			g = ((in_bad >> s) & 1u) ? 0u : (((in_start >> s) & 1u) ? 1u : g + 1u);
+		}
+		return g >= P.k && p0 + s < nwin;
+	}
+};
+
+// ---------------------------------------------------------------- ordered updates, pass 2, grouped
+// The per-window form of OP_CBF_COMMIT / OP_BFCHK_COMMIT waits for three dependent round trips per window
+// (sketch -> counters -> update).  Here a thread handles G windows at a time, so that the G*H*2 sketch reads,
+// then the G*H counter reads (or bit atomics), are in flight together.  Exact for the same reason as the
+// per-window form: only k-mers that share no slot with any other k-mer of the batch are touched, so the
+// order in which their reads and writes are issued does not matter.  Contiguous ntHash, h <= 8.
+template<int OP, int H, bool POW2>
+BTL_HD ThreadOut tile_phase_c_commit(const SeqParams& P, const TileSmem& sm, uint64_t t0, int tid)
+{
+	constexpr int G = H <= 4 ? 4 : 2;
+	ThreadOut out;
+	out.validw = 0;
+	out.hitw = 0;
+	const uint64_t nwin64 = P.n_windows > t0 ? P.n_windows - t0 : 0;
+	const uint32_t p0 = (uint32_t)tid * kWPT;
+	if (p0 >= nwin64)
+		return out;
+	Roller r;
+	r.init(P, sm, t0, tid, (uint32_t)kTile);
+	for (uint32_t s0 = 0; s0 < (uint32_t)kWPT; s0 += G) {
+		uint64_t slot[G][H];
+		uint32_t okmask = 0;
+#pragma unroll
+		for (int g = 0; g < G; g++) {
+			const bool ok = r.step(P, sm, s0 + g);
+			okmask |= (uint32_t)ok << g;
+			const uint64_t b = r.RC < r.F ? r.RC : r.F;
+#pragma unroll
+			for (int i = 0; i < H; i++)
+				slot[g][i] = fastmod<POW2>(i ? multi_mix(b, P.mult[i]) : b, P.fm);
+		}
+		out.validw |= okmask << s0;
+		if (!okmask)
+			continue;
+		// sketch: "counted twice" words of both positions of every slot
+		uint32_t w1[G][H], w2[G][H];
+#pragma unroll
+		for (int g = 0; g < G; g++)
+#pragma unroll
+			for (int i = 0; i < H; i++) {
+				const bool on = (okmask >> g) & 1u;
+				w1[g][i] = on ? ld_cg(P.resv_contended + (resv_pos1(slot[g][i], P.resv_log2) >> 5)) : 0u;
+				w2[g][i] = on ? ld_cg(P.resv_contended + (resv_pos2(slot[g][i], P.resv_log2) >> 5)) : 0u;
+			}
+		uint32_t freemask = 0; // windows that share no slot with any other k-mer of the batch
+#pragma unroll
+		for (int g = 0; g < G; g++) {
+			uint32_t c = 0;
+#pragma unroll
+			for (int i = 0; i < H; i++)
+				c |= (w1[g][i] >> (resv_pos1(slot[g][i], P.resv_log2) & 31)) &
+				     (w2[g][i] >> (resv_pos2(slot[g][i], P.resv_log2) & 31)) & 1u;
+			freemask |= (((okmask >> g) & 1u) & (c ^ 1u)) << g;
+		}
+		if (OP == OP_CBF_COMMIT) {
+			uint8_t* cnt = (uint8_t*)P.filter;
+			uint32_t v[G][H];
+#pragma unroll
+			for (int g = 0; g < G; g++)
+#pragma unroll
+				for (int i = 0; i < H; i++)
+					v[g][i] = ((freemask >> g) & 1u) ? (uint32_t)ld_cg(cnt + slot[g][i]) : 255u;
+#pragma unroll
+			for (int g = 0; g < G; g++) {
+				if (!((freemask >> g) & 1u))
+					continue;
+				uint32_t mn = 255;
+#pragma unroll
+				for (int i = 0; i < H; i++)
+					mn = v[g][i] < mn ? v[g][i] : mn;
+				if (mn != 255) { // CountingBloomFilter.hpp:134-162
+#pragma unroll
+					for (int i = 0; i < H; i++)
+						if (v[g][i] == mn)
+							*(volatile uint8_t*)(cnt + slot[g][i]) = (uint8_t)(mn + 1);
+				}
+				if (mn >= P.threshold) // insertAndCheck reports the minimum before the update, :206-214
+					out.hitw |= 1u << (s0 + g);
+			}
+		} else {
+			uint32_t* words = (uint32_t*)P.filter;
+			uint32_t old[G][H];
+#pragma unroll
+			for (int g = 0; g < G; g++)
+#pragma unroll
+				for (int i = 0; i < H; i++)
+					old[g][i] = ((freemask >> g) & 1u)
+					                ? mem_atomic_or(words + (slot[g][i] >> 5), 1u << (uint32_t)(slot[g][i] & 31))
+					                : 0u;
+#pragma unroll
+			for (int g = 0; g < G; g++) {
+				uint32_t found = (freemask >> g) & 1u;
+#pragma unroll
+				for (int i = 0; i < H; i++)
+					found &= old[g][i] >> (uint32_t)(slot[g][i] & 31);
+				out.hitw |= (found & 1u) << (s0 + g);
+			}
+		}
+		// the others wait for the index-ordered residual rounds
+		const uint32_t defer = okmask & ~freemask;
+#pragma unroll
+		for (int g = 0; g < G; g++) {
+			if (!((defer >> g) & 1u))
+				continue;
+			const uint32_t w = p0 + s0 + g;
+			const uint32_t at = mem_atomic_inc(P.pending_count);
+			P.pending[at] = (uint32_t)(t0 + w);
+			if (P.pending_slots) {
+#pragma unroll
+				for (int i = 0; i < H; i++)
+					P.pending_slots[(t0 + w) * H + i] = slot[g][i];
+			}
+		}
+	}
+	return out;
+}
+
+template<int OP, bool POW2>
+BTL_HD bool tile_phase_c_commit_any(const SeqParams& P, const TileSmem& sm, uint64_t t0, int tid, ThreadOut& out)
+{
+	switch (P.h) {
+	case 1: out = tile_phase_c_commit<OP, 1, POW2>(P, sm, t0, tid); return true;
+	case 2: out = tile_phase_c_commit<OP, 2, POW2>(P, sm, t0, tid); return true;
+	case 3: out = tile_phase_c_commit<OP, 3, POW2>(P, sm, t0, tid); return true;
+	case 4: out = tile_phase_c_commit<OP, 4, POW2>(P, sm, t0, tid); return true;
+	case 5: out = tile_phase_c_commit<OP, 5, POW2>(P, sm, t0, tid); return true;
+	case 6: out = tile_phase_c_commit<OP, 6, POW2>(P, sm, t0, tid); return true;
+	case 7: out = tile_phase_c_commit<OP, 7, POW2>(P, sm, t0, tid); return true;
+	case 8: out = tile_phase_c_commit<OP, 8, POW2>(P, sm, t0, tid); return true;
+	}
+	return false;
+}
+
 template<int OP, bool SPACED, bool POW2>
 BTL_HD ThreadOut tile_phase_c(const SeqParams& P, const TileSmem& sm, uint64_t t0, int tid)
 {
+	if ((OP == OP_CBF_COMMIT || OP == OP_BFCHK_COMMIT) && !SPACED && !P.ungrouped_commit) {
+		ThreadOut grouped;
+		if (tile_phase_c_commit_any<(OP == OP_BFCHK_COMMIT ? OP_BFCHK_COMMIT : OP_CBF_COMMIT), POW2>(P, sm, t0, tid, grouped))
+			return grouped;
+	}
 	ThreadOut out;
 	out.validw = 0;
 	out.hitw = 0;
@@ -638,6 +881,13 @@ BTL_HD ThreadOut tile_phase_c(const SeqParams& P, const TileSmem& sm, uint64_t t
 template<bool POW2, class Fn>
 BTL_HD void list_for_each_hash(const SeqParams& P, uint32_t w, Fn&& fn)
 {
+	if (P.pending_slots) { // recorded when the window was deferred
+		const uint64_t* src = P.pending_slots + (uint64_t)w * P.h;
+		for (uint32_t i = 0; i < P.h; i++)
+			if (!fn(ld_cg(src + i)))
+				return;
+		return;
+	}
 	const uint8_t* s = P.bases + w;
 	const uint32_t k = P.k;
 	uint64_t F = 0, RC = 0;

@@ -102,6 +102,23 @@ def test_random_cbf_host_driven_rounds(oracle, golden):
     S.check_golden_bf(be, golden)
 
 
+def test_random_cbf_ungrouped_commit(oracle, golden):
+    """pass 2 of the ordered updates one window at a time (the form spaced seeds and h > 8 use)"""
+    from _backends import GpuBackend
+    be = GpuBackend(chunk=4096, batch=4096, resv_log2=12, list_log2=8, ungrouped_commit=1)
+    S.check_random_cbf(be, oracle, 9, 4, 256, seed=1, n_seqs=80, max_len=200)
+    S.check_random_cbf(be, oracle, 25, 6, 100_000, seed=2)
+    S.check_golden_cbf(be, golden)
+    S.check_golden_bf(be, golden)
+
+
+@pytest.mark.parametrize("h", [1, 3, 5, 8, 11])
+def test_random_cbf_every_group_width(gpu_small, gpu, oracle, h):
+    """grouped commit pass for each compile-time h (and the general form beyond 8)"""
+    S.check_random_cbf(gpu_small, oracle, 13, h, 40_000, seed=h)
+    S.check_random_cbf(gpu, oracle, 21, h, 1 << 20, seed=10 + h, n_seqs=60, max_len=2000)
+
+
 def test_random_cbf_small_tables(gpu_small, oracle):
     S.check_random_cbf(gpu_small, oracle, 9, 4, 256, seed=1, n_seqs=80, max_len=200)
     f = gpu_small.filter(1, 64, 3, 5)
