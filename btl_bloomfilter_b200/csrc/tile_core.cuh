@@ -60,6 +60,56 @@ BTL_HD uint32_t ld_cg(const uint32_t* p) { return *(const volatile uint32_t*)p; 
 BTL_HD uint64_t ld_cg(const uint64_t* p) { return *(const volatile uint64_t*)p; }
 #endif
 
+// L2 residency hints for the ordered updates: the reservation sketch (re-read by every pass of a batch) is
+// marked evict_last, the counters that stream through once per batch evict_first, so that the stream does
+// not push the sketch out of the 126 MB L2.
+#if defined(__CUDA_ARCH__)
+BTL_HD uint64_t l2_keep()
+{
+	uint64_t p;
+	asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+BTL_HD uint64_t l2_stream()
+{
+	uint64_t p;
+	asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+BTL_HD uint32_t ld_keep(const uint32_t* a)
+{
+	uint32_t v;
+	asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(l2_keep()) : "memory");
+	return v;
+}
+BTL_HD uint32_t atomic_or_keep(uint32_t* a, uint32_t v)
+{
+	uint32_t old;
+	asm volatile("atom.global.or.L2::cache_hint.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(a), "r"(v), "l"(l2_keep()) : "memory");
+	return old;
+}
+BTL_HD void red_or_keep(uint32_t* a, uint32_t v)
+{
+	asm volatile("red.global.or.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(a), "r"(v), "l"(l2_keep()) : "memory");
+}
+BTL_HD uint32_t ld_stream(const uint8_t* a)
+{
+	uint32_t v;
+	asm volatile("ld.global.cg.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(l2_stream()) : "memory");
+	return v;
+}
+BTL_HD void st_stream(uint8_t* a, uint32_t v)
+{
+	asm volatile("st.global.L2::cache_hint.u8 [%0], %1, %2;" ::"l"(a), "r"(v), "l"(l2_stream()) : "memory");
+}
+#else
+BTL_HD uint32_t ld_keep(const uint32_t* a) { return *(const volatile uint32_t*)a; }
+BTL_HD uint32_t atomic_or_keep(uint32_t* a, uint32_t v) { return __sync_fetch_and_or(a, v); }
+BTL_HD void red_or_keep(uint32_t* a, uint32_t v) { __sync_fetch_and_or(a, v); }
+BTL_HD uint32_t ld_stream(const uint8_t* a) { return *(const volatile uint8_t*)a; }
+BTL_HD void st_stream(uint8_t* a, uint32_t v) { *(volatile uint8_t*)a = (uint8_t)v; }
+#endif
+
 BTL_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) // (hi:lo >> sh) low word, sh in [0,31]
 {
 #if defined(__CUDA_ARCH__)
@@ -365,12 +415,12 @@ BTL_HD uint32_t resv_pos2(uint64_t slot, uint32_t log2)
 BTL_HD void resv_count(const SeqParams& P, uint32_t e)
 {
 	uint32_t bit = 1u << (e & 31);
-	if (mem_atomic_or(P.resv_touched + (e >> 5), bit) & bit)
-		mem_red_or(P.resv_contended + (e >> 5), bit);
+	if (atomic_or_keep(P.resv_touched + (e >> 5), bit) & bit)
+		red_or_keep(P.resv_contended + (e >> 5), bit);
 }
 BTL_HD bool resv_twice(const SeqParams& P, uint32_t e)
 {
-	return (ld_cg(P.resv_contended + (e >> 5)) >> (e & 31)) & 1u;
+	return (ld_keep(P.resv_contended + (e >> 5)) >> (e & 31)) & 1u;
 }
 
 // ---------------------------------------------------------------- the fused per-window operation
@@ -762,8 +812,8 @@ BTL_HD ThreadOut tile_phase_c_commit(const SeqParams& P, const TileSmem& sm, uin
 #pragma unroll
 			for (int i = 0; i < H; i++) {
 				const bool on = (okmask >> g) & 1u;
-				w1[g][i] = on ? ld_cg(P.resv_contended + (resv_pos1(slot[g][i], P.resv_log2) >> 5)) : 0u;
-				w2[g][i] = on ? ld_cg(P.resv_contended + (resv_pos2(slot[g][i], P.resv_log2) >> 5)) : 0u;
+				w1[g][i] = on ? ld_keep(P.resv_contended + (resv_pos1(slot[g][i], P.resv_log2) >> 5)) : 0u;
+				w2[g][i] = on ? ld_keep(P.resv_contended + (resv_pos2(slot[g][i], P.resv_log2) >> 5)) : 0u;
 			}
 		uint32_t freemask = 0; // windows that share no slot with any other k-mer of the batch
 #pragma unroll
@@ -782,7 +832,7 @@ BTL_HD ThreadOut tile_phase_c_commit(const SeqParams& P, const TileSmem& sm, uin
 			for (int g = 0; g < G; g++)
 #pragma unroll
 				for (int i = 0; i < H; i++)
-					v[g][i] = ((freemask >> g) & 1u) ? (uint32_t)ld_cg(cnt + slot[g][i]) : 255u;
+					v[g][i] = ((freemask >> g) & 1u) ? ld_stream(cnt + slot[g][i]) : 255u;
 #pragma unroll
 			for (int g = 0; g < G; g++) {
 				if (!((freemask >> g) & 1u))
@@ -795,7 +845,7 @@ BTL_HD ThreadOut tile_phase_c_commit(const SeqParams& P, const TileSmem& sm, uin
 #pragma unroll
 					for (int i = 0; i < H; i++)
 						if (v[g][i] == mn)
-							*(volatile uint8_t*)(cnt + slot[g][i]) = (uint8_t)(mn + 1);
+							st_stream(cnt + slot[g][i], mn + 1);
 				}
 				if (mn >= P.threshold) // insertAndCheck reports the minimum before the update, :206-214
 					out.hitw |= 1u << (s0 + g);
