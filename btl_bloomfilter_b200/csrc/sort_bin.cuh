@@ -90,7 +90,7 @@ BTL_HD size_t sort_arrays_bytes(uint32_t n_bins, int h)
 	const size_t cap = (size_t)kSortThreads * sort_round_windows(h) * h;
 	size_t s = nbr * 8;                 // gdelta
 	s += cap * 8;                       // sorted_off, sorted_aux
-	s += nbr * 4 * 3;                   // hist, base, cursor
+	s += nbr * 4 * 3 + 32 * 4;          // hist (+ 32 per-lane dump slots for invalid windows), base, cursor
 	s += (kSortThreads / 32 + 2) * 4;   // warp sums, total, overflow flag
 	return (s + 15) / 16 * 16;
 }
@@ -108,7 +108,6 @@ __global__ void __launch_bounds__(kSortThreads, 2) bin_kernel_sort(const __grid_
 	constexpr int ITEMS = W * H;
 	constexpr uint32_t CAPACITY = (uint32_t)kSortThreads * ITEMS;
 	constexpr uint32_t NW = kSortThreads / 32;
-	constexpr uint32_t kNone = 0xffffffffu;
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t nb = P.n_bins, nbr = (nb + 1u) & ~1u;
@@ -118,7 +117,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) bin_kernel_sort(const __grid_
 	uint64_t* const gdelta = reinterpret_cast<uint64_t*>(p);     p += (size_t)nbr * 8;
 	uint32_t* const sorted_off = reinterpret_cast<uint32_t*>(p); p += (size_t)CAPACITY * 4;
 	uint32_t* const sorted_aux = reinterpret_cast<uint32_t*>(p); p += (size_t)CAPACITY * 4;
-	uint32_t* const hist = reinterpret_cast<uint32_t*>(p);       p += (size_t)nbr * 4;
+	uint32_t* const hist = reinterpret_cast<uint32_t*>(p);       p += (size_t)(nbr + 32) * 4;
 	uint32_t* const base = reinterpret_cast<uint32_t*>(p);       p += (size_t)nbr * 4;
 	uint32_t* const cursor = reinterpret_cast<uint32_t*>(p);     p += (size_t)nbr * 4;
 	uint32_t* const wsum = reinterpret_cast<uint32_t*>(p); // [NW] warp sums, [NW] total, [NW+1] overflow flag
@@ -128,6 +127,11 @@ __global__ void __launch_bounds__(kSortThreads, 2) bin_kernel_sort(const __grid_
 		hist[b] = 0;
 		cursor[b] = b < nb ? P.bin_counts[(uint64_t)b * P.bin_writers + writer] : 0u;
 	}
+	if (tid < 32)
+		hist[nbr + tid] = 0;
+	// Items of windows that are not k-mers are counted in a per-lane dump slot behind the histogram instead of
+	// being branched around: the four atomics of a window then issue back to back and their latencies overlap.
+	const uint32_t dump = nbr + (uint32_t)lane;
 
 	// tile t belongs to writer (t + bin_rot) % gridDim.x: the host advances bin_rot from launch to launch so
 	// that a stream of small batches still spreads evenly over the writers' sub-buckets
@@ -157,8 +161,9 @@ __global__ void __launch_bounds__(kSortThreads, 2) bin_kernel_sort(const __grid_
 				for (int i = 0; i < H; i++) {
 					const uint64_t n = fastmod<POW2>(hv[i], P.fm);
 					const uint32_t part = (uint32_t)(n >> P.bin_shift);
+					const uint32_t bin = ok ? part : dump;
 					it_off[ws * H + i] = (uint32_t)n & P.bin_mask;
-					it_pr[ws * H + i] = ok ? (part << 16) | atomicAdd(hist + part, 1u) : kNone;
+					it_pr[ws * H + i] = (bin << 16) | (atomicAdd(hist + bin, 1u) & 0xffffu);
 				}
 			}
 			__syncthreads();
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) bin_kernel_sort(const __grid_
 					if (v) {
 						const uint32_t c = cursor[b];
 						uint32_t cn = c + v;
-						cn = cn < c ? kNone : cn;
+						cn = cn < c ? 0xffffffffu : cn;
 						cursor[b] = cn;
 						gdelta[b] = ((uint64_t)b * P.bin_writers + writer) * P.bin_cap + c - e;
 						if (cn > P.bin_cap)
@@ -215,8 +220,8 @@ __global__ void __launch_bounds__(kSortThreads, 2) bin_kernel_sort(const __grid_
 #pragma unroll
 				for (int i = 0; i < H; i++) {
 					const uint32_t pr = it_pr[ws * H + i];
-					if (pr != kNone) {
-						const uint32_t part = pr >> 16;
+					const uint32_t part = pr >> 16;
+					if (part < nbr) {
 						const uint32_t pos = base[part] + (pr & 0xffffu);
 						sorted_off[pos] = it_off[ws * H + i];
 						sorted_aux[pos] = QUERY ? part | ((r.p0 + round * W + ws) << 12) : part;
