@@ -320,7 +320,7 @@ def main():
         h_roff = t_roff.numpy().view(np.uint64)
         t_goff = [torch.tensor([0, g_lens[j]], dtype=torch.int64).pin_memory() for j in range(n_host)]
         h_goff = [t.numpy().view(np.uint64) for t in t_goff]
-        S2 = min(S, 16)
+        S2 = min(S, 32)
         h_counts = torch.zeros((S2 + 4, 4), dtype=torch.int64).pin_memory()
         counts = h_counts.numpy().view(np.uint64)
         torch.cuda.synchronize()
