@@ -302,6 +302,31 @@ def main():
     k_ins, k_qry, k_hit = int(st[0]), int(st[2]), int(st[3])
     assert k_hit == k_qry, "a k-mer of an inserted chunk was not found (%d of %d)" % (k_hit, k_qry)
 
+    # ---- the miss set: reads of independent random bases, almost every k-mer absent.  Reported next
+    # to the headline (which is the hit set: no early exit); outside the timed region of `value`.
+    miss = None
+    if rank == 0:
+        d_miss = torch.empty(read_bases + 64, dtype=torch.uint8, device=dev)
+        ctx.synth_genome_device(d_miss.data_ptr(), 0, read_bases, 43 << 40)
+        d_ms = torch.zeros(2, dtype=torch.int64, device=dev)
+        reps = 3
+        filt.containsSeqsDevice(d_miss.data_ptr(), read_bases, d_roff.data_ptr(), n_reads, d_hits.data_ptr(), 0, d_ms.data_ptr())
+        torch.cuda.synchronize()
+        d_ms.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            filt.containsSeqsDevice(d_miss.data_ptr(), read_bases, d_roff.data_ptr(), n_reads, d_hits.data_ptr(), 0,
+                                    d_ms.data_ptr())
+        b.record(stream)
+        torch.cuda.synchronize()
+        mk, mh = [int(x) for x in d_ms.cpu().numpy()]
+        ms_miss = a.elapsed_time(b) / reps
+        miss = {"gkmers_s": mk / reps / (ms_miss * 1e-3) / 1e9, "ms_per_batch": ms_miss, "kmers_per_batch": mk // reps,
+                "hit_fraction": mh / max(1, mk),
+                "path": "adaptive: sampled hit fraction on the device picks the early-exit kernel for read sets that mostly miss"}
+        del d_miss
+
     # ---- end to end through the host-buffer C ABI (pinned inputs; H2D, kernels and D2H inside the timed region)
     # Streaming form (btlbf_insert_seqs_async / btlbf_contains_seqs_async): every step copies its genome chunk
     # and reads host->device, runs the kernels and copies the hit bits + counts device->host; the calls are
@@ -432,6 +457,8 @@ def main():
             "config": config, "insert_gkmers_s": k_ins_all / (ms_insert * 1e-3) / 1e9,
             "query_gkmers_s": k_qry_all / (ms_query * 1e-3) / 1e9, "kmers_per_step": (k_ins_all + k_qry_all) / S,
             "roofline": roof, "roofline_query": roof_q, "gpu_launches": launches_all, "clocks": clocks}
+    if miss:
+        line["query_miss_set"] = miss
     if e2e:
         line["e2e"] = {"value": e2e["kmers"] / e2e["seconds"] / 1e9, "unit": "Gk-mer/s", "steps": e2e["steps"],
                        "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],

@@ -120,6 +120,9 @@ struct btlbf_ctx
 	int64_t bin_kernel = 0;                     // 0 auto (sort-bin kernel when the shape allows), 1 legacy kernels only
 	int64_t bin_max_parts = 512;                // the sort-bin path widens the partitions until there are at most this many
 	int settle_error = 0;
+	int64_t query_adaptive = 1;      // partitioned query: sample the batch, fall back to the early-exit kernel when few k-mers hit
+	int64_t query_adaptive_pct = 20; // ... fewer than this percentage of the sampled k-mers
+	int64_t query_adaptive_min_tiles = 256; // batches below this many 4096-window tiles are not sampled
 	int64_t query_chunk_factor = 4; // BloomFilter queries of the host-buffer calls run in chunks of this many chunk_bases
 };
 
@@ -484,6 +487,16 @@ extern "C" int btlbf_ctx_set_option(btlbf_ctx* ctx, const char* key, int64_t val
 		if (value < 0)
 			return fail(BTLBF_ERR_ARG, "bin_accum_bytes out of range");
 		ctx->bin_accum_bytes = value;
+	} else if (k == "query_adaptive") {
+		ctx->query_adaptive = value != 0;
+	} else if (k == "query_adaptive_min_tiles") {
+		if (value < 1)
+			return fail(BTLBF_ERR_ARG, "query_adaptive_min_tiles must be >= 1");
+		ctx->query_adaptive_min_tiles = value;
+	} else if (k == "query_adaptive_pct") {
+		if (value < 0 || value > 101)
+			return fail(BTLBF_ERR_ARG, "query_adaptive_pct out of range [0,101]");
+		ctx->query_adaptive_pct = value;
 	} else if (k == "query_chunk_factor") {
 		if (value < 1 || value > 16)
 			return fail(BTLBF_ERR_ARG, "query_chunk_factor out of range [1,16]");
@@ -1261,14 +1274,49 @@ static int binned_query(btlbf_filter* f, SeqParams P, cudaStream_t s)
 		P.valid_bits = (uint32_t*)ctx->q_valid.p;
 	}
 	uint64_t* stats = P.stats;
-	CU(cudaMemsetAsync(P.hit_bits, 0xff, words * 4, s));
+	cudaError_t e = cudaSuccess;
+	// Adaptive path selection, entirely on the device (no host round trip, so calls still queue back to back):
+	// the early-exit kernel runs over a strided sample of the tiles; a one-thread kernel turns the sample's hit
+	// fraction into a flag; then BOTH paths are launched and the kernels of the one that lost return at once.
+	// Absent k-mers cost the early-exit kernel ~1/(1-occupancy) probes but the partitioned path all h of them
+	// (plus an atomic per missing bit), so read sets that mostly miss are faster on the direct kernel.
+	const uint64_t tiles = (P.n_windows + kTile - 1) / kTile;
+	const bool adaptive = ctx->query_adaptive && mode == BIN_SORT && tiles >= (uint64_t)ctx->query_adaptive_min_tiles &&
+	                      P.n_seeds == 0;
+	CU(cudaMemsetAsync(P.hit_bits, 0xff, words * 4, s)); // the partitioned path clears the bits of missing k-mers
+	if (adaptive) {
+		unsigned long long* sample = ctx->d_scalars + 8; // [8] valid, [9] hits, [10] flag
+		uint32_t* flag = reinterpret_cast<uint32_t*>(ctx->d_scalars + 10);
+		CU(cudaMemsetAsync(sample, 0, 24, s));
+		SeqParams S = P;
+		S.hit_bits = S.valid_bits = nullptr;
+		S.stats = reinterpret_cast<uint64_t*>(sample);
+		S.tile_count = (uint32_t)(tiles < 64 ? tiles : 64);
+		S.tile_stride = (uint32_t)(tiles / S.tile_count);
+		S.tile_first = S.tile_stride / 2;
+		S.query_mode = 0; // all h probes of a window in flight together: the sample's latency is what matters
+		TRY(launch(ctx, OP_BF_CONTAINS, S, s));
+		e = launch_query_gate(sample, flag, (uint32_t)ctx->query_adaptive_pct, s);
+		if (e != cudaSuccess)
+			return fail(BTLBF_ERR_CUDA, "query gate launch failed: %s", cudaGetErrorString(e));
+		SeqParams D = P;
+		D.gate = flag;
+		D.gate_want = 1;
+		D.query_mode = 1;
+		D.tiles_per_cta = 8; // fewer CTAs to retire when the partitioned path is the one that runs
+		TRY(launch(ctx, OP_BF_CONTAINS, D, s));
+		ctx->launches++;
+		P.gate = flag;
+		P.gate_want = 0;
+	}
 	if (mode == BIN_SORT)
 		CU(cudaMemsetAsync(P.bin_counts, 0, (size_t)P.n_bins * P.bin_writers * 4, s));
-	cudaError_t e = launch_bin(P, true, grid, s);
+	e = launch_bin(P, true, grid, s);
 	if (e == cudaSuccess)
 		e = launch_probe_bins(P, s);
 	if (e == cudaSuccess)
-		e = launch_finalize_hits(P.hit_bits, P.valid_bits, words, stats ? (unsigned long long*)(stats + 1) : nullptr, s);
+		e = launch_finalize_hits(P.hit_bits, P.valid_bits, words, stats ? (unsigned long long*)(stats + 1) : nullptr, P.gate,
+		                         P.gate_want, s);
 	if (e != cudaSuccess)
 		return fail(BTLBF_ERR_CUDA, "partitioned query launch failed: %s", cudaGetErrorString(e));
 	ctx->launches += 3;

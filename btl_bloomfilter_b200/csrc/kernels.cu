@@ -60,8 +60,23 @@ template<int OP, bool SPACED, bool POW2>
 __global__ void __launch_bounds__(kTPB) seq_kernel(const __grid_constant__ SeqParams P)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
+	if (P.gate && *P.gate != P.gate_want)
+		return;
 	const TileSmem sm = carve_smem(smem_raw, P.k, SPACED);
-	run_tile<OP, SPACED, POW2>(P, sm, (uint64_t)blockIdx.x * kTile, threadIdx.x);
+	if (P.tile_count) { // a strided sample of the tiles
+		run_tile<OP, SPACED, POW2>(P, sm, ((uint64_t)P.tile_first + (uint64_t)blockIdx.x * P.tile_stride) * kTile, threadIdx.x);
+		return;
+	}
+	const uint32_t per = P.tiles_per_cta ? P.tiles_per_cta : 1u;
+	const uint64_t tiles = (P.n_windows + kTile - 1) / kTile;
+	for (uint32_t j = 0; j < per; j++) {
+		const uint64_t tile = (uint64_t)blockIdx.x * per + j;
+		if (tile >= tiles)
+			break;
+		if (j)
+			__syncthreads(); // the previous tile is fully consumed before its staging area is overwritten
+		run_tile<OP, SPACED, POW2>(P, sm, tile * kTile, threadIdx.x);
+	}
 }
 
 // ---------------------------------------------------------------- partitioned build, pass 1
@@ -322,6 +337,8 @@ __device__ __forceinline__ void probe_one(const uint32_t* region, uint32_t* hit,
 
 __global__ void __launch_bounds__(kApplyThreads) probe_bins_kernel(const __grid_constant__ SeqParams P, uint32_t blocks_per_part)
 {
+	if (P.gate && *P.gate != P.gate_want)
+		return;
 	const uint32_t part = blockIdx.x / blocks_per_part, sub = blockIdx.x % blocks_per_part;
 	const uint32_t* region = (const uint32_t*)P.filter + ((uint64_t)part << (P.bin_shift - 5));
 	if (part + 1 < P.n_bins) {
@@ -362,8 +379,11 @@ __global__ void __launch_bounds__(kApplyThreads) probe_bins_kernel(const __grid_
 
 // hit &= valid, and the number of hits is added to stats[1]
 __global__ void __launch_bounds__(256) finalize_hits_kernel(uint32_t* hit, const uint32_t* valid, uint64_t n_words,
-                                                            unsigned long long* hits_out)
+                                                            unsigned long long* hits_out, const uint32_t* gate,
+                                                            uint32_t gate_want)
 {
+	if (gate && *gate != gate_want)
+		return;
 	unsigned long long acc = 0;
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (uint64_t)gridDim.x * blockDim.x) {
 		uint32_t h = hit[i] & valid[i];
@@ -511,14 +531,27 @@ cudaError_t launch_probe_bins(const SeqParams& P, cudaStream_t stream)
 	return cudaGetLastError();
 }
 
+// adaptive query: picks the path from the hit fraction of a sample of the batch, on the device
+__global__ void query_gate_kernel(const unsigned long long* sample_stats, uint32_t* flag, uint32_t pct)
+{
+	const unsigned long long valid = sample_stats[0], hits = sample_stats[1];
+	*flag = (valid > 0 && hits * 100ull < valid * (unsigned long long)pct) ? 1u : 0u;
+}
+
+cudaError_t launch_query_gate(const unsigned long long* sample_stats, uint32_t* flag, uint32_t pct, cudaStream_t stream)
+{
+	query_gate_kernel<<<1, 1, 0, stream>>>(sample_stats, flag, pct);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_finalize_hits(uint32_t* hit, const uint32_t* valid, uint64_t n_words, unsigned long long* hits_out,
-                                 cudaStream_t stream)
+                                 const uint32_t* gate, uint32_t gate_want, cudaStream_t stream)
 {
 	if (n_words == 0)
 		return cudaSuccess;
 	uint64_t want = (n_words + 255) / 256;
 	unsigned grid = (unsigned)(want > 148 * 8 ? 148 * 8 : want);
-	finalize_hits_kernel<<<grid, 256, 0, stream>>>(hit, valid, n_words, hits_out);
+	finalize_hits_kernel<<<grid, 256, 0, stream>>>(hit, valid, n_words, hits_out, gate, gate_want);
 	return cudaGetLastError();
 }
 
@@ -551,6 +584,10 @@ static cudaError_t launch_one(const SeqParams& P, cudaStream_t stream)
 			return e;
 	}
 	uint64_t tiles = (P.n_windows + kTile - 1) / kTile;
+	if (P.tile_count)
+		tiles = P.tile_count;
+	else if (P.tiles_per_cta > 1)
+		tiles = (tiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
 	if (tiles == 0)
 		return cudaSuccess;
 	if (tiles > 0x7fffffffULL)

@@ -79,6 +79,13 @@ struct SeqParams
 	// knobs
 	uint32_t force_generic;
 	uint32_t query_mode;
+	// device-side path selection (adaptive query): a kernel whose gate is set runs only when *gate == gate_want
+	const uint32_t* gate;
+	uint32_t gate_want;
+	// seq_kernel over a subset of the tiles: tile = tile_first + blockIdx.x * tile_stride, tile_count tiles
+	// (tile_count == 0: every tile of the chunk)
+	uint32_t tile_first, tile_stride, tile_count;
+	uint32_t tiles_per_cta; // seq_kernel: consecutive tiles handled by one CTA (0 = 1)
 	uint32_t ungrouped_commit; // ordered updates, pass 2: one window at a time (the general form) even where the grouped form applies
 };
 
@@ -97,7 +104,10 @@ cudaError_t launch_bin(const SeqParams& P, bool query, uint32_t grid, cudaStream
 cudaError_t launch_apply_bins(const SeqParams& P, cudaStream_t stream);
 cudaError_t launch_probe_bins(const SeqParams& P, cudaStream_t stream);
 cudaError_t launch_finalize_hits(uint32_t* hit, const uint32_t* valid, uint64_t n_words, unsigned long long* hits_out,
-                                 cudaStream_t stream);
+                                 const uint32_t* gate, uint32_t gate_want, cudaStream_t stream);
+// *flag = 1 (direct early-exit kernel) when fewer than pct percent of the sampled k-mers {stats[0] valid,
+// stats[1] hits} were hits, else 0 (partitioned query)
+cudaError_t launch_query_gate(const unsigned long long* sample_stats, uint32_t* flag, uint32_t pct, cudaStream_t stream);
 bool bin_query_supported(const SeqParams& P, uint32_t n_bins);
 bool bin_sort_eligible(const SeqParams& P, uint32_t n_bins); // the sort-bin kernel (sort_bin.cuh) serves this shape
 uint32_t bin_sort_tile();                                    // windows per CTA pass of the sort-bin kernel

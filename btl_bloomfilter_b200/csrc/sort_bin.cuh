@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(kSortThreads, 2) bin_kernel_sort(const __grid_
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t nb = P.n_bins, nbr = (nb + 1u) & ~1u;
 	const uint32_t writer = blockIdx.x;
+	if (P.gate && *P.gate != P.gate_want) // adaptive query: the other path was chosen for this batch
+		return;
 
 	uint8_t* p = smem_raw;
 	uint64_t* const gdelta = reinterpret_cast<uint64_t*>(p);     p += (size_t)nbr * 8;

@@ -105,6 +105,21 @@ class BloomFilter
 		return n;
 	}
 	// The query twin (README.md:46-57): one hit bit and one valid bit per window.
+	// FASTA / FASTQ files: the record loop of swig/writeBloom_rolling.cpp:19-59 (read a record, insertSeq) as one
+	// call; threads = 0 picks the number of parser threads.  Returns the k-mers inserted / found.
+	uint64_t insertFile(const std::string& path, int threads = 0, uint64_t* nSeqs = nullptr)
+	{
+		uint64_t n = 0;
+		btlbf::check(btlbf_insert_file(m_f, path.c_str(), threads, nSeqs, &n), path.c_str());
+		return n;
+	}
+	uint64_t queryFile(const std::string& path, uint64_t* nKmers = nullptr, int threads = 0, uint64_t* nSeqs = nullptr) const
+	{
+		uint64_t hits = 0;
+		btlbf::check(btlbf_query_file(m_f, path.c_str(), threads, nSeqs, nKmers, &hits), path.c_str());
+		return hits;
+	}
+
 	btlbf::SeqHits containsSeqs(const btlbf::SeqBatch& b) const
 	{
 		return containsSeqs(b.bases.data(), b.offsets.data(), b.size());

@@ -98,6 +98,25 @@ bloomScenario(const std::string& tmp)
 	oa << a;
 	ob << b;
 	CHECK(oa.str() == ob.str());
+	{
+		// the same sequences through a FASTA file (multi-line records): insertFile == insertSeqs
+		std::ofstream fa(tmp + "/seqs.fa");
+		for (size_t i = 0; i < seqs.size(); i++) {
+			fa << ">s" << i << " record\n";
+			for (size_t j = 0; j < seqs[i].size(); j += 10)
+				fa << seqs[i].substr(j, 10) << "\n";
+		}
+		fa.close();
+		BloomFilter c(8 * 1237, 4, 7);
+		uint64_t nSeqs = 0;
+		CHECK(c.insertFile(tmp + "/seqs.fa", 0, &nSeqs) == n);
+		CHECK(nSeqs == seqs.size());
+		std::ostringstream oc;
+		oc << c;
+		CHECK(oc.str() == oa.str());
+		uint64_t nk = 0;
+		CHECK(c.queryFile(tmp + "/seqs.fa", &nk) == n && nk == n);
+	}
 	btlbf::SeqHits h = a.containsSeqs(seqs);
 	CHECK(h.nKmers == n && h.nHits == n);
 	btlbf::SeqBatch batch(seqs);

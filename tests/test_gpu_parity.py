@@ -565,3 +565,23 @@ def test_mibf_bit_vector_build(oracle, bits, forced):
     r = bv.containsSeqs((q, qo))
     nk, nh, hit, valid = oracle.bf_contains_seqs(filt, bits, h, k, q, qo)
     assert (r.n_kmers, r.n_hits) == (nk, nh) and np.array_equal(r.hit_bits, hit)
+
+
+@pytest.mark.parametrize("pct", [0, 20, 101])
+def test_adaptive_query_paths_agree(oracle, pct):
+    """Partitioned query with device-side path selection: pct=0 always keeps the partitioned kernels, 101 always
+    hands the batch to the early-exit kernel, 20 decides from the sampled hit fraction; hit-rich and miss-rich
+    read sets must give the oracle's bits on every setting."""
+    from _backends import GpuBackend
+    be = GpuBackend(bin_shift=12, query_adaptive=1, query_adaptive_pct=pct, query_adaptive_min_tiles=1)
+    bits, h, k = 1 << 20, 4, 25
+    rng = np.random.default_rng(77)
+    b, off = S.rand_batch(rng, 30, 3000, p_n=0.005)
+    f = be.filter(0, bits, h, k)
+    filt = np.zeros(bits // 8, np.uint8)
+    assert f.insert((b, off)) == oracle.bf_insert_seqs(filt, bits, h, k, b, off)
+    miss = S.rand_batch(rng, 40, 2500)
+    for (x, xo) in ((b, off), miss, (np.concatenate([b, miss[0]]), np.concatenate([off, off[-1] + miss[1][1:]]))):
+        nk, nh, hit, valid = f.contains((x, xo))
+        e = oracle.bf_contains_seqs(filt, bits, h, k, x, xo)
+        assert (nk, nh) == e[:2] and np.array_equal(hit, e[2]) and np.array_equal(valid, e[3])
