@@ -120,6 +120,7 @@ struct btlbf_ctx
 	int64_t bin_kernel = 0;                     // 0 auto (sort-bin kernel when the shape allows), 1 legacy kernels only
 	int64_t bin_max_parts = 512;                // the sort-bin path widens the partitions until there are at most this many
 	int settle_error = 0;
+	int64_t peer_unroll = 1, peer_grid = 0, peer_mode = 0; // fused multi-GPU merge: vectors in flight per thread and peer, CTAs
 	int64_t query_adaptive = 1;      // partitioned query: sample the batch, fall back to the early-exit kernel when few k-mers hit
 	int64_t query_adaptive_pct = 20; // ... fewer than this percentage of the sampled k-mers
 	int64_t query_adaptive_min_tiles = 256; // batches below this many 4096-window tiles are not sampled
@@ -487,6 +488,12 @@ extern "C" int btlbf_ctx_set_option(btlbf_ctx* ctx, const char* key, int64_t val
 		if (value < 0)
 			return fail(BTLBF_ERR_ARG, "bin_accum_bytes out of range");
 		ctx->bin_accum_bytes = value;
+	} else if (k == "peer_unroll") {
+		ctx->peer_unroll = value;
+	} else if (k == "peer_mode") {
+		ctx->peer_mode = value;
+	} else if (k == "peer_grid") {
+		ctx->peer_grid = value < 0 ? 0 : value;
 	} else if (k == "query_adaptive") {
 		ctx->query_adaptive = value != 0;
 	} else if (k == "query_adaptive_min_tiles") {
@@ -864,6 +871,9 @@ extern "C" int btlbf_merge_peers(btlbf_ctx* ctx, int kind, void* const* bases, i
 	}
 	M.world = (uint32_t)world;
 	M.sat_add = kind == BTLBF_COUNTING8;
+	M.unroll = (uint32_t)ctx->peer_unroll;
+	M.grid = (uint32_t)ctx->peer_grid;
+	M.mode = (uint32_t)ctx->peer_mode;
 	TRY(btlbf_merge_slice(nbytes, world, rank, &M.lo, &M.hi));
 	cudaError_t e = launch_peer_merge(M, joined(ctx));
 	if (e != cudaSuccess)

@@ -961,43 +961,59 @@ __global__ void __launch_bounds__(256) merge_kernel(uint8_t* __restrict__ dst, c
 // stored into all N filters.  No staging buffer, one pass; the NVLink loads of one vector overlap the
 // stores of the previous ones.  Ranges of different ranks are disjoint, so the kernels of all ranks run
 // concurrently; the host brackets them with barriers.
-template<int WORLD>
+template<int WORLD, int UNROLL>
 __global__ void __launch_bounds__(256) peer_merge_kernel(const __grid_constant__ PeerMergeParams M)
 {
 	const uint64_t nvec = (M.hi - M.lo) / 16;
 	const int world = WORLD ? WORLD : (int)M.world;
-	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (uint64_t)gridDim.x * blockDim.x) {
-		const uint64_t o = M.lo + i * 16;
-		uint4 v[WORLD ? WORLD : 1];
-		uint4 acc;
+	// a CTA handles UNROLL consecutive groups of 256 vectors per iteration: UNROLL * WORLD 16-byte loads per
+	// thread are in flight before the first one is consumed
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * UNROLL;
+	for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x * UNROLL + threadIdx.x; i0 < nvec; i0 += stride) {
+		uint4 v[UNROLL][WORLD ? WORLD : 1];
 		if (WORLD) {
 #pragma unroll
-			for (int p = 0; p < WORLD; p++)
-				v[p] = *reinterpret_cast<const uint4*>(M.base[p] + o);
-			acc = v[0];
+			for (int u = 0; u < UNROLL; u++) {
+				const uint64_t i = i0 + (uint64_t)u * blockDim.x;
 #pragma unroll
-			for (int p = 1; p < WORLD; p++) {
-				if (M.sat_add) {
-					acc.x = __vaddus4(acc.x, v[p].x); acc.y = __vaddus4(acc.y, v[p].y);
-					acc.z = __vaddus4(acc.z, v[p].z); acc.w = __vaddus4(acc.w, v[p].w);
-				} else {
-					acc.x |= v[p].x; acc.y |= v[p].y; acc.z |= v[p].z; acc.w |= v[p].w;
-				}
-			}
-		} else {
-			acc = *reinterpret_cast<const uint4*>(M.base[0] + o);
-			for (int p = 1; p < world; p++) {
-				uint4 b = *reinterpret_cast<const uint4*>(M.base[p] + o);
-				if (M.sat_add) {
-					acc.x = __vaddus4(acc.x, b.x); acc.y = __vaddus4(acc.y, b.y);
-					acc.z = __vaddus4(acc.z, b.z); acc.w = __vaddus4(acc.w, b.w);
-				} else {
-					acc.x |= b.x; acc.y |= b.y; acc.z |= b.z; acc.w |= b.w;
-				}
+				for (int p = 0; p < WORLD; p++)
+					v[u][p] = i < nvec && (p == 0 || M.mode != 2) ? *reinterpret_cast<const uint4*>(M.base[p] + M.lo + i * 16)
+					                                             : make_uint4(0, 0, 0, 0);
 			}
 		}
-		for (int p = 0; p < world; p++)
-			*reinterpret_cast<uint4*>(M.base[p] + o) = acc;
+#pragma unroll
+		for (int u = 0; u < UNROLL; u++) {
+			const uint64_t i = i0 + (uint64_t)u * blockDim.x;
+			if (i >= nvec)
+				break;
+			const uint64_t o = M.lo + i * 16;
+			uint4 acc;
+			if (WORLD) {
+				acc = v[u][0];
+#pragma unroll
+				for (int p = 1; p < WORLD; p++) {
+					if (M.sat_add) {
+						acc.x = __vaddus4(acc.x, v[u][p].x); acc.y = __vaddus4(acc.y, v[u][p].y);
+						acc.z = __vaddus4(acc.z, v[u][p].z); acc.w = __vaddus4(acc.w, v[u][p].w);
+					} else {
+						acc.x |= v[u][p].x; acc.y |= v[u][p].y; acc.z |= v[u][p].z; acc.w |= v[u][p].w;
+					}
+				}
+			} else {
+				acc = *reinterpret_cast<const uint4*>(M.base[0] + o);
+				for (int p = 1; p < world; p++) {
+					uint4 b = *reinterpret_cast<const uint4*>(M.base[p] + o);
+					if (M.sat_add) {
+						acc.x = __vaddus4(acc.x, b.x); acc.y = __vaddus4(acc.y, b.y);
+						acc.z = __vaddus4(acc.z, b.z); acc.w = __vaddus4(acc.w, b.w);
+					} else {
+						acc.x |= b.x; acc.y |= b.y; acc.z |= b.z; acc.w |= b.w;
+					}
+				}
+			}
+			for (int p = 0; p < (M.mode == 1 ? 1 : world); p++)
+				*reinterpret_cast<uint4*>(M.base[p] + o) = acc;
+		}
 	}
 }
 
@@ -1008,14 +1024,23 @@ cudaError_t launch_peer_merge(const PeerMergeParams& M, cudaStream_t stream)
 	uint64_t nvec = (M.hi - M.lo) / 16;
 	if (nvec == 0)
 		return cudaSuccess;
-	uint64_t want = (nvec + 255) / 256;
-	unsigned grid = (unsigned)(want > 148 * 8 ? 148 * 8 : want);
+	const unsigned unroll = M.unroll == 2 || M.unroll == 4 ? M.unroll : 1;
+	uint64_t want = (nvec + 256 * unroll - 1) / (256 * unroll);
+	const uint64_t cap = M.grid ? M.grid : 148 * 8;
+	unsigned grid = (unsigned)(want > cap ? cap : want);
+#define BTL_PEER(W)                                                                  \
+	do {                                                                             \
+		if (unroll == 4) peer_merge_kernel<W, 4><<<grid, 256, 0, stream>>>(M);       \
+		else if (unroll == 2) peer_merge_kernel<W, 2><<<grid, 256, 0, stream>>>(M);  \
+		else peer_merge_kernel<W, 1><<<grid, 256, 0, stream>>>(M);                   \
+	} while (0)
 	switch (M.world) {
-	case 2: peer_merge_kernel<2><<<grid, 256, 0, stream>>>(M); break;
-	case 4: peer_merge_kernel<4><<<grid, 256, 0, stream>>>(M); break;
-	case 8: peer_merge_kernel<8><<<grid, 256, 0, stream>>>(M); break;
-	default: peer_merge_kernel<0><<<grid, 256, 0, stream>>>(M); break;
+	case 2: BTL_PEER(2); break;
+	case 4: BTL_PEER(4); break;
+	case 8: BTL_PEER(8); break;
+	default: peer_merge_kernel<0, 1><<<grid, 256, 0, stream>>>(M); break;
 	}
+#undef BTL_PEER
 	return cudaGetLastError();
 }
 

@@ -156,6 +156,9 @@ struct PeerMergeParams
 	uint32_t world;
 	int sat_add;
 	uint64_t lo, hi; // multiples of 16
+	uint32_t unroll; // 16-byte vectors per thread and peer in flight (1, 2 or 4)
+	uint32_t grid;   // CTAs (0: 8 per SM)
+	uint32_t mode;   // 0: the merge; measurement only: 1 = peer loads without peer stores, 2 = peer stores without peer loads
 };
 cudaError_t launch_peer_merge(const PeerMergeParams& M, cudaStream_t stream);
 cudaError_t launch_synth_genome(uint8_t* out, uint64_t start, uint64_t n, uint64_t seed,

@@ -138,8 +138,8 @@ def bench_merge(filt, ctx, dev, repeats=3):
     dist.all_gather(pops, pop)
     ms = float(tt[0])
     traffic = 2.0 * (world - 1) / world * pad  # bytes sent (= received) per GPU: all-to-all + all-gather
-    out = {"nccl_ms": ms, "filter_bytes": int(nbytes), "nccl_bytes_per_gpu_per_direction": int(traffic),
-           "nccl_GBps_per_gpu_per_direction": traffic / (ms * 1e-3) / 1e9,
+    out = {"nccl_ms": ms, "filter_bytes": int(nbytes), "link_bytes_per_gpu_per_direction": int(traffic),
+           "nccl_link_GBps_per_gpu_per_direction": traffic / (ms * 1e-3) / 1e9,
            "identical_popcount_on_all_ranks": len({int(p) for p in pops}) == 1, "popcount": int(pops[0])}
     # the fused kernel over peer memory, on the (already merged, hence idempotent under OR) filters
     if filt.KIND == 0:
@@ -162,11 +162,10 @@ def bench_merge(filt, ctx, dev, repeats=3):
         pops2 = [torch.zeros_like(pop2) for _ in range(world)]
         dist.all_gather(pops2, pop2)
         out["fused_ms"] = float(tf[0])
-        # the fused kernel moves (N-1)/N of the filter in (peer loads) and the same amount out (peer stores),
-        # both at the same time: half the NCCL path's per-direction traffic, in one phase
-        one_way = (world - 1) / world * pad
-        out["fused_bytes_in_and_out_per_gpu"] = int(one_way)
-        out["fused_GBps_per_gpu_per_direction"] = one_way / (float(tf[0]) * 1e-3) / 1e9
+        # every NVLink direction of a GPU carries the payload of its own peer loads / stores plus that of the
+        # peers' stores / loads aimed at it: 2 (N-1)/N of the filter per direction, like the NCCL path, but in
+        # one phase
+        out["fused_link_GBps_per_gpu_per_direction"] = traffic / (float(tf[0]) * 1e-3) / 1e9
         out["fused_popcount_unchanged"] = all(int(p) == int(pops[0]) for p in pops2)
     out["ms"] = min(ms, out.get("fused_ms", ms))
     return out
