@@ -398,6 +398,8 @@ extern "C" int btlbf_ctx_set_stream(btlbf_ctx* ctx, void* cuda_stream)
 	return BTLBF_OK;
 }
 
+static int take_settle_error(btlbf_ctx* ctx);
+
 extern "C" int btlbf_ctx_sync(btlbf_ctx* ctx)
 {
 	TRY(use(ctx));
@@ -406,14 +408,22 @@ extern "C" int btlbf_ctx_sync(btlbf_ctx* ctx)
 	CU(cudaStreamSynchronize(ctx->copy_out));
 	for (int i = 0; i < kTickets; i++)
 		ctx->ticket[i].in_use = false;
-	return BTLBF_OK;
+	return take_settle_error(ctx);
+}
+
+// a failed pass-2 launch inside joined() (which cannot report it) is reported by the next sync / flush
+static int take_settle_error(btlbf_ctx* ctx)
+{
+	int rc = ctx->settle_error;
+	ctx->settle_error = 0;
+	return rc == 0 ? BTLBF_OK : fail(rc, "a deferred pass of the partitioned build failed to launch");
 }
 
 extern "C" int btlbf_ctx_flush(btlbf_ctx* ctx)
 {
 	TRY(use(ctx));
 	joined(ctx);
-	return BTLBF_OK;
+	return take_settle_error(ctx);
 }
 
 extern "C" int btlbf_ctx_aux_stream(btlbf_ctx* ctx, void** cuda_stream)
@@ -623,6 +633,8 @@ extern "C" int btlbf_filter_clear(btlbf_filter* f)
 	if (!f)
 		return fail(BTLBF_ERR_ARG, "null filter");
 	TRY(use(f->ctx));
+	if (f->ctx->acc.f == f)
+		f->ctx->acc.f = nullptr; // k-mers still parked in the partition buckets vanish with the rest
 	CU(cudaMemsetAsync(f->d_data, 0, (f->bytes + 15) / 16 * 16, joined(f->ctx)));
 	return BTLBF_OK;
 }
@@ -657,6 +669,8 @@ extern "C" int btlbf_filter_upload(btlbf_filter* f, const void* host, uint64_t n
 		return fail(BTLBF_ERR_ARG, "upload of %llu bytes into a %llu-byte filter", (unsigned long long)nbytes,
 		            (unsigned long long)f->bytes);
 	TRY(use(f->ctx));
+	if (f->ctx->acc.f == f)
+		f->ctx->acc.f = nullptr; // overwritten anyway
 	CU(cudaMemcpyAsync(f->d_data, host, nbytes, cudaMemcpyHostToDevice, joined(f->ctx)));
 	uint64_t pad = (f->bytes + 15) / 16 * 16 - f->bytes;
 	if (pad)

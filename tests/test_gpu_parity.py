@@ -585,3 +585,24 @@ def test_adaptive_query_paths_agree(oracle, pct):
         nk, nh, hit, valid = f.contains((x, xo))
         e = oracle.bf_contains_seqs(filt, bits, h, k, x, xo)
         assert (nk, nh) == e[:2] and np.array_equal(hit, e[2]) and np.array_equal(valid, e[3])
+
+
+def test_clear_and_upload_drop_parked_kmers(oracle):
+    """k-mers parked in the partition buckets (pass 1 done, pass 2 pending) must not survive a clear() or a
+    whole-array upload that logically follows them"""
+    from _backends import GpuBackend
+    be = GpuBackend(bin_shift=10)
+    bits, h, k = 1 << 18, 4, 21
+    rng = np.random.default_rng(5)
+    b, off = S.rand_batch(rng, 8, 3000)
+    f = be.filter(0, bits, h, k)
+    f.insert((b, off))
+    f.f.clear()
+    assert not f.bytes().any()
+    f.insert((b, off))
+    other = rng.integers(0, 256, bits // 8).astype(np.uint8)
+    f.set_bytes(other)
+    assert np.array_equal(f.bytes(), other)
+    filt = other.copy()
+    assert f.insert((b, off)) == oracle.bf_insert_seqs(filt, bits, h, k, b, off)
+    assert np.array_equal(f.bytes(), filt)
