@@ -22,7 +22,7 @@ python -c "
 import json
 d=json.load(open('gpurun_out/bench_$tag.json'))
 print('value %.2f insert %.2f query %.2f e2e %.2f launches %d' % (d['value'], d['insert_gkmers_s'], d['query_gkmers_s'], d['e2e']['value'], d['gpu_launches']))
-print('roofline frac %.3f query frac %.3f' % (d['roofline']['frac'], d['roofline_query']['frac']))
+print('roofline (query) frac %.3f build frac %.3f step frac %.3f' % (d['roofline']['frac'], d['roofline_build']['frac'], d['roofline_step']['frac']))
 print('cpu', d['cpu_baseline']['value'], d['cpu_baseline']['cores'])
 r=json.load(open('gpurun_out/bench_ref_$tag.json')); print('ref arm', r['value'], r['cpu_baseline']['cores'])
 "

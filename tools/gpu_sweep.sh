@@ -5,6 +5,6 @@ for a in "$@"; do
   python - "$a" <<'PY'
 import json,sys
 d=json.load(open("gpurun_out/sweep.json"))
-print("%-40s value %.2f insert %.2f (%.2f ms, frac %.3f) query %.2f (%.2f ms, frac %.3f) launches %d" % (sys.argv[1], d["value"], d["insert_gkmers_s"], d["roofline"]["launch_ms"], d["roofline"]["frac"], d["query_gkmers_s"], d["roofline_query"]["launch_ms"], d["roofline_query"]["frac"], d["gpu_launches"]))
+print("%-40s value %.2f insert %.2f (%.2f ms, frac %.3f) query %.2f (%.2f ms, frac %.3f) launches %d" % (sys.argv[1], d["value"], d["insert_gkmers_s"], d["roofline_build"]["launch_ms"], d["roofline_build"]["frac"], d["query_gkmers_s"], d["roofline"]["launch_ms"], d["roofline"]["frac"], d["gpu_launches"]))
 PY
 done
