@@ -29,6 +29,7 @@ SIGNATURES = {
     "btlbf_ctx_flush": [vp],
     "btlbf_ctx_aux_stream": [vp, C.POINTER(vp)],
     "btlbf_ctx_launch_count": [vp, u64p],
+    "btlbf_ctx_counter": [vp, C.c_char_p, u64p],
     "btlbf_ctx_set_option": [vp, C.c_char_p, C.c_int64],
     "btlbf_filter_create": [vp, C.c_int, u64, u32, u32, u32, C.POINTER(vp)],
     "btlbf_filter_wrap": [vp, C.c_int, u64, u32, u32, u32, vp, u64, C.POINTER(vp)],

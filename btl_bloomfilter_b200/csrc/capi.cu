@@ -106,6 +106,10 @@ struct btlbf_ctx
 	Ticket ticket[kTickets];
 	uint64_t slot_seq = 0, ticket_seq = 0;
 	DevBuf ibin_items[2], ibin_counts[2], qbin_items, qbin_counts, q_hit, q_valid;
+	DevBuf ibin2_items, ibin2_counts; // level-2 buckets of the two-level pass 2 (apply2.cu)
+	int64_t bin_two_level = 0;        // 1: two-level pass 2 (apply2.cu); measured slower than the L2-atomics pass on B200
+	int64_t bin_two_level_min = (int64_t)1 << 26; // items below which the one-level pass is used
+	uint64_t two_level_passes = 0;
 	uint64_t binned_launches = 0;
 	// Accumulation of the partitioned build: pass 1 of successive batches appends to the same sub-buckets and
 	// pass 2 runs once they are full or the filter contents are needed (settle()).
@@ -375,6 +379,8 @@ extern "C" int btlbf_ctx_destroy(btlbf_ctx* ctx)
 	}
 	release(ctx->qbin_items);
 	release(ctx->qbin_counts);
+	release(ctx->ibin2_items);
+	release(ctx->ibin2_counts);
 	if (ctx->aux) cudaStreamDestroy(ctx->aux);
 	release(ctx->q_hit);
 	release(ctx->q_valid);
@@ -431,6 +437,19 @@ extern "C" int btlbf_ctx_aux_stream(btlbf_ctx* ctx, void** cuda_stream)
 	if (!ctx || !cuda_stream)
 		return fail(BTLBF_ERR_ARG, "null argument");
 	*cuda_stream = (void*)ctx->aux;
+	return BTLBF_OK;
+}
+
+extern "C" int btlbf_ctx_counter(btlbf_ctx* ctx, const char* name, uint64_t* value)
+{
+	if (!ctx || !name || !value)
+		return fail(BTLBF_ERR_ARG, "null argument");
+	std::string k(name);
+	if (k == "launches") *value = ctx->launches;
+	else if (k == "binned_launches") *value = ctx->binned_launches;
+	else if (k == "two_level_passes") *value = ctx->two_level_passes;
+	else
+		return fail(BTLBF_ERR_ARG, "unknown counter '%s'", name);
 	return BTLBF_OK;
 }
 
@@ -518,6 +537,10 @@ extern "C" int btlbf_ctx_set_option(btlbf_ctx* ctx, const char* key, int64_t val
 		if (value < 1 || value > 16)
 			return fail(BTLBF_ERR_ARG, "query_chunk_factor out of range [1,16]");
 		ctx->query_chunk_factor = value;
+	} else if (k == "bin_two_level") {
+		ctx->bin_two_level = value != 0;
+	} else if (k == "bin_two_level_min") {
+		ctx->bin_two_level_min = value < 0 ? 0 : value;
 	} else if (k == "bin_kernel") {
 		ctx->bin_kernel = value != 0;
 	} else if (k == "bin_max_parts") {
@@ -1158,14 +1181,58 @@ static int bin_setup(btlbf_filter* f, SeqParams& P, bool query, uint64_t capacit
 
 // pass 2 of the partitioned build for the sub-buckets described by P: on the background stream when
 // overlapping (it then runs under the next batches' pass 1), else on s
-static int apply_pass(btlbf_ctx* ctx, const SeqParams& P, int slot, cudaStream_t s)
+static int apply_pass(btlbf_ctx* ctx, const SeqParams& P, int slot, cudaStream_t s, uint64_t windows)
 {
 	cudaStream_t s2 = ctx->overlap ? ctx->aux : s;
 	if (ctx->overlap) {
 		CU(cudaEventRecord(ctx->ev_bin_done[slot], s));
 		CU(cudaStreamWaitEvent(s2, ctx->ev_bin_done[slot], 0));
 	}
-	cudaError_t e = launch_apply_bins(P, s2);
+	// Two-level pass 2 (apply2.cu) when there are enough items to pay for splitting them a second time.  Not in
+	// overlap mode: its plain stores of whole slices must not race with the direct atomics of a concurrent pass 1.
+	uint32_t sub_shift = 0, n_sub = 0;
+	const uint64_t items = windows * P.h;
+	bool two = ctx->bin_two_level && !ctx->overlap && P.bin_segs > 1 && items >= (uint64_t)ctx->bin_two_level_min &&
+	           apply2_geometry(P.bin_shift, &sub_shift, &n_sub);
+	cudaError_t e = cudaSuccess;
+	if (two) {
+		Apply2Params A;
+		memset(&A, 0, sizeof A);
+		A.items = P.bin_items; A.counts = P.bin_counts;
+		A.n_bins = P.n_bins; A.writers = P.bin_writers; A.cap = P.bin_cap; A.bin_shift = P.bin_shift;
+		A.sub_shift = sub_shift; A.n_sub = n_sub;
+		A.writers2 = P.bin_writers < 32 ? P.bin_writers : 32;
+		double parts = (double)P.fm.m / (double)((uint64_t)1 << P.bin_shift);
+		double expect = (double)items / parts / n_sub / A.writers2;
+		uint64_t cap2 = (uint64_t)(expect * 1.3) + 32;
+		cap2 = (cap2 + 3) / 4 * 4;
+		const uint64_t buckets = (uint64_t)P.n_bins * n_sub * A.writers2;
+		if (cap2 > 0x7ffffff0ULL || buckets * cap2 * 4 > ((uint64_t)64 << 30))
+			two = false;
+		else {
+			A.cap2 = (uint32_t)cap2;
+			if (buckets * cap2 * 4 > ctx->ibin2_items.cap || buckets * 4 > ctx->ibin2_counts.cap)
+				CU(cudaStreamSynchronize(s2)); // growing a buffer frees the old one
+			int rc = ensure(ctx->ibin2_items, buckets * cap2 * 4);
+			if (rc == BTLBF_OK)
+				rc = ensure(ctx->ibin2_counts, buckets * 4);
+			if (rc != BTLBF_OK) {
+				cudaGetLastError();
+				two = false; // not enough memory for the second level: the one-level pass needs none
+			} else {
+				A.items2 = (uint32_t*)ctx->ibin2_items.p;
+				A.counts2 = (uint32_t*)ctx->ibin2_counts.p;
+				A.filter = (uint32_t*)P.filter;
+				A.m = P.fm.m;
+				A.alloc_words = ((P.fm.m + 127) / 128) * 4;
+				e = launch_apply2(A, s2);
+				ctx->launches++; // two kernels
+				ctx->two_level_passes++;
+			}
+		}
+	}
+	if (!two)
+		e = launch_apply_bins(P, s2);
 	if (e != cudaSuccess)
 		return fail(BTLBF_ERR_CUDA, "partitioned build (pass 2) launch failed: %s", cudaGetErrorString(e));
 	CU(cudaEventRecord(ctx->ev_apply_done[slot], s2));
@@ -1185,7 +1252,7 @@ static int settle(btlbf_ctx* ctx)
 	if (!ctx->acc.f)
 		return BTLBF_OK;
 	ctx->acc.f = nullptr;
-	int rc = apply_pass(ctx, ctx->acc.P, ctx->acc.slot, ctx->active);
+	int rc = apply_pass(ctx, ctx->acc.P, ctx->acc.slot, ctx->active, ctx->acc.windows);
 	if (rc != BTLBF_OK)
 		ctx->settle_error = rc;
 	return rc;
@@ -1259,7 +1326,7 @@ static int binned_insert(btlbf_filter* f, SeqParams P, cudaStream_t s)
 			TRY(settle(ctx));
 		return BTLBF_OK;
 	}
-	return apply_pass(ctx, P, slot, s);
+	return apply_pass(ctx, P, slot, s, P.n_windows);
 }
 
 // Partitioned query: bin (offset, window) pairs by filter partition, test them while the partition is

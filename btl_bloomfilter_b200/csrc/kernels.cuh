@@ -112,6 +112,23 @@ bool bin_query_supported(const SeqParams& P, uint32_t n_bins);
 bool bin_sort_eligible(const SeqParams& P, uint32_t n_bins); // the sort-bin kernel (sort_bin.cuh) serves this shape
 uint32_t bin_sort_tile();                                    // windows per CTA pass of the sort-bin kernel
 
+// Two-level pass 2 of the partitioned build (apply2.cu): the items of every partition are split once more by
+// slice (refine), then each slice is ORed in shared memory and written back once.
+struct Apply2Params
+{
+	const uint32_t* items;  // level 1: sub-bucket (partition p, writer w) at items[(p*writers + w)*cap ...]
+	const uint32_t* counts; // level 1: appended per sub-bucket (may exceed cap)
+	uint32_t n_bins, writers, cap, bin_shift;
+	uint32_t* items2;       // level 2: bucket (partition p, slice s, writer j) at items2[((p*n_sub + s)*writers2 + j)*cap2 ...]
+	uint32_t* counts2;
+	uint32_t sub_shift, n_sub, writers2, cap2; // log2(bits per slice), slices per partition, refine CTAs per partition
+	uint32_t* filter;
+	uint64_t m;             // filter bits
+	uint64_t alloc_words;   // 32-bit words of the filter's allocation (a multiple of 4)
+};
+bool apply2_geometry(uint32_t bin_shift, uint32_t* sub_shift, uint32_t* n_sub);
+cudaError_t launch_apply2(const Apply2Params& A, cudaStream_t stream);
+
 // residual rounds of the ordered updates on the compacted list of deferred windows
 struct ListParams
 {

@@ -129,6 +129,15 @@ class Context:
         check(self.L.btlbf_ctx_aux_stream(self.handle, C.byref(p)))
         return p.value
 
+    def counter(self, name):
+        n = C.c_uint64()
+        check(self.L.btlbf_ctx_counter(self.handle, name.encode(), C.byref(n)))
+        return n.value
+
+    @property
+    def two_level_passes(self):
+        return self.counter("two_level_passes")
+
     @property
     def launch_count(self):
         n = C.c_uint64()

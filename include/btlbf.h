@@ -88,6 +88,8 @@ int btlbf_ctx_flush(btlbf_ctx *ctx);
 int btlbf_ctx_aux_stream(btlbf_ctx *ctx, void **cuda_stream); /* the background cudaStream_t (for timing) */
 /* number of kernels this context has launched so far (for accounting / tests) */
 int btlbf_ctx_launch_count(btlbf_ctx *ctx, uint64_t *count);
+/* diagnostics: "launches", "binned_launches" (passes 1 of the partitioned paths), "two_level_passes" */
+int btlbf_ctx_counter(btlbf_ctx *ctx, const char *name, uint64_t *value);
 /* tuning / debugging knobs: "force_generic" (1: byte-LUT hashing path for every tile),
  * "query_mode" (0: all probes in flight, 1: early-exit probing), "chunk_bases" (windows per
  * pipeline stage of the host-buffer calls), "cbf_batch" (windows per batch of the ordered updates),

@@ -606,3 +606,22 @@ def test_clear_and_upload_drop_parked_kmers(oracle):
     filt = other.copy()
     assert f.insert((b, off)) == oracle.bf_insert_seqs(filt, bits, h, k, b, off)
     assert np.array_equal(f.bytes(), filt)
+
+
+@pytest.mark.parametrize("shift", [8, 20, 24])
+def test_two_level_pass2_equals_oracle(oracle, golden, shift):
+    """pass 2 of the partitioned build through apply2.cu (refine by slice, OR in shared memory), forced for
+    small accumulations; includes a skewed input whose level-2 buckets overflow into direct atomics"""
+    from _backends import GpuBackend
+    be = GpuBackend(bin_shift=shift, bin_two_level=1, bin_two_level_min=0)
+    S.check_golden_bf(be, golden)
+    S.check_random_bf(be, oracle, 25, 4, 1 << 26, seed=3, n_seqs=60, max_len=4000)
+    S.check_random_bf(be, oracle, 32, 6, 32 * 1237 * 64 + 8, seed=4)
+    S.check_cfg1(be, oracle, golden)
+    assert be.ctx.two_level_passes > 0
+    f = be.filter(0, 1 << 22, 4, 11)
+    seqs = ["A" * 30000, "ACGT" * 5000, "ACGTTGCA" * 3000]
+    b, off = O.as_batch(seqs)
+    filt = np.zeros((1 << 22) // 8, np.uint8)
+    assert f.insert(seqs) == oracle.bf_insert_seqs(filt, 1 << 22, 4, 11, b, off)
+    assert np.array_equal(f.bytes(), filt)
