@@ -907,10 +907,12 @@ BTL_HD bool tile_phase_c_commit_any(const SeqParams& P, const TileSmem& sm, uint
 template<int OP, bool SPACED, bool POW2>
 BTL_HD ThreadOut tile_phase_c(const SeqParams& P, const TileSmem& sm, uint64_t t0, int tid)
 {
-	if ((OP == OP_CBF_COMMIT || OP == OP_BFCHK_COMMIT) && !SPACED && !P.ungrouped_commit) {
-		ThreadOut grouped;
-		if (tile_phase_c_commit_any<(OP == OP_BFCHK_COMMIT ? OP_BFCHK_COMMIT : OP_CBF_COMMIT), POW2>(P, sm, t0, tid, grouped))
-			return grouped;
+	if constexpr ((OP == OP_CBF_COMMIT || OP == OP_BFCHK_COMMIT) && !SPACED) { // (instantiated for these two only)
+		if (!P.ungrouped_commit) {
+			ThreadOut grouped;
+			if (tile_phase_c_commit_any<OP, POW2>(P, sm, t0, tid, grouped))
+				return grouped;
+		}
 	}
 	ThreadOut out;
 	out.validw = 0;
