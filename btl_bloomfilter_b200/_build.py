@@ -34,13 +34,18 @@ def build_library(force=False, verbose=False):
     nvcc = _nvcc()
     objs = []
     procs = []
+    newest_header = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        objs.append(obj)
+        # objects are reused when neither their source nor any header is newer (force rebuilds everything)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(
+                newest_header, os.path.getmtime(os.path.join(CSRC, src))):
+            continue
         cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
-        objs.append(obj)
     for src, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0:

@@ -19,7 +19,8 @@ for kv in sys.argv[1:]:
     k_, v_ = kv.split("=")
     ctx.set_option(k_, int(v_))
 CH, RL = 64 << 20, 150
-NR = CH // RL
+QF = int(os.environ.get("QUERY_FACTOR", "4"))  # read bases per query batch, in units of CH
+NR = CH * QF // RL
 RB = NR * RL
 roff = torch.arange(0, RB + 1, RL, dtype=torch.int64, device=dev)
 goff = torch.tensor([0, CH], dtype=torch.int64, device=dev)
@@ -39,26 +40,28 @@ def timed(fn, reps):
     return a.elapsed_time(b) / reps
 
 
-def run(name, make, k, h, reps=3, insert_windows=CH, bytes_ins=None, bytes_qry=None):
+def run(name, make, k, h, reps=6, insert_windows=CH, bytes_ins=None, bytes_qry=None):
     f = make()
     g = [torch.empty(CH + 64, dtype=torch.uint8, device=dev) for _ in range(reps + 1)]
-    r = [torch.empty(RB + 64, dtype=torch.uint8, device=dev) for _ in range(reps + 1)]
+    r = [torch.empty(RB + 64, dtype=torch.uint8, device=dev) for _ in range(3)]
     for i in range(reps + 1):
         ctx.synth_genome_device(g[i].data_ptr(), i * CH, CH, 42)
+    for i in range(3):
         ctx.synth_reads_device(r[i].data_ptr(), 0, NR, RL, i * CH, CH, 42, 7 + i)
     st = torch.zeros(4, dtype=torch.int64, device=dev)
     iw = insert_windows
     io = torch.tensor([0, iw], dtype=torch.int64, device=dev)
     ms_i = timed(lambda i: f.insertSeqsDevice(g[i].data_ptr(), iw, io.data_ptr(), 1, st.data_ptr()), reps)
     st.zero_()
-    ms_q = timed(lambda i: f.containsSeqsDevice(r[i].data_ptr(), RB, roff.data_ptr(), NR, hits.data_ptr(), 0,
-                                                st[2:].data_ptr()), reps)
+    ms_q = timed(lambda i: f.containsSeqsDevice(r[i % 3].data_ptr(), RB, roff.data_ptr(), NR, hits.data_ptr(), 0,
+                                                st[2:].data_ptr()), 2)
     kq = NR * (RL - k + 1)
     ki = iw - k + 1
     s = st.cpu().numpy()
     out = {"config": name, "k": k, "hashes": h, "insert_windows": iw, "insert_ms": ms_i,
            "insert_gkmers_s": ki / ms_i / 1e6, "query_kmers": kq, "query_ms": ms_q, "query_gkmers_s": kq / ms_q / 1e6,
-           "query_hit_fraction": float(s[3]) / max(1.0, float(s[2])), "options": sys.argv[1:]}
+           "query_hit_fraction": float(s[3]) / max(1.0, float(s[2])), "options": sys.argv[1:],
+           "insert_batches_per_timing": reps, "query_bases_per_batch": RB}
     if bytes_ins:
         out["insert_frac_of_6546GBs"] = out["insert_gkmers_s"] * bytes_ins / 6546.6
     if bytes_qry:
