@@ -1605,7 +1605,12 @@ static int host_pipeline(btlbf_ctx* ctx, btlbf_filter* f, const HashCfg* hash_on
 	uint64_t chunk = (uint64_t)ctx->chunk_bases;
 	// the partitioned query streams the whole filter once per chunk: larger chunks for it
 	if (op == PUB_CONTAINS && f && f->kind == BTLBF_BLOOM && f->bytes >= ((uint64_t)96 << 20))
-		chunk *= (uint64_t)ctx->query_chunk_factor;
+		chunk *= (uint64_t)(async || ctx->query_chunk_factor < 2 ? ctx->query_chunk_factor : ctx->query_chunk_factor / 2);
+	// (a blocking call has nothing else in flight: two chunks at least, so that its own copies and kernels overlap)
+	// ... while pass 1 of the partitioned build appends to the same sub-buckets whatever the chunk size: small
+	// chunks let the H2D copy of one overlap the kernel of the previous one inside a single blocking call
+	if (op == PUB_INSERT && f && f->kind == BTLBF_BLOOM && f->bytes >= ((uint64_t)96 << 20) && chunk > ((uint64_t)16 << 20))
+		chunk = (chunk / 4 + kTile - 1) / kTile * kTile;
 	if (op == PUB_HASH) { // keep the per-chunk hash buffer around 256 MiB
 		uint64_t lim = ((uint64_t)256 << 20) / ((uint64_t)H * 9);
 		lim = lim / kTile * kTile;
