@@ -67,12 +67,14 @@ __device__ __forceinline__ void expand_hashes(const SeqParams& P, const TileSmem
 	} else {
 		const uint64_t* TF = sm.sttab;
 		const uint64_t* TR = sm.sttab + (size_t)P.k * 8;
+		const bool packed = !P.force_generic && sm.scratch[1] == 0; // see for_each_hash (tile_core.cuh)
 #pragma unroll
 		for (int j = 0; j < H; j++) {
 			uint64_t fs = F, rs = RC;
 			for (uint32_t t = P.st_dc_off[j]; t < P.st_dc_off[j + 1]; t++) {
 				uint32_t pos = P.st_dc[t];
-				uint32_t c = sm.tile[w + pos] & 7u;
+				uint32_t q = w + pos;
+				uint32_t c = packed ? (sm.codes[q >> 4] >> (2 * (q & 15))) & 3u : sm.tile[q] & 7u;
 				fs ^= TF[pos * 8 + c];
 				rs ^= TR[pos * 8 + c];
 			}

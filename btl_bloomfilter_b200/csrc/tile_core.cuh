@@ -293,11 +293,16 @@ BTL_HD void for_each_hash(const SeqParams& P, const TileSmem& sm, uint32_t w, ui
 	} else {
 		const uint64_t* TF = sm.sttab;
 		const uint64_t* TR = sm.sttab + (size_t)P.k * 8;
+		// The class of a don't-care base: from the 2-bit plane when the tile has no exotic bytes (lanes are 32
+		// bases apart: 2-way bank conflicts there against 8-way on the byte plane -- these reads are what bounds
+		// the spaced-seed kernels), else from the byte plane (bit 2 = self-complementary raw byte).
+		const bool packed = !P.force_generic && sm.scratch[1] == 0;
 		for (uint32_t j = 0; j < P.n_seeds; j++) {
 			uint64_t fs = F, rs = RC;
 			for (uint32_t t = P.st_dc_off[j]; t < P.st_dc_off[j + 1]; t++) {
 				uint32_t pos = P.st_dc[t];
-				uint32_t c = sm.tile[w + pos] & 7u;
+				uint32_t q = w + pos;
+				uint32_t c = packed ? (sm.codes[q >> 4] >> (2 * (q & 15))) & 3u : sm.tile[q] & 7u;
 				fs ^= TF[pos * 8 + c];
 				rs ^= TR[pos * 8 + c];
 			}
