@@ -162,6 +162,30 @@ def cpu_reference_run(n_steps, warmup, sample_bases, threads=0, verbose=False):
             "ms_per_step": tot_t / n_steps * 1e3, "kmers_per_step": tot_k / n_steps}
 
 
+def bind_to_gpu_numa_node(torch, index):
+    """N > 1: run this rank (and first-touch its pinned buffers) on the CPUs next to its GPU, so that eight ranks do
+    not pull their host buffers across the socket interconnect.  Best effort; returns what it did."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"pci": bdf, "cpus": len(cpus)}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:80]}
+    return None
+
+
 # ---------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -207,6 +231,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = B.Context(local_rank)
@@ -491,6 +516,8 @@ def main():
                             "steps": e2e["steps_sync"], "api": "btlbf_insert_seqs + btlbf_contains_seqs (blocking)"}
     if merge:
         line["merge"] = merge
+    if numa:
+        line["config"]["host_numa_binding"] = numa
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_reference_run(2, 1, args.cpu_sample)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "insert_gkmers_s",
