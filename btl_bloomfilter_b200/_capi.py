@@ -56,6 +56,7 @@ SIGNATURES = {
     "btlbf_seqfile_open": [C.c_char_p, u32, C.c_int, C.c_int, C.POINTER(vp)],
     "btlbf_seqfile_next": [vp, vp, u64, u64p, u64, u64p, u64p, u64p, C.POINTER(C.c_int)],
     "btlbf_seqfile_close": [vp],
+    "btlbf_ingest_release": [],
     "btlbf_filter_ctx": [vp, C.POINTER(vp)],
     "btlbf_insert_seqs": [vp, vp, u64p, u64, u64p],
     "btlbf_contains_seqs": [vp, vp, u64p, u64, vp, vp, u64p, u64p],

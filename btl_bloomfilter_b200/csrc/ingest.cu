@@ -16,6 +16,7 @@
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <fcntl.h>
@@ -377,10 +378,23 @@ namespace {
 struct Batch
 {
 	char* bases = nullptr; // pinned
-	std::vector<uint64_t> offsets;
+	uint64_t* offsets = nullptr;
 	uint64_t n_bases = 0, n_seqs = 0;
 	uint64_t* counts = nullptr; // pinned {n_kmers, n_hits}
 };
+
+// Pinned staging buffers are expensive to create (~0.4 s per GB): they are kept for the life of the process and
+// handed out to one file call at a time (btlbf_ingest_release frees them).
+struct PinnedCache
+{
+	std::mutex mu;
+	std::vector<char*> bases; // each `cap` bytes
+	std::vector<uint64_t*> offsets; // each kIngestBatch / 16 + 1 entries
+	uint64_t* counts = nullptr;
+	size_t counts_slots = 0;
+	bool busy = false;
+} g_pinned;
+constexpr uint64_t kIngestBatch = (uint64_t)32 << 20; // bases per batch
 
 struct Pool
 {
@@ -412,29 +426,48 @@ int file_op(btlbf_filter* f, const char* path, bool query, int threads, uint64_t
 		return failf(BTLBF_ERR_ARG, "cannot open '%s'", path);
 	if ((uint64_t)sb.st_size < ((uint64_t)threads << 20))
 		threads = 1;
-	const uint64_t cap = (uint64_t)32 << 20; // bases per batch
+	const uint64_t cap = kIngestBatch;
 	const uint64_t cap_seqs = cap / 16;
 	const int n_batches = threads + 6;       // being filled + in flight (kTickets) + slack
 	std::vector<Batch> store((size_t)n_batches);
 	Pool pool;
-	uint64_t* counts_block = nullptr;
+	{
+		std::unique_lock<std::mutex> lk(g_pinned.mu);
+		if (g_pinned.busy)
+			return failf(BTLBF_ERR_STATE, "another file call is in progress in this process");
+		if (g_pinned.counts_slots < (size_t)n_batches) {
+			if (g_pinned.counts)
+				cudaFreeHost(g_pinned.counts);
+			g_pinned.counts = nullptr;
+			g_pinned.counts_slots = 0;
+			if (cudaHostAlloc((void**)&g_pinned.counts, (size_t)n_batches * 16, cudaHostAllocDefault) != cudaSuccess)
+				return failf(BTLBF_ERR_NOMEM, "pinned allocation failed");
+			g_pinned.counts_slots = (size_t)n_batches;
+		}
+		while (g_pinned.bases.size() < (size_t)n_batches) {
+			char* b = nullptr;
+			if (cudaHostAlloc((void**)&b, cap, cudaHostAllocDefault) != cudaSuccess)
+				return failf(BTLBF_ERR_NOMEM, "pinned allocation of %llu bytes failed", (unsigned long long)cap);
+			g_pinned.bases.push_back(b);
+		}
+		while (g_pinned.offsets.size() < (size_t)n_batches) {
+			uint64_t* o = (uint64_t*)malloc((cap_seqs + 1) * sizeof(uint64_t));
+			if (!o)
+				return failf(BTLBF_ERR_NOMEM, "out of host memory");
+			g_pinned.offsets.push_back(o);
+		}
+		g_pinned.busy = true;
+	}
 	auto cleanup = [&]() {
-		for (Batch& b : store)
-			if (b.bases)
-				cudaFreeHost(b.bases);
-		if (counts_block)
-			cudaFreeHost(counts_block);
+		std::unique_lock<std::mutex> lk(g_pinned.mu);
+		g_pinned.busy = false;
 	};
-	if (cudaHostAlloc((void**)&counts_block, (size_t)n_batches * 16, cudaHostAllocDefault) != cudaSuccess)
-		return failf(BTLBF_ERR_NOMEM, "pinned allocation failed");
 	for (int i = 0; i < n_batches; i++) {
 		Batch& b = store[(size_t)i];
-		if (cudaHostAlloc((void**)&b.bases, cap, cudaHostAllocDefault) != cudaSuccess) {
-			cleanup();
-			return failf(BTLBF_ERR_NOMEM, "pinned allocation of %llu bytes failed", (unsigned long long)cap);
-		}
-		b.offsets.resize(cap_seqs + 1);
-		b.counts = counts_block + 2 * i;
+		b.bases = g_pinned.bases[(size_t)i];
+		b.offsets = g_pinned.offsets[(size_t)i];
+		b.counts = g_pinned.counts + 2 * i;
+		b.counts[0] = b.counts[1] = 0;
 		pool.free_list.push_back(&b);
 	}
 	std::vector<btlbf_seqfile*> readers((size_t)threads, nullptr);
@@ -463,7 +496,7 @@ int file_op(btlbf_filter* f, const char* path, bool query, int threads, uint64_t
 				pool.free_list.pop_front();
 			}
 			uint64_t nrec = 0;
-			int e = btlbf_seqfile_next(r, b->bases, cap, b->offsets.data(), cap_seqs, &b->n_bases, &b->n_seqs, &nrec, &done);
+			int e = btlbf_seqfile_next(r, b->bases, cap, b->offsets, cap_seqs, &b->n_bases, &b->n_seqs, &nrec, &done);
 			records[(size_t)t] += nrec;
 			std::unique_lock<std::mutex> lk(pool.mu);
 			if (e != BTLBF_OK) {
@@ -513,9 +546,9 @@ int file_op(btlbf_filter* f, const char* path, bool query, int threads, uint64_t
 			pool.ready.pop_front();
 		}
 		if (query)
-			err = btlbf_contains_seqs_async(f, b->bases, b->offsets.data(), b->n_seqs, nullptr, nullptr, b->counts);
+			err = btlbf_contains_seqs_async(f, b->bases, b->offsets, b->n_seqs, nullptr, nullptr, b->counts);
 		else
-			err = btlbf_insert_seqs_async(f, b->bases, b->offsets.data(), b->n_seqs, b->counts);
+			err = btlbf_insert_seqs_async(f, b->bases, b->offsets, b->n_seqs, b->counts);
 		if (err != BTLBF_OK) {
 			std::unique_lock<std::mutex> lk(pool.mu);
 			pool.error = err;
@@ -561,6 +594,24 @@ int file_op(btlbf_filter* f, const char* path, bool query, int threads, uint64_t
 }
 
 } // namespace
+
+extern "C" int btlbf_ingest_release(void)
+{
+	std::unique_lock<std::mutex> lk(g_pinned.mu);
+	if (g_pinned.busy)
+		return failf(BTLBF_ERR_STATE, "a file call is in progress");
+	for (char* b : g_pinned.bases)
+		cudaFreeHost(b);
+	g_pinned.bases.clear();
+	for (uint64_t* o : g_pinned.offsets)
+		free(o);
+	g_pinned.offsets.clear();
+	if (g_pinned.counts)
+		cudaFreeHost(g_pinned.counts);
+	g_pinned.counts = nullptr;
+	g_pinned.counts_slots = 0;
+	return BTLBF_OK;
+}
 
 extern "C" int btlbf_insert_file(btlbf_filter* f, const char* path, int threads, uint64_t* n_seqs, uint64_t* n_kmers)
 {

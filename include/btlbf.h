@@ -190,6 +190,9 @@ int btlbf_increment_all_seqs(btlbf_filter *f, const char *bases, const uint64_t 
 int btlbf_insert_file(btlbf_filter *f, const char *path, int threads, uint64_t *n_seqs, uint64_t *n_kmers);
 int btlbf_query_file(btlbf_filter *f, const char *path, int threads, uint64_t *n_seqs, uint64_t *n_kmers,
                      uint64_t *n_hits);
+/* The file calls keep their pinned staging buffers (32 MiB each, parser threads + 6 of them) for the life of
+ * the process; btlbf_ingest_release frees them. */
+int btlbf_ingest_release(void);
 /* The parser alone (no GPU involved): region `region` of `n_regions` equal cuts of the file, aligned to
  * line (FASTA) / record (FASTQ) starts.  btlbf_seqfile_next fills one flat batch: bases[0..*n_bases),
  * offsets[0..*n_seqs] (pieces; a piece that continues a cut sequence starts with its previous `overlap`
