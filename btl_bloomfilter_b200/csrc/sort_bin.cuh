@@ -91,7 +91,7 @@ BTL_HD size_t sort_arrays_bytes(uint32_t n_bins, int h)
 	const size_t nbr = (n_bins + 1u) & ~1u;
 	const size_t cap = (size_t)kSortThreads * sort_round_windows(h) * h;
 	size_t s = nbr * 8;                 // gdelta
-	s += cap * 8;                       // sorted_off, sorted_aux
+	s += cap * 8;                       // sorted: (offset, partition [| window]) pairs
 	s += nbr * 4 * 3 + 32 * 4;          // hist (+ 32 per-lane dump slots for invalid windows), base, cursor
 	s += (kSortThreads / 32 + 2) * 4;   // warp sums, total, overflow flag
 	return (s + 15) / 16 * 16;
@@ -119,8 +119,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) bin_kernel_sort(const __grid_
 
 	uint8_t* p = smem_raw;
 	uint64_t* const gdelta = reinterpret_cast<uint64_t*>(p);     p += (size_t)nbr * 8;
-	uint32_t* const sorted_off = reinterpret_cast<uint32_t*>(p); p += (size_t)CAPACITY * 4;
-	uint32_t* const sorted_aux = reinterpret_cast<uint32_t*>(p); p += (size_t)CAPACITY * 4;
+	uint2* const sorted = reinterpret_cast<uint2*>(p);           p += (size_t)CAPACITY * 8; // gdelta keeps this 8-byte aligned
 	uint32_t* const hist = reinterpret_cast<uint32_t*>(p);       p += (size_t)(nbr + 32) * 4;
 	uint32_t* const base = reinterpret_cast<uint32_t*>(p);       p += (size_t)nbr * 4;
 	uint32_t* const cursor = reinterpret_cast<uint32_t*>(p);     p += (size_t)nbr * 4;
@@ -227,8 +226,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) bin_kernel_sort(const __grid_
 					const uint32_t part = pr >> 16;
 					if (part < nbr) {
 						const uint32_t pos = base[part] + (pr & 0xffffu);
-						sorted_off[pos] = it_off[ws * H + i];
-						sorted_aux[pos] = QUERY ? part | ((r.p0 + round * W + ws) << 12) : part;
+						sorted[pos] = make_uint2(it_off[ws * H + i], QUERY ? part | ((r.p0 + round * W + ws) << 12) : part);
 					}
 				}
 			}
@@ -237,7 +235,8 @@ __global__ void __launch_bounds__(kSortThreads, 2) bin_kernel_sort(const __grid_
 			total = wsum[NW];
 			const bool overflow = wsum[NW + 1] != 0;
 			for (uint32_t pos = tid; pos < total; pos += kSortThreads) {
-				const uint32_t off = sorted_off[pos], aux = sorted_aux[pos];
+				const uint2 item = sorted[pos];
+				const uint32_t off = item.x, aux = item.y;
 				const uint32_t part = QUERY ? aux & 0xfffu : aux;
 				const uint64_t idx = gdelta[part] + pos;
 				const uint32_t wid = (uint32_t)t0 + (aux >> 12);
