@@ -364,7 +364,7 @@ bool bin_sort_eligible(const SeqParams& P, uint32_t n_bins)
 		return false;
 	if (P.n_seeds && P.h2 != 1)
 		return false;
-	return sort_smem_bytes(P.k, P.n_seeds != 0, n_bins, (int)P.h) <= 110 * 1024;
+	return sort_smem_bytes(P.k, P.n_seeds != 0, n_bins, (int)P.h) <= (size_t)(220 / kSortCtasPerSm) * 1024;
 }
 
 static cudaError_t bin_select(const SeqParams& P, uint32_t n_bins, bool query, BinKernel* K, int* occ)

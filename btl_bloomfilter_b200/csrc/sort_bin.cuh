@@ -3,7 +3,7 @@
 // Serves h <= kMaxSortHashes hashes per k-mer and <= kMaxSortBins filter partitions (everything the
 // BASELINE configs use); other shapes fall back to bin_kernel_warp / bin_kernel_cta in kernels.cu.
 //
-// Persistent CTAs of kSortThreads threads; every CTA is the only writer of its own sub-bucket of each
+// Persistent CTAs of kSortThreads threads (256, four per SM: measured against 192, 512 and 1024); every CTA is the only writer of its own sub-bucket of each
 // filter partition.  A thread rolls kWPT consecutive windows (same staging and rolling as seq_kernel);
 // after every W of them the CTA counting-sorts the kSortThreads*W*h items it holds in registers:
 //   A   item -> (partition, offset); its rank inside the partition is the return value of a
@@ -23,9 +23,13 @@
 
 namespace btl {
 
-constexpr int kSortThreads = 512;
-constexpr int kSortTile = kSortThreads * kWPT; // windows per CTA pass (16384)
-constexpr uint32_t kMaxSortBins = 1024;        // the scan handles two partitions per thread
+#ifndef BTL_SORT_THREADS
+#define BTL_SORT_THREADS 256
+#endif
+constexpr int kSortThreads = BTL_SORT_THREADS;
+constexpr int kSortCtasPerSm = 1024 / kSortThreads;  // 64 registers per thread: 1024 threads fill an SM's register file
+constexpr int kSortTile = kSortThreads * kWPT;       // windows per CTA pass (8192)
+constexpr uint32_t kMaxSortBins = 2 * kSortThreads;  // the scan handles two partitions per thread
 constexpr int kMaxSortHashes = 8;
 
 BTL_HD constexpr int sort_round_windows(int h)
@@ -104,7 +108,7 @@ inline size_t sort_smem_bytes(uint32_t k, bool spaced, uint32_t n_bins, int h)
 
 #if defined(__CUDACC__)
 template<int H, bool SPACED, bool POW2, bool QUERY>
-__global__ void __launch_bounds__(kSortThreads, 2) bin_kernel_sort(const __grid_constant__ SeqParams P)
+__global__ void __launch_bounds__(kSortThreads, kSortCtasPerSm) bin_kernel_sort(const __grid_constant__ SeqParams P)
 {
 	constexpr int W = sort_round_windows(H);
 	constexpr int ITEMS = W * H;
