@@ -90,13 +90,23 @@ int btlbf_ctx_aux_stream(btlbf_ctx *ctx, void **cuda_stream); /* the background 
 int btlbf_ctx_launch_count(btlbf_ctx *ctx, uint64_t *count);
 /* diagnostics: "launches", "binned_launches" (passes 1 of the partitioned paths), "two_level_passes" */
 int btlbf_ctx_counter(btlbf_ctx *ctx, const char *name, uint64_t *value);
-/* tuning / debugging knobs: "force_generic" (1: byte-LUT hashing path for every tile),
- * "query_mode" (0: all probes in flight, 1: early-exit probing), "chunk_bases" (windows per
- * pipeline stage of the host-buffer calls), "cbf_batch" (windows per batch of the ordered updates),
- * "resv_log2", "list_log2", "drain_threshold" (sizes of the ordered-update reservation tables),
- * "bin_mode" / "bin_query_mode" (partitioned BloomFilter build / query: 0 auto, 1 always, -1 never),
- * "bin_part_log2" (bits per
- * L2-resident filter partition), "bin_slack_pct", "l2_fetch_granularity" */
+/* Tuning / debugging knobs (none of them changes a result):
+ *   hashing        "force_generic" (1: byte-class hashing path for every tile)
+ *   host pipeline  "chunk_bases" (windows per pipeline stage), "query_chunk_factor" (partitioned queries run in
+ *                  chunks of this many chunk_bases)
+ *   partitioned    "bin_mode" / "bin_query_mode" (build / query: 0 auto, 1 always, -1 never), "bin_part_log2" (bits
+ *   BloomFilter    per L2-resident partition), "bin_max_parts", "bin_slack_pct", "bin_accum_bytes" (sub-bucket storage
+ *   paths          one accumulation of builds may use), "bin_kernel" (1: general-shape pass-1 kernels only),
+ *                  "bin_two_level" / "bin_two_level_min" (optional two-level pass 2), "overlap" (pass 2 on the
+ *                  background stream)
+ *   query          "query_mode" (direct kernel: 0 all probes in flight, 1 early exit), "query_adaptive",
+ *                  "query_adaptive_pct", "query_adaptive_min_tiles" (device-side choice between the partitioned and the
+ *                  early-exit query from a sampled hit fraction)
+ *   ordered        "cbf_batch" (windows per batch), "resv_log2", "list_log2", "drain_threshold", "ordered_coop"
+ *   updates        (0: host-driven residual rounds), "ungrouped_commit"
+ *   multi-GPU      "peer_unroll", "peer_grid", "peer_mode" (fused merge kernel shape; peer_mode 1 / 2 are
+ *                  measurement-only half merges)
+ *   device         "l2_fetch_granularity" */
 int btlbf_ctx_set_option(btlbf_ctx *ctx, const char *key, int64_t value);
 
 /* ---- filters ---- */
