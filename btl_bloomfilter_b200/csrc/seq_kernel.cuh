@@ -103,7 +103,14 @@ inline cudaError_t launch_op(const SeqParams& P, cudaStream_t stream)
 	return pow2 ? launch_one<OP, false, true>(P, stream) : launch_one<OP, false, false>(P, stream);
 }
 
+cudaError_t launch_seq_bloom(SeqOp op, const SeqParams& P, cudaStream_t stream); // seq_ops_bloom.cu
 cudaError_t launch_seq_cbf_commit(const SeqParams& P, cudaStream_t stream);
 cudaError_t launch_seq_bfchk_commit(const SeqParams& P, cudaStream_t stream);
+
+// general-shape pass-1 kernels of the partitioned paths (bin_legacy.cu)
+constexpr uint32_t kMaxWarpBins = 256;
+const void* bin_warp_kernel(bool query, bool spaced, bool pow2);
+const void* bin_cta_kernel(bool spaced, bool pow2);
+size_t bin_warp_smem_bytes(uint32_t k, bool spaced, uint32_t n_bins);
 
 } // namespace btl
