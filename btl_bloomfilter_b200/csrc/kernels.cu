@@ -19,7 +19,10 @@ namespace btl {
 // Blocks are ordered partition-major, so at any moment the whole GPU is ORing into one or two
 // 2^bin_shift-bit regions of the filter, which stay resident in L2 (one HBM read and one write-back per
 // line instead of one 128-byte fetch per random bit).  One warp drains one sub-bucket at a time.
-constexpr int kApplyThreads = 256;
+#ifndef BTL_APPLY_THREADS
+#define BTL_APPLY_THREADS 256
+#endif
+constexpr int kApplyThreads = BTL_APPLY_THREADS;
 __global__ void __launch_bounds__(kApplyThreads) apply_bins_kernel(const __grid_constant__ SeqParams P, uint32_t blocks_per_part)
 {
 	const uint32_t part = blockIdx.x / blocks_per_part, sub = blockIdx.x % blocks_per_part;
