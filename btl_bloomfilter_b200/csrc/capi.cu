@@ -95,7 +95,7 @@ struct btlbf_ctx
 	int64_t force_generic = 0, query_mode = 0, ungrouped_commit = 0;
 	int64_t chunk_bases = (int64_t)64 << 20; // windows per pipeline stage of the host-buffer calls
 	int64_t cbf_batch = (int64_t)4 << 20;    // windows per batch of the ordered (exact) updates
-	int64_t resv_log2 = 29, list_log2 = 24;  // reservation sketch bits per table / residual-round table entries
+	int64_t resv_log2 = 28, list_log2 = 24;  // reservation sketch bits per table (2 x 32 MiB: stays in L2) / residual-round table entries
 	int64_t drain_threshold = 4096;
 	int64_t ordered_coop = 1; // residual rounds of the ordered updates: 1 cooperative grid kernel, 0 host-driven rounds
 	int64_t bin_mode = 0;       // partitioned BloomFilter build: 0 auto, 1 always, -1 never
@@ -1291,7 +1291,7 @@ static int binned_insert(btlbf_filter* f, SeqParams P, cudaStream_t s)
 			if (e != cudaSuccess)
 				return fail(BTLBF_ERR_CUDA, "partitioned build (pass 1) launch failed: %s", cudaGetErrorString(e));
 			ctx->acc.windows += P.n_windows;
-			ctx->acc.tiles += (P.n_windows + bin_sort_tile() - 1) / bin_sort_tile();
+			ctx->acc.tiles += (P.n_windows + bin_sort_tile(P, P.n_bins) - 1) / bin_sort_tile(P, P.n_bins);
 			ctx->launches++;
 			ctx->binned_launches++;
 			return BTLBF_OK;
@@ -1319,7 +1319,7 @@ static int binned_insert(btlbf_filter* f, SeqParams P, cudaStream_t s)
 		ctx->acc.f = f;
 		ctx->acc.P = P;
 		ctx->acc.windows = P.n_windows;
-		ctx->acc.tiles = (P.n_windows + bin_sort_tile() - 1) / bin_sort_tile();
+		ctx->acc.tiles = (P.n_windows + bin_sort_tile(P, P.n_bins) - 1) / bin_sort_tile(P, P.n_bins);
 		ctx->acc.capacity = target;
 		ctx->acc.slot = slot;
 		if (ctx->acc.windows >= ctx->acc.capacity)

@@ -150,24 +150,43 @@ struct BinKernel
 	uint32_t tile; // windows per CTA pass
 };
 
+// CTA size of the sort-bin kernel for this shape: 256 threads when a round (threads * W * h items) still gives
+// every partition a run of ~14 items, else 512; 0 when the shape is not served at all.
+static int sort_threads_for(const SeqParams& P, uint32_t n_bins)
+{
+	if (P.bin_legacy || P.h > (uint32_t)kMaxSortHashes || (P.n_seeds && P.h2 != 1))
+		return 0;
+	const bool spaced = P.n_seeds != 0;
+	for (int threads : { 256, 512 }) {
+		if (n_bins > sort_max_bins(threads))
+			continue;
+		if (sort_smem_bytes(P.k, spaced, n_bins, (int)P.h, threads) > (size_t)(220 / sort_ctas_per_sm(threads)) * 1024)
+			continue;
+		const uint64_t round_items = (uint64_t)threads * sort_round_windows((int)P.h) * P.h;
+		if (threads == 256 && round_items < (uint64_t)14 * n_bins)
+			continue;
+		return threads;
+	}
+	return 0;
+}
+
 bool bin_sort_eligible(const SeqParams& P, uint32_t n_bins)
 {
-	if (P.bin_legacy || P.h > (uint32_t)kMaxSortHashes || n_bins > kMaxSortBins)
-		return false;
-	if (P.n_seeds && P.h2 != 1)
-		return false;
-	return sort_smem_bytes(P.k, P.n_seeds != 0, n_bins, (int)P.h) <= (size_t)(220 / kSortCtasPerSm) * 1024;
+	return sort_threads_for(P, n_bins) != 0;
 }
 
 static cudaError_t bin_select(const SeqParams& P, uint32_t n_bins, bool query, BinKernel* K, int* occ)
 {
 	const bool spaced = P.n_seeds != 0, pow2 = P.fm.pow2 != 0;
-	if (bin_sort_eligible(P, n_bins)) {
+	if (const int threads = sort_threads_for(P, n_bins)) {
 		K->mode = BIN_SORT;
-		K->threads = kSortThreads;
-		K->tile = kSortTile;
-		K->smem = sort_smem_bytes(P.k, spaced, n_bins, (int)P.h);
-		K->fn = query ? bin_sort_kernel_query((int)P.h, spaced, pow2) : bin_sort_kernel_build((int)P.h, spaced, pow2);
+		K->threads = threads;
+		K->tile = sort_tile(threads);
+		K->smem = sort_smem_bytes(P.k, spaced, n_bins, (int)P.h, threads);
+		if (threads == 256)
+			K->fn = query ? bin_sort_kernel_query_256((int)P.h, spaced, pow2) : bin_sort_kernel_build_256((int)P.h, spaced, pow2);
+		else
+			K->fn = query ? bin_sort_kernel_query_512((int)P.h, spaced, pow2) : bin_sort_kernel_build_512((int)P.h, spaced, pow2);
 	} else if (n_bins <= kMaxWarpBins) {
 		K->mode = BIN_WARP;
 		K->threads = kTPB;
@@ -194,9 +213,10 @@ static cudaError_t bin_select(const SeqParams& P, uint32_t n_bins, bool query, B
 	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, K->fn, K->threads, K->smem);
 }
 
-uint32_t bin_sort_tile()
+uint32_t bin_sort_tile(const SeqParams& P, uint32_t n_bins)
 {
-	return (uint32_t)kSortTile;
+	const int threads = sort_threads_for(P, n_bins);
+	return threads ? sort_tile(threads) : (uint32_t)kTile;
 }
 
 bool bin_query_supported(const SeqParams& P, uint32_t n_bins)

@@ -110,7 +110,7 @@ cudaError_t launch_finalize_hits(uint32_t* hit, const uint32_t* valid, uint64_t 
 cudaError_t launch_query_gate(const unsigned long long* sample_stats, uint32_t* flag, uint32_t pct, cudaStream_t stream);
 bool bin_query_supported(const SeqParams& P, uint32_t n_bins);
 bool bin_sort_eligible(const SeqParams& P, uint32_t n_bins); // the sort-bin kernel (sort_bin.cuh) serves this shape
-uint32_t bin_sort_tile();                                    // windows per CTA pass of the sort-bin kernel
+uint32_t bin_sort_tile(const SeqParams& P, uint32_t n_bins); // windows per CTA pass of the sort-bin kernel for this shape
 
 // Two-level pass 2 of the partitioned build (apply2.cu): the items of every partition are split once more by
 // slice (refine), then each slice is ORed in shared memory and written back once.

@@ -3,7 +3,7 @@
 // Serves h <= kMaxSortHashes hashes per k-mer and <= kMaxSortBins filter partitions (everything the
 // BASELINE configs use); other shapes fall back to bin_kernel_warp / bin_kernel_cta in kernels.cu.
 //
-// Persistent CTAs of kSortThreads threads (256, four per SM: measured against 192, 512 and 1024); every CTA is the only writer of its own sub-bucket of each
+// Persistent CTAs of 256 or 512 threads (see sort_threads_for()); every CTA is the only writer of its own sub-bucket of each
 // filter partition.  A thread rolls kWPT consecutive windows (same staging and rolling as seq_kernel);
 // after every W of them the CTA counting-sorts the kSortThreads*W*h items it holds in registers:
 //   A   item -> (partition, offset); its rank inside the partition is the return value of a
@@ -23,13 +23,12 @@
 
 namespace btl {
 
-#ifndef BTL_SORT_THREADS
-#define BTL_SORT_THREADS 256
-#endif
-constexpr int kSortThreads = BTL_SORT_THREADS;
-constexpr int kSortCtasPerSm = 1024 / kSortThreads;  // 64 registers per thread: 1024 threads fill an SM's register file
-constexpr int kSortTile = kSortThreads * kWPT;       // windows per CTA pass (8192)
-constexpr uint32_t kMaxSortBins = 2 * kSortThreads;  // the scan handles two partitions per thread
+// Two CTA shapes are built: 256 threads (four CTAs per SM: cheaper barriers, the faster one whenever a round still
+// gives every partition a run of ~16 items) and 512 threads (two per SM: rounds twice as large, for many partitions
+// or few hashes per k-mer).  sort_threads_for() picks.
+BTL_HD constexpr int sort_ctas_per_sm(int threads) { return 1024 / threads; } // 64 registers per thread: 1024 threads fill the register file
+BTL_HD constexpr uint32_t sort_tile(int threads) { return (uint32_t)threads * kWPT; } // windows per CTA pass
+BTL_HD constexpr uint32_t sort_max_bins(int threads) { return 2u * (uint32_t)threads; } // the scan handles two partitions per thread
 constexpr int kMaxSortHashes = 8;
 
 BTL_HD constexpr int sort_round_windows(int h)
@@ -38,8 +37,10 @@ BTL_HD constexpr int sort_round_windows(int h)
 }
 
 // kernel entry points by shape; instantiated in sort_bin_build.cu (QUERY = false) and sort_bin_query.cu
-const void* bin_sort_kernel_build(int h, bool spaced, bool pow2);
-const void* bin_sort_kernel_query(int h, bool spaced, bool pow2);
+const void* bin_sort_kernel_build_256(int h, bool spaced, bool pow2);
+const void* bin_sort_kernel_build_512(int h, bool spaced, bool pow2);
+const void* bin_sort_kernel_query_256(int h, bool spaced, bool pow2);
+const void* bin_sort_kernel_query_512(int h, bool spaced, bool pow2);
 
 #if defined(__CUDACC__)
 __device__ __forceinline__ void bin_direct_or(const SeqParams& P, uint32_t part, uint32_t off)
@@ -90,26 +91,28 @@ __device__ __forceinline__ void expand_hashes(const SeqParams& P, const TileSmem
 #endif // __CUDACC__
 
 // dynamic shared memory of bin_kernel_sort: the sort arrays, then the tile staging area
-BTL_HD size_t sort_arrays_bytes(uint32_t n_bins, int h)
+BTL_HD size_t sort_arrays_bytes(uint32_t n_bins, int h, int threads)
 {
 	const size_t nbr = (n_bins + 1u) & ~1u;
-	const size_t cap = (size_t)kSortThreads * sort_round_windows(h) * h;
+	const size_t cap = (size_t)threads * sort_round_windows(h) * h;
 	size_t s = nbr * 8;                 // gdelta
 	s += cap * 8;                       // sorted: (offset, partition [| window]) pairs
 	s += nbr * 4 * 3 + 32 * 4;          // hist (+ 32 per-lane dump slots for invalid windows), base, cursor
-	s += (kSortThreads / 32 + 2) * 4;   // warp sums, total, overflow flag
+	s += (size_t)(threads / 32 + 2) * 4;   // warp sums, total, overflow flag
 	return (s + 15) / 16 * 16;
 }
 
-inline size_t sort_smem_bytes(uint32_t k, bool spaced, uint32_t n_bins, int h)
+inline size_t sort_smem_bytes(uint32_t k, bool spaced, uint32_t n_bins, int h, int threads)
 {
-	return sort_arrays_bytes(n_bins, h) + tile_smem_bytes(k, spaced, 0, kSortTile);
+	return sort_arrays_bytes(n_bins, h, threads) + tile_smem_bytes(k, spaced, 0, sort_tile(threads));
 }
 
 #if defined(__CUDACC__)
-template<int H, bool SPACED, bool POW2, bool QUERY>
-__global__ void __launch_bounds__(kSortThreads, kSortCtasPerSm) bin_kernel_sort(const __grid_constant__ SeqParams P)
+template<int THREADS, int H, bool SPACED, bool POW2, bool QUERY>
+__global__ void __launch_bounds__(THREADS, sort_ctas_per_sm(THREADS)) bin_kernel_sort(const __grid_constant__ SeqParams P)
 {
+	constexpr int kSortThreads = THREADS;
+	constexpr uint32_t kSortTile = sort_tile(THREADS);
 	constexpr int W = sort_round_windows(H);
 	constexpr int ITEMS = W * H;
 	constexpr uint32_t CAPACITY = (uint32_t)kSortThreads * ITEMS;
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(kSortThreads, kSortCtasPerSm) bin_kernel_sort(
 	uint32_t* const base = reinterpret_cast<uint32_t*>(p);       p += (size_t)nbr * 4;
 	uint32_t* const cursor = reinterpret_cast<uint32_t*>(p);     p += (size_t)nbr * 4;
 	uint32_t* const wsum = reinterpret_cast<uint32_t*>(p); // [NW] warp sums, [NW] total, [NW+1] overflow flag
-	const TileSmem sm = carve_smem(smem_raw + sort_arrays_bytes(nb, H), P.k, SPACED, 0, kSortTile);
+	const TileSmem sm = carve_smem(smem_raw + sort_arrays_bytes(nb, H, THREADS), P.k, SPACED, 0, kSortTile);
 
 	for (uint32_t b = tid; b < nbr; b += kSortThreads) {
 		hist[b] = 0;
@@ -271,26 +274,28 @@ __global__ void __launch_bounds__(kSortThreads, kSortCtasPerSm) bin_kernel_sort(
 		P.bin_counts[(uint64_t)b * P.bin_writers + writer] = cursor[b];
 }
 
-template<bool QUERY, int H>
+template<int THREADS, bool QUERY, int H>
 static const void* bin_sort_kernel_shape(bool spaced, bool pow2)
 {
 	if (spaced)
-		return pow2 ? (const void*)bin_kernel_sort<H, true, true, QUERY> : (const void*)bin_kernel_sort<H, true, false, QUERY>;
-	return pow2 ? (const void*)bin_kernel_sort<H, false, true, QUERY> : (const void*)bin_kernel_sort<H, false, false, QUERY>;
+		return pow2 ? (const void*)bin_kernel_sort<THREADS, H, true, true, QUERY>
+		            : (const void*)bin_kernel_sort<THREADS, H, true, false, QUERY>;
+	return pow2 ? (const void*)bin_kernel_sort<THREADS, H, false, true, QUERY>
+	            : (const void*)bin_kernel_sort<THREADS, H, false, false, QUERY>;
 }
 
-template<bool QUERY>
+template<int THREADS, bool QUERY>
 static const void* bin_sort_kernel_any(int h, bool spaced, bool pow2)
 {
 	switch (h) {
-	case 1: return bin_sort_kernel_shape<QUERY, 1>(spaced, pow2);
-	case 2: return bin_sort_kernel_shape<QUERY, 2>(spaced, pow2);
-	case 3: return bin_sort_kernel_shape<QUERY, 3>(spaced, pow2);
-	case 4: return bin_sort_kernel_shape<QUERY, 4>(spaced, pow2);
-	case 5: return bin_sort_kernel_shape<QUERY, 5>(spaced, pow2);
-	case 6: return bin_sort_kernel_shape<QUERY, 6>(spaced, pow2);
-	case 7: return bin_sort_kernel_shape<QUERY, 7>(spaced, pow2);
-	case 8: return bin_sort_kernel_shape<QUERY, 8>(spaced, pow2);
+	case 1: return bin_sort_kernel_shape<THREADS, QUERY, 1>(spaced, pow2);
+	case 2: return bin_sort_kernel_shape<THREADS, QUERY, 2>(spaced, pow2);
+	case 3: return bin_sort_kernel_shape<THREADS, QUERY, 3>(spaced, pow2);
+	case 4: return bin_sort_kernel_shape<THREADS, QUERY, 4>(spaced, pow2);
+	case 5: return bin_sort_kernel_shape<THREADS, QUERY, 5>(spaced, pow2);
+	case 6: return bin_sort_kernel_shape<THREADS, QUERY, 6>(spaced, pow2);
+	case 7: return bin_sort_kernel_shape<THREADS, QUERY, 7>(spaced, pow2);
+	case 8: return bin_sort_kernel_shape<THREADS, QUERY, 8>(spaced, pow2);
 	}
 	return nullptr;
 }

@@ -1,0 +1,11 @@
+// sort_bin_build_256.cu -- instantiates the sort-bin kernel (sort_bin.cuh), 256-thread CTAs, for the partitioned BUILD (offsets only).
+#include "sort_bin.cuh"
+
+namespace btl {
+
+const void* bin_sort_kernel_build_256(int h, bool spaced, bool pow2)
+{
+	return bin_sort_kernel_any<256, false>(h, spaced, pow2);
+}
+
+} // namespace btl
