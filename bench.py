@@ -1,31 +1,35 @@
 #!/usr/bin/env python3
-"""bench.py -- k-mer insert + query throughput of the BloomFilter hot path on B200.
+"""bench.py -- k-mer insert + query throughput of the Bloom-filter hot path on B200.
 
-Workload (BASELINE.json configs[1], "cfg2"): 3 Gbp synthetic genome, k=25, 4 hashes, 31,568,113,856-bit
-filter (the reference's calcOptimalSize(3e9, 0.01), 3.95 GB), built in chunks, then 150 bp read queries.
-One STEP = one pass of the hot path over one batch: insert one 64 Mi-window genome chunk into the filter
-and query one batch of 150 bp reads (4 x 64 MiB of bases by default) sampled from that chunk (all k-mers
-present: no early exit).  Like the workload itself (build the filter, then query reads), the timed region
-runs the K build batches first and the K query batches after them; both are inside the timed region.
+Headline workload (BASELINE.json configs[1], "cfg2"): 3 Gbp synthetic genome, k=25, 4 hashes, 31,568,113,856-bit
+filter (the reference's calcOptimalSize(3e9, 0.01), 3.95 GB), built in 64 Mi-window chunks, then 150 bp read queries.
+One STEP = one pass of the hot path over one batch: insert one genome chunk and query one batch of 150 bp reads
+(4 x 64 MiB of bases) sampled from an inserted chunk (every k-mer present: no early exit).  Like the workload itself
+(build the filter, then query reads) the timed region runs the K build batches, settles the filter -- at N > 1:
+MERGES the per-GPU partial filters (one fused kernel per GPU over NVLink peer memory, bracketed by stream-ordered
+cross-rank barriers) -- and then runs the K query batches.  Everything is inside the timed region.
 
-  value     whole-job Gk-mer/s (inserted + queried) with the batches already resident in HBM
-            (btlbf_insert_seqs_dev / btlbf_contains_seqs_dev), CUDA events, max over ranks
-  e2e       the same steps through the host-buffer C-ABI calls (btlbf_insert_seqs / btlbf_contains_seqs):
-            pinned host inputs, H2D + kernels + D2H of the hit bits inside the timed region
-  roofline  the phase that dominates the step (the query: pass 1 bin_kernel_sort + pass 2 probe_bins_kernel):
-            (32*h + 1) algorithmic bytes per k-mer / its mean duration per step (CUDA events inside the timed
-            region) against the measured HBM copy bandwidth; roofline_build (64*h + 1 bytes per k-mer) and
-            roofline_step (both phases) follow
-  cpu_baseline  the reference's own CPU path (oracle/_ref: unmodified headers, OpenMP over reads / chunks)
-            on a bounded sample of the same workload, same filter size, on this box's host cores
+  value     whole-job Gk-mer/s (inserted + queried, all ranks) with the batches already resident in HBM
+            (btlbf_insert_seqs_dev / btlbf_contains_seqs_dev), CUDA events, max over ranks; at N > 1 the merge is
+            part of it (`per_gpu_rate` x N is what N independent GPUs would do without it)
+  e2e       the same steps through the host-buffer C-ABI calls: pinned host inputs, H2D + kernels + D2H of the hit
+            bits (+ the merge at N > 1) inside the timed region
+  roofline  the phase that dominates the step (the query): (32*h + 1) algorithmic bytes per k-mer / its mean
+            duration per step against the measured HBM copy bandwidth; roofline_build and roofline_step follow
+  job       (cfg2) the complete BASELINE job, strong-scaled: the 45 chunks of the 3 Gbp genome sharded over the N
+            ranks -> merge -> 1e8 reads sharded over the ranks, one pair of events, max over ranks
+  configs   (default run) the other BASELINE.json configs -- cfg3, cfg4 (counting filter), cfg5a / cfg5b (spaced
+            seeds) -- through the same K-step loop with fewer steps: device rate, roofline fraction, e2e and the
+            reference's CPU path beside each
+  cpu_baseline  the reference's own CPU path (oracle/_ref: unmodified headers, OpenMP over reads / pieces) on a
+            bounded sample of the same workload, same filter size, on this box's host cores
 
-`--impl reference` times only that CPU path, K bounded-sample steps.  N > 1 (torchrun): one rank per GPU,
-units (genome chunks / read batches) sharded across ranks, no data-path collective ("weak" scaling);
-the partial filters are merged afterwards (all-to-all of 1/N slices + OR + all-gather) and that merge
-is timed and reported separately under "merge".
+`--impl reference` times only that CPU path, K bounded-sample steps of --config.  `--config NAME` makes another
+BASELINE config the headline of the line.
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -38,13 +42,35 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# host threads available to this process, taken before anything narrows the affinity mask or torchrun's
+# OMP_NUM_THREADS=1 gets a say (the reference arm passes this number to OpenMP explicitly)
+HOST_THREADS = len(os.sched_getaffinity(0))
+
 G_LEN = 3_000_000_000
-K, H = 25, 4
-FILTER_BITS = 31_568_113_856  # BloomFilter::calcOptimalSize(3e9, 0.01) with 4 hashes (BloomFilter.hpp:406-413)
-CHUNK = 64 << 20              # windows per insert launch
+CHUNK = 64 << 20              # windows per insert batch
 READ_LEN = 150
+KMAX = 32                     # the genome buffers carry KMAX-1 halo bytes: every config inserts CHUNK k-mers per batch
 GENOME_SEED, READ_SEED = 42, 7
-WORKLOAD = "cfg2: 3 Gbp synthetic genome build (k=25, h=4, 31.57 Gbit filter) + 150 bp read query"
+JOB_READS = 100_000_000       # "then query >= 1e8 150 bp reads"
+_SP = ["111101110111001", "111110110100111"]
+SEEDS31 = [x + "1" + x[::-1] for x in _SP]  # two symmetric 31-character masks
+
+CONFIGS = {
+    "cfg2": dict(kind="bloom", k=25, h=4, size=31_568_113_856,  # BloomFilter::calcOptimalSize(3e9, 0.01), BloomFilter.hpp:406-413
+                 workload="cfg2: 3 Gbp synthetic genome build (k=25, h=4, 31.57 Gbit filter) + 150 bp read query"),
+    "cfg3": dict(kind="bloom", k=32, h=6, size=1 << 35,
+                 workload="cfg3: 150 bp read query vs 4 GiB filter (k=32, h=6, 2^35 bits) built from the same genome"),
+    "cfg4": dict(kind="counting", k=25, h=4, size=16_000_000_000, threshold=2,
+                 workload="cfg4: CountingBloomFilter<uint8_t>, 16e9 counters, k=25, h=4, threshold-2 read query"),
+    "cfg5a": dict(kind="bloom", k=31, h=2, size=1 << 29, seeds=SEEDS31, h2=1,
+                  workload="cfg5a: spaced seeds (stHashIterator, k=31, 2 seeds), 64 MiB L2-resident filter"),
+    "cfg5b": dict(kind="bloom", k=31, h=2, size=1 << 37, seeds=SEEDS31, h2=1,
+                  workload="cfg5b: spaced seeds (stHashIterator, k=31, 2 seeds), 16 GiB filter"),
+}
+
+
+def filter_bytes(cfg):
+    return cfg["size"] // 8 if cfg["kind"] == "bloom" else cfg["size"]
 
 
 def measured_peak():
@@ -53,6 +79,17 @@ def measured_peak():
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def source_sha():
+    """Hash of the kernel sources: profiles carry it so that a stale ncu figure is never attached to a new binary."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "btl_bloomfilter_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".hpp")):
+            with open(os.path.join(d, name), "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -104,47 +141,71 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------- CPU reference arm
-def cpu_reference_run(n_steps, warmup, sample_bases, threads=0, verbose=False):
-    """The reference's CPU path on a bounded sample per step: insert `sample_bases` of the genome
-    (64 kb pieces, OpenMP over pieces) + query sample_bases/150 reads sampled from it."""
+def mem_available():
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable"):
+                return int(ln.split()[1]) * 1024
+    except Exception:
+        pass
+    return 1 << 62
+
+
+def cpu_reference_run(cfg, n_steps, warmup, sample_bases, threads=0, verbose=False):
+    """The reference's CPU path on a bounded sample per step: insert `sample_bases` of the genome (64 kb pieces,
+    OpenMP over pieces; README.md:30-43 / 86-113, stHashIterator.hpp:53-57 for spaced seeds) + query
+    sample_bases/150 reads sampled from it, against a filter of the config's full size."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _oracle as O
     orc = O.Oracle()
     use_ref = O.Ref.available()
+    k, h, kind = cfg["k"], cfg["h"], cfg["kind"]
+    seeds = cfg.get("seeds")
+    if not use_ref and (kind != "bloom" or seeds):
+        return {"unavailable": "oracle/_ref (the compiled reference) is needed for the counting / spaced-seed CPU legs"}
+    need = filter_bytes(cfg) + (2 << 30)
+    if mem_available() < need:
+        return {"unavailable": "host has %.1f GB available, the %s-size filter needs %.1f GB" %
+                (mem_available() / 1e9, cfg["kind"], need / 1e9)}
     piece = 65536
+    threads = int(threads or HOST_THREADS)
     if use_ref:
         R = O.Ref()
-        cores = R.L.ref_max_threads()
-        filt = R.bf_new(FILTER_BITS, H, K)
+        filt = R.L.ref_cbf_new(cfg["size"], h, k, cfg.get("threshold", 1)) if kind == "counting" else R.bf_new(cfg["size"], h, k)
+        sp = R._seeds(seeds) if seeds else None
     else:
-        cores = orc.L.ora_max_threads()
-        filt = np.zeros(FILTER_BITS // 8, np.uint8)
-    threads = threads or cores
+        filt = np.zeros(cfg["size"] // 8, np.uint8)
     n_reads = sample_bases // READ_LEN
     roff = (READ_LEN * np.arange(n_reads + 1)).astype(np.uint64)
     tot_k, tot_t, per = 0, 0.0, []
+
+    def leg(bases, off, n_seqs, do_insert):
+        nk, nh = O.u64(), O.u64()
+        if not use_ref:
+            t = orc.L.ora_bench_bf(O._p8(filt), cfg["size"], h, k, O._p8(bases), O._p64(off), n_seqs, do_insert, threads,
+                                   C.byref(nk), C.byref(nh))
+        elif kind == "counting":
+            t = R.L.ref_bench_cbf(filt, O._p8(bases), O._p64(off), n_seqs, do_insert, threads, C.byref(nk), C.byref(nh))
+        elif seeds:
+            t = R.L.ref_bench_st_bf(filt, sp, len(seeds), cfg.get("h2", 1), O._p8(bases), O._p64(off), n_seqs, do_insert,
+                                    threads, C.byref(nk), C.byref(nh))
+        else:
+            t = R.L.ref_bench_bf(filt, O._p8(bases), O._p64(off), n_seqs, do_insert, threads, C.byref(nk), C.byref(nh))
+        return t, nk.value, nh.value
+
     for s in range(warmup + n_steps):
-        g0 = (s * sample_bases) % (G_LEN - sample_bases - K)
-        g = orc.synth_genome(g0, sample_bases + K - 1, GENOME_SEED)
+        g0 = (s * sample_bases) % (G_LEN - sample_bases - k)
+        g = orc.synth_genome(g0, sample_bases + k - 1, GENOME_SEED)
         # 64 kb pieces overlapping by k-1 so that every window is inserted exactly once
         starts = np.arange(0, sample_bases, piece, dtype=np.uint64)
-        pieces = [g[int(a): int(min(a + piece + K - 1, g.size))] for a in starts]
+        pieces = [g[int(a): int(min(a + piece + k - 1, g.size))] for a in starts]
         pb = np.concatenate(pieces)
         poff = np.concatenate([[0], np.cumsum([p.size for p in pieces])]).astype(np.uint64)
         reads = orc.synth_reads(0, n_reads, READ_LEN, sample_bases, GENOME_SEED, READ_SEED + s, g_start=g0)
-        nk, nh = O.u64(), O.u64()
-        if use_ref:
-            t_i = R.L.ref_bench_bf(filt, O._p8(pb), O._p64(poff), poff.size - 1, 1, threads, C.byref(nk), C.byref(nh))
-            k_i = nk.value
-            t_q = R.L.ref_bench_bf(filt, O._p8(reads), O._p64(roff), n_reads, 0, threads, C.byref(nk), C.byref(nh))
-        else:
-            t_i = orc.L.ora_bench_bf(O._p8(filt), FILTER_BITS, H, K, O._p8(pb), O._p64(poff), poff.size - 1, 1, threads,
-                                     C.byref(nk), C.byref(nh))
-            k_i = nk.value
-            t_q = orc.L.ora_bench_bf(O._p8(filt), FILTER_BITS, H, K, O._p8(reads), O._p64(roff), n_reads, 0, threads,
-                                     C.byref(nk), C.byref(nh))
-        k_q = nk.value
-        assert nh.value == k_q, "CPU reference: a k-mer of an inserted region was not found"
+        t_i, k_i, _ = leg(pb, poff, poff.size - 1, 1)
+        t_q, k_q, n_hit = leg(reads, roff, n_reads, 0)
+        if kind == "bloom":
+            assert n_hit == k_q, "CPU reference: a k-mer of an inserted region was not found"
         if s >= warmup:
             tot_k += k_i + k_q
             tot_t += t_i + t_q
@@ -152,11 +213,12 @@ def cpu_reference_run(n_steps, warmup, sample_bases, threads=0, verbose=False):
         if verbose:
             print("cpu step %d: insert %.2f Mk/s, query %.2f Mk/s" % (s, k_i / t_i / 1e6, k_q / t_q / 1e6), file=sys.stderr)
     if use_ref:
-        R.L.ref_bf_free(filt)
-    return {"value": tot_k / tot_t / 1e9, "unit": "Gk-mer/s", "cores": int(threads),
+        (R.L.ref_cbf_free if kind == "counting" else R.L.ref_bf_free)(filt)
+    return {"value": tot_k / tot_t / 1e9, "unit": "Gk-mer/s", "cores": threads,
             "kind": "reference" if use_ref else "port",
-            "sample": "%d steps x (%d bp genome insert in 64 kb pieces + %d reads x %d bp query), %d-bit filter, "
-                      "OpenMP over pieces/reads" % (n_steps, sample_bases, n_reads, READ_LEN, FILTER_BITS),
+            "sample": "%d steps x (%d bp genome insert in 64 kb pieces + %d reads x %d bp query), %s filter of %d %s, "
+                      "OpenMP over pieces/reads" % (n_steps, sample_bases, n_reads, READ_LEN, kind, cfg["size"],
+                                                    "bits" if kind == "bloom" else "counters"),
             "insert_gkmers_s": float(np.mean([p[0] for p in per])) / 1e9,
             "query_gkmers_s": float(np.mean([p[1] for p in per])) / 1e9,
             "ms_per_step": tot_t / n_steps * 1e3, "kmers_per_step": tot_k / n_steps}
@@ -186,13 +248,509 @@ def bind_to_gpu_numa_node(torch, index):
     return None
 
 
+# ---------------------------------------------------------------- the GPU side
+class Env:
+    """Everything the configs share: the device, the stream, the context, the synthetic inputs in HBM."""
+
+    def __init__(self, args, torch, dist, B):
+        self.torch, self.dist, self.B, self.args = torch, dist, B, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.numa = bind_to_gpu_numa_node(torch, self.local_rank) if self.world > 1 else None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.ctx = B.Context(self.local_rank)
+        # the library's kernels run on torch's current stream so that torch.cuda.Event brackets them
+        self.stream = torch.cuda.Stream(device=self.dev, priority=args.stream_priority)
+        torch.cuda.set_stream(self.stream)
+        self.ctx.set_stream(self.stream.cuda_stream)
+        self.options = {}
+        if args.l2_fetch:
+            self.ctx.set_option("l2_fetch_granularity", args.l2_fetch)
+        for kv in args.opt:
+            key, val = kv.split("=")
+            self.ctx.set_option(key, int(val))
+            self.options[key] = int(val)
+        self.chunk = args.chunk // 16384 * 16384
+        self.n_chunks = (G_LEN + self.chunk - 1) // self.chunk
+        self.n_reads = self.chunk * args.query_factor // READ_LEN
+        self.read_bases = self.n_reads * READ_LEN
+        self.token = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.host = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def stream_barrier(self):
+        """Cross-rank barrier in stream order (no host synchronisation): a one-word NCCL all-reduce."""
+        if self.world > 1:
+            self.dist.all_reduce(self.token)
+
+    def make_inputs(self, n_genome, n_read):
+        """Genome chunks of this rank's shard (chunk c = rank + world * i) and read batches sampled from the first of
+        them, generated in HBM (replayable by the oracle: tests/test_gpu_parity.py)."""
+        torch, ctx = self.torch, self.ctx
+        self.g, self.g_chunk, self.g_len, self.r = [], [], [], []
+        for i in range(n_genome):
+            c = (self.rank + self.world * i) % self.n_chunks
+            g0 = c * self.chunk
+            glen = min(self.chunk + KMAX - 1, G_LEN - g0)
+            t = torch.empty(self.chunk + 64, dtype=torch.uint8, device=self.dev)
+            ctx.synth_genome_device(t.data_ptr(), g0, glen, GENOME_SEED)
+            self.g.append(t)
+            self.g_chunk.append(c)
+            self.g_len.append(glen)
+        for j in range(n_read):
+            c = self.g_chunk[j]
+            t = torch.empty(self.read_bases + 64, dtype=torch.uint8, device=self.dev)
+            ctx.synth_reads_device(t.data_ptr(), 0, self.n_reads, READ_LEN, c * self.chunk,
+                                   min(self.chunk, G_LEN - c * self.chunk), GENOME_SEED, READ_SEED + c)
+            self.r.append(t)
+        self.d_roff = torch.arange(0, self.read_bases + 1, READ_LEN, dtype=torch.int64, device=self.dev)
+        self.d_hits = torch.zeros((self.read_bases + 31) // 32 + 8, dtype=torch.int32, device=self.dev)
+        self._goff = {}
+        torch.cuda.synchronize()
+
+    def goff(self, n):
+        if n not in self._goff:
+            self._goff[n] = self.torch.tensor([0, n], dtype=self.torch.int64, device=self.dev)
+        return self._goff[n]
+
+    def insert_len(self, i, k):
+        """bases of genome buffer i a config with k-mer size k inserts: chunk windows + the k-1 halo"""
+        return min(self.chunk + k - 1, self.g_len[i])
+
+    def make_host_inputs(self, n_host):
+        """Pinned host copies of the first n_host genome chunks / read batches (shared by every config's e2e leg)."""
+        if self.host is not None:
+            return self.host
+        torch = self.torch
+        H = {"n": n_host}
+        H["genome"] = [torch.empty(self.g_len[j], dtype=torch.uint8).pin_memory() for j in range(n_host)]
+        H["reads"] = [torch.empty(self.read_bases, dtype=torch.uint8).pin_memory() for _ in range(n_host)]
+        for j in range(n_host):
+            H["genome"][j].copy_(self.g[j][: self.g_len[j]])
+            H["reads"][j].copy_(self.r[j][: self.read_bases])
+        H["hits"] = [torch.zeros((self.read_bases + 31) // 32 * 4, dtype=torch.uint8).pin_memory() for _ in range(n_host)]
+        t_roff = torch.arange(0, self.read_bases + 1, READ_LEN, dtype=torch.int64).pin_memory()
+        H["t_roff"] = t_roff
+        H["roff"] = t_roff.numpy().view(np.uint64)
+        H["counts_t"] = torch.zeros((64, 4), dtype=torch.int64).pin_memory()
+        H["counts"] = H["counts_t"].numpy().view(np.uint64)
+        torch.cuda.synchronize()
+        self.host = H
+        return H
+
+
+def make_filter(env, cfg):
+    B = env.B
+    if cfg["kind"] == "counting":
+        return B.CountingBloomFilter(cfg["size"], cfg["h"], cfg["k"], cfg.get("threshold", 1), ctx=env.ctx)
+    f = B.BloomFilter(cfg["size"], cfg["h"], cfg["k"], ctx=env.ctx)
+    if cfg.get("seeds"):
+        f.setSeeds(cfg["seeds"], cfg.get("h2", 1))
+    return f
+
+
+def filter_view(env, filt):
+    from btl_bloomfilter_b200 import parallel
+    ptr, nbytes = filt.device_ptr()
+    return parallel.device_tensor_from_ptr(ptr, nbytes, env.dev)
+
+
+def merge_parity(env, cfg):
+    """N > 1, before anything is timed: one chunk per rank into per-GPU partial filters of the config's full size,
+    fused merge; every rank then builds the same N chunks alone (BloomFilter: into one filter; counting: N partial
+    builds + saturating add, the definition of the sharded counting build) and compares the two arrays byte by byte
+    on the device.  Single-GPU builds are what tests/ pin to the oracle."""
+    from btl_bloomfilter_b200 import parallel
+    from btl_bloomfilter_b200._capi import check
+    torch, ctx = env.torch, env.ctx
+    k = cfg["k"]
+    a = make_filter(env, cfg)
+    st = torch.zeros(2, dtype=torch.int64, device=env.dev)
+    n0 = env.insert_len(0, k)
+    a.insertSeqsDevice(env.g[0].data_ptr(), n0, env.goff(n0).data_ptr(), 1, st.data_ptr())
+    pm = parallel.PeerMerge(ctx, *a.device_ptr(), a.KIND)
+    pm.merge()
+    pm.close()
+    b = make_filter(env, cfg)
+    part = make_filter(env, cfg) if cfg["kind"] == "counting" else None
+    tmp = torch.empty(env.chunk + 64, dtype=torch.uint8, device=env.dev)
+    for r in range(env.world):
+        c = r % env.n_chunks
+        glen = min(env.chunk + k - 1, G_LEN - c * env.chunk)
+        ctx.synth_genome_device(tmp.data_ptr(), c * env.chunk, glen, GENOME_SEED)
+        if part is None:
+            b.insertSeqsDevice(tmp.data_ptr(), glen, env.goff(glen).data_ptr(), 1, 0)
+        else:
+            part.clear()
+            part.insertSeqsDevice(tmp.data_ptr(), glen, env.goff(glen).data_ptr(), 1, 0)
+            ptr, nbytes = part.device_ptr()
+            check(ctx.L.btlbf_filter_merge_from_device(b._h, C.c_void_p(ptr), nbytes))
+    same = bool(torch.equal(filter_view(env, a), filter_view(env, b)))
+    pop = a.getPop() if cfg["kind"] == "bloom" else a.popCount()
+    t = torch.tensor([1 if same else 0, pop, -pop], dtype=torch.int64, device=env.dev)
+    env.dist.all_reduce(t, op=env.dist.ReduceOp.MIN)
+    del a, b, part, tmp
+    return {"merge_parity": bool(t[0] == 1), "identical_popcount_on_all_ranks": bool(int(t[1]) == -int(t[2])),
+            "popcount": int(t[1]), "chunks": env.world,
+            "how": "sharded build + fused merge == the same chunks built on one GPU (byte-compared on the device)"}
+
+
+def run_config(env, name, cfg, S, W, headline):
+    """The K-step loop of one config: K build batches -> settle (-> merge at N > 1) -> K query batches."""
+    torch, dist, ctx, world = env.torch, env.dist, env.ctx, env.world
+    k, h, kind = cfg["k"], cfg["h"], cfg["kind"]
+    counting = kind == "counting"
+    n_g, n_r = len(env.g), len(env.r)
+    n_q = max(1, min(n_r, S))  # the read buffers the timed queries cycle over: their chunks are inserted by then
+    filt = make_filter(env, cfg)
+    out = {"workload": cfg["workload"], "k": k, "hashes": h, "filter_bytes": filter_bytes(cfg)}
+    pm = None
+    if world > 1:
+        from btl_bloomfilter_b200 import parallel
+        if headline or counting:
+            out["merge_check"] = merge_parity(env, cfg)
+        pm = parallel.PeerMerge(ctx, *filt.device_ptr(), filt.KIND)
+    d_stats = torch.zeros(4, dtype=torch.int64, device=env.dev)
+
+    def build_dev(i):
+        j = i % n_g
+        n = env.insert_len(j, k)
+        filt.insertSeqsDevice(env.g[j].data_ptr(), n, env.goff(n).data_ptr(), 1, d_stats.data_ptr())
+
+    def query_dev(i):
+        j = i % n_q
+        filt.containsSeqsDevice(env.r[j].data_ptr(), env.read_bases, env.d_roff.data_ptr(), env.n_reads,
+                                env.d_hits.data_ptr(), 0, d_stats[2:].data_ptr())
+
+    def merge_dev():
+        if pm is None:
+            return
+        env.stream_barrier()  # every rank's partial build (pass 2 included: ctx.flush) is complete
+        pm.launch()
+        env.stream_barrier()  # every rank's byte range has been written into every filter
+
+    # ---- warm-up.  Counting filters: the chunks behind the read batches are inserted once here and once more in the
+    # timed region (2x coverage), so that every queried k-mer reaches the threshold (a hit set, like the BloomFilter's)
+    for i in range(n_q if counting else W):
+        build_dev(i)
+    ctx.flush()
+    if not counting:
+        merge_dev()  # (counting: one merge only, the timed one -- a second saturating add would count every k-mer N times over)
+    for i in range(W):
+        query_dev(i)
+    torch.cuda.synchronize()
+    if not counting:
+        filt.clear()
+    d_stats.zero_()
+    ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(S)]
+    ev_q = [torch.cuda.Event(enable_timing=True) for _ in range(S)]
+    t_start, t_built, t_mid, t_end = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+    sampler = ClockSampler(env.local_rank)
+    if env.rank == 0 and headline:
+        sampler.start()
+    launches0 = ctx.launch_count
+    env.barrier()
+    torch.cuda.synchronize()
+    t_start.record(env.stream)
+    for i in range(S):
+        build_dev(i)
+        ev_b[i].record(env.stream)
+    ctx.flush()  # every k-mer parked in the partition buckets reaches the filter (pass 2)
+    t_built.record(env.stream)
+    merge_dev()
+    t_mid.record(env.stream)
+    for i in range(S):
+        query_dev(i)
+        ev_q[i].record(env.stream)
+    t_end.record(env.stream)
+    torch.cuda.synchronize()
+    env.barrier()
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if (env.rank == 0 and headline) else None
+    ms_total = t_start.elapsed_time(t_end)
+    ms_build = t_start.elapsed_time(t_built)
+    ms_merge = t_built.elapsed_time(t_mid)
+    ms_query = t_mid.elapsed_time(t_end)
+    d_b = [(t_start if i == 0 else ev_b[i - 1]).elapsed_time(ev_b[i]) for i in range(S)]
+    d_q = [(t_mid if i == 0 else ev_q[i - 1]).elapsed_time(ev_q[i]) for i in range(S)]
+    st = d_stats.cpu().numpy()
+    k_ins, k_qry, k_hit = int(st[0]), int(st[2]), int(st[3])
+    if kind == "bloom":
+        assert k_hit == k_qry, "%s: a k-mer of an inserted chunk was not found (%d of %d)" % (name, k_hit, k_qry)
+    out["query_hit_fraction"] = k_hit / max(1, k_qry)
+    if counting:
+        out["ordered_deferred_rounds"] = list(filt.orderedStats())
+
+    # ---- the miss set (SURVEY 8d): reads of independent random bases, almost every k-mer absent
+    miss = None
+    if env.rank == 0 and headline:
+        d_miss = torch.empty(env.read_bases + 64, dtype=torch.uint8, device=env.dev)
+        ctx.synth_genome_device(d_miss.data_ptr(), 0, env.read_bases, 43 << 40)
+        d_ms = torch.zeros(2, dtype=torch.int64, device=env.dev)
+        reps = 3
+        qm = lambda: filt.containsSeqsDevice(d_miss.data_ptr(), env.read_bases, env.d_roff.data_ptr(), env.n_reads,  # noqa: E731
+                                             env.d_hits.data_ptr(), 0, d_ms.data_ptr())
+        qm()
+        torch.cuda.synchronize()
+        d_ms.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(env.stream)
+        for _ in range(reps):
+            qm()
+        b.record(env.stream)
+        torch.cuda.synchronize()
+        mk, mh = [int(x) for x in d_ms.cpu().numpy()]
+        ms_miss = a.elapsed_time(b) / reps
+        miss = {"gkmers_s": mk / reps / (ms_miss * 1e-3) / 1e9, "ms_per_batch": ms_miss, "kmers_per_batch": mk // reps,
+                "hit_fraction": mh / max(1, mk),
+                "path": "adaptive: sampled hit fraction on the device picks the early-exit kernel for read sets that mostly miss"}
+        del d_miss
+
+    # ---- end to end through the host-buffer C ABI (pinned inputs; H2D, kernels, D2H -- and the merge -- in the timed
+    # region).  Streaming form (btlbf_insert_seqs_async / btlbf_contains_seqs_async): the calls are queued back to back,
+    # so the copies of one step overlap the kernels of another; results are checked after the final btlbf_ctx_sync.
+    e2e = None
+    if not env.args.no_e2e:
+        Hh = env.make_host_inputs(min(n_r, 4))
+        n_host = Hh["n"]
+        counts = Hh["counts"]
+        S2 = min(S, 32 if headline else 6)
+        nh_q = max(1, min(n_host, S2))
+        goffs = [np.array([0, env.insert_len(j, k)], dtype=np.uint64) for j in range(n_host)]
+
+        def build_host_async(i, slot):
+            j = i % n_host
+            filt.insertSeqsAsync((Hh["genome"][j].numpy()[: int(goffs[j][1])], goffs[j]), counts[slot, 0:2])
+
+        def query_host_async(i, slot):
+            j = i % nh_q
+            filt.containsSeqsAsync((Hh["reads"][j].numpy(), Hh["roff"]), Hh["hits"][j].numpy(), counts[slot, 2:4])
+
+        def merge_host():
+            if pm is not None:
+                pm.merge()  # flush + synchronise + barrier | kernel | synchronise + barrier
+
+        # warm-up of the host path: the pinned buffers, the copy engines and the PCIe link (which trains up under
+        # traffic) -- a fresh process on a fresh box measures ~20 % low without it
+        for rep in range(2 if counting else 3):
+            for i in range(min(4, S2)):
+                build_host_async(i, 60 + (i & 1))
+            ctx.sync()
+            merge_host()
+            for i in range(min(4, S2)):
+                query_host_async(i, 60 + (i & 1))
+            ctx.sync()
+        counts[:] = 0
+        env.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(S2):
+            build_host_async(i, i)
+        if pm is not None:
+            ctx.sync()
+            merge_host()
+        for i in range(S2):
+            query_host_async(i, i)
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        env.barrier()
+        ke = int(counts[:S2, 0].sum() + counts[:S2, 2].sum())
+        if kind == "bloom":
+            assert np.array_equal(counts[:S2, 2], counts[:S2, 3]) and counts[:S2, 2].all(), "e2e: a queried k-mer was not found"
+        e2e = {"kmers": ke, "seconds": dt, "steps": S2,
+               "h2d": int(goffs[0][1]) + env.read_bases + (env.n_reads + 1) * 8 + 16, "d2h": int(Hh["hits"][0].numel()) + 32}
+        if headline:
+            def step_host_sync(i):
+                j = i % n_host
+                a = filt.insertSeqs((Hh["genome"][j].numpy()[: int(goffs[j][1])], goffs[j]))
+                r = filt.containsSeqs((Hh["reads"][j % nh_q].numpy(), Hh["roff"]), hit_out=Hh["hits"][j].numpy(), want_valid=False)
+                return a, r.n_kmers, r.n_hits
+            S3 = min(S, 6)
+            t0 = time.perf_counter()
+            ks = 0
+            for i in range(S3):
+                a, q, hq = step_host_sync(i)
+                ks += a + q
+            e2e.update({"kmers_sync": ks, "seconds_sync": time.perf_counter() - t0, "steps_sync": S3})
+            env.barrier()
+
+    # ---- reductions over ranks (max time, summed work)
+    if world > 1:
+        t = torch.tensor([ms_total, ms_build, ms_merge, ms_query, e2e["seconds"] if e2e else 0.0,
+                          e2e.get("seconds_sync", 0.0) if e2e else 0.0], dtype=torch.float64, device=env.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_build, ms_merge, ms_query = (float(x) for x in t[:4])
+        w = torch.tensor([k_ins, k_qry, e2e["kmers"] if e2e else 0, launches, e2e.get("kmers_sync", 0) if e2e else 0],
+                         dtype=torch.int64, device=env.dev)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        k_ins_all, k_qry_all, ke_all, launches_all, ks_all = [int(x) for x in w]
+        if e2e:
+            e2e["seconds"], e2e["kmers"] = float(t[4]), ke_all
+            if "seconds_sync" in e2e:
+                e2e["seconds_sync"], e2e["kmers_sync"] = float(t[5]), ks_all
+    else:
+        k_ins_all, k_qry_all, launches_all = k_ins, k_qry, launches
+
+    peak, peak_src = measured_peak()
+    # algorithmic bytes of SURVEY.md 8d: build 64 B per hash (32 B sector read + 32 B dirty write-back) + 1 input byte
+    # per k-mer, query 32 B per hash + 1
+    b_ins, b_qry = 64 * h + 1, 32 * h + 1
+    ins_gk = k_ins / (ms_build * 1e-3) / 1e9   # this rank's phases (rank 0 reports; ranks are symmetric)
+    qry_gk = k_qry / (ms_query * 1e-3) / 1e9
+    out.update({"value": (k_ins_all + k_qry_all) / (ms_total * 1e-3) / 1e9, "unit": "Gk-mer/s", "steps": S, "warmup": W,
+                "ms_per_step": ms_total / S, "insert_gkmers_s": k_ins_all / (ms_build * 1e-3) / 1e9,
+                "query_gkmers_s": k_qry_all / (ms_query * 1e-3) / 1e9, "kmers_per_step": (k_ins_all + k_qry_all) / S,
+                "build_ms": ms_build, "merge_ms": ms_merge, "query_ms": ms_query,
+                "insert_frac": ins_gk * b_ins / peak, "query_frac": qry_gk * b_qry / peak,
+                "bytes_per_kmer": {"insert": b_ins, "query": b_qry}, "gpu_launches": launches_all})
+    if world > 1:
+        # what the ranks do when nothing connects them: the same phases without the merge
+        out["per_gpu_rate"] = (k_ins + k_qry) / ((ms_build + ms_query) * 1e-3) / 1e9
+        out["merge"] = {"ms": ms_merge, "filter_bytes": filter_bytes(cfg), "how": "btlbf_merge_peers: one kernel per GPU over "
+                        "NVLink peer memory (reduce-scatter + all-gather in one pass), two stream-ordered barriers",
+                        "link_GBps_per_gpu_per_direction": 2.0 * (world - 1) / world * filter_bytes(cfg) / (ms_merge * 1e-3) / 1e9}
+    if e2e:
+        out["e2e"] = {"value": e2e["kmers"] / e2e["seconds"] / 1e9, "unit": "Gk-mer/s", "steps": e2e["steps"],
+                      "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                      "api": "btlbf_insert_seqs_async + btlbf_contains_seqs_async (streaming), pinned host buffers"
+                             + (", btlbf_merge_peers between the phases" if world > 1 else "")}
+        if "seconds_sync" in e2e:
+            out["e2e_sync"] = {"value": e2e["kmers_sync"] / e2e["seconds_sync"] / 1e9, "unit": "Gk-mer/s",
+                               "steps": e2e["steps_sync"], "api": "btlbf_insert_seqs + btlbf_contains_seqs (blocking)"}
+    if headline:
+        ins_bytes, qry_bytes = b_ins * (k_ins / S), b_qry * (k_qry / S)
+        ins_ms, qry_ms = ms_build / S, ms_query / S
+        pass1 = float(np.median(d_b))
+        roof_b = {"bound": "hbm", "kernel": "build: bin_kernel_sort per batch + apply_bins_kernel per accumulation (all "
+                  "durations of the build phase added)" if not counting else "counting build: OP_RESV_TOUCH + OP_CBF_COMMIT "
+                  "+ list_drain_coop_kernel per 4 Mi-window batch", "achieved": ins_bytes / (ins_ms * 1e-3) / 1e9,
+                  "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None, "bytes_per_kmer": b_ins,
+                  "kmers_per_launch": k_ins / S, "launch_ms": ins_ms, "pass1_ms": pass1, "pass2_ms": ins_ms - pass1,
+                  "gkmers_s": ins_gk, "share_of_step": ms_build / ms_total}
+        roof_b["frac"] = roof_b["achieved"] / peak
+        roof_b["note"] = ("a fraction above 1 is possible: the partitioned build replaces one random 32-byte sector per hash "
+                          "(the algorithmic model) by streaming traffic -- compare `traffic` with achieved x launch_ms")
+        roof_q = {"bound": "hbm", "kernel": "query: bin_kernel_sort (pass 1) overlapped with probe_bins_kernel (pass 2) of the "
+                  "previous sub-batch + finalize_hits_kernel" if not counting else "counting query", "achieved": qry_bytes / (qry_ms * 1e-3) / 1e9,
+                  "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None, "bytes_per_kmer": b_qry,
+                  "kmers_per_launch": k_qry / S, "launch_ms": qry_ms, "call_ms_median": float(np.median(d_q)),
+                  "gkmers_s": qry_gk, "share_of_step": ms_query / ms_total}
+        roof_q["frac"] = roof_q["achieved"] / peak
+        # dram__bytes_read.sum + dram__bytes_write.sum per step from the ncu --set full capture of this same command
+        # (written by tools/summarize_ncu.py); attached only when it was taken from these very kernel sources
+        prof = os.path.join(ROOT, "profiles", "r2_dram_bytes_per_step.json")
+        if name == "cfg2" and os.path.exists(prof) and not env.options:
+            try:
+                t = json.load(open(prof))
+                if t.get("source_sha") == source_sha():
+                    roof_b["traffic"], roof_q["traffic"] = t["build_bytes_per_step"], t["query_bytes_per_step"]
+                    roof_b["traffic_source"] = roof_q["traffic_source"] = (
+                        "profiles/r2_dram_bytes_per_step.json: ncu --set full of this command at kernel sources %s; "
+                        "a constant from that capture, not measured by this run" % t["source_sha"])
+                else:
+                    roof_q["traffic_source"] = "none: the committed ncu capture is of other kernel sources"
+            except Exception:
+                pass
+        roof_s = {"bound": "hbm", "kernel": "whole step (build phase + merge + query phase)", "unit": "GB/s", "peak": peak,
+                  "achieved": (ins_bytes + qry_bytes) / (ms_total / S * 1e-3) / 1e9, "launch_ms": ms_total / S,
+                  "traffic": (roof_b["traffic"] + roof_q["traffic"]) if roof_b["traffic"] and roof_q["traffic"] else None}
+        roof_s["frac"] = roof_s["achieved"] / peak
+        probe_file = os.path.join(ROOT, "profiles", "r1_random_access_probe.jsonl")
+        if os.path.exists(probe_file):
+            try:
+                roof_q["random_access_probe"] = [json.loads(ln) for ln in open(probe_file) if ln.strip()]
+            except Exception:
+                pass
+        out.update({"roofline": roof_q, "roofline_build": roof_b, "roofline_step": roof_s, "clocks": clocks})
+        if miss:
+            out["query_miss_set"] = miss
+        if name == "cfg2":
+            out["job"] = run_job(env, cfg, filt, pm)
+    if pm is not None:
+        pm.close()
+    del filt
+    torch.cuda.synchronize()
+    return out
+
+
+def run_job(env, cfg, filt, pm):
+    """The complete cfg2 job, strong-scaled: every chunk of the 3 Gbp genome (sharded round-robin over the ranks) ->
+    merge -> 1e8 reads (sharded), between one pair of events; max over ranks."""
+    torch, dist, ctx, world = env.torch, env.dist, env.ctx, env.world
+    k = cfg["k"]
+    n_mine = len([c for c in range(env.n_chunks) if c % world == env.rank])
+    if n_mine > len(env.g):
+        return {"skipped": "needs every chunk of the rank's shard resident (run without --job-chunks limits)"}
+    n_batches = (JOB_READS + env.n_reads - 1) // env.n_reads
+    q_mine = len([b for b in range(n_batches) if b % world == env.rank])
+    d_stats = torch.zeros(4, dtype=torch.int64, device=env.dev)
+    best = None
+    for rep in range(2):
+        filt.clear()
+        d_stats.zero_()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        env.barrier()
+        torch.cuda.synchronize()
+        ev[0].record(env.stream)
+        for i in range(n_mine):
+            n = env.insert_len(i, k)
+            filt.insertSeqsDevice(env.g[i].data_ptr(), n, env.goff(n).data_ptr(), 1, d_stats.data_ptr())
+        ctx.flush()
+        ev[1].record(env.stream)
+        if pm is not None:
+            env.stream_barrier()
+            pm.launch()
+            env.stream_barrier()
+        ev[2].record(env.stream)
+        for i in range(q_mine):
+            filt.containsSeqsDevice(env.r[i % len(env.r)].data_ptr(), env.read_bases, env.d_roff.data_ptr(), env.n_reads,
+                                    env.d_hits.data_ptr(), 0, d_stats[2:].data_ptr())
+        ev[3].record(env.stream)
+        torch.cuda.synchronize()
+        env.barrier()
+        ms = [ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]), ev[0].elapsed_time(ev[3])]
+        if best is None or ms[3] < best[3]:
+            best = ms
+    st = d_stats.cpu().numpy()
+    assert int(st[2]) == int(st[3]), "job: a k-mer of the genome was not found after the full build"
+    pop = filt.getPop()
+    kk = torch.tensor([int(st[0]), int(st[2])], dtype=torch.int64, device=env.dev)
+    tt = torch.tensor(best, dtype=torch.float64, device=env.dev)
+    pp = torch.tensor([pop, -pop], dtype=torch.int64, device=env.dev)
+    if world > 1:
+        dist.all_reduce(kk, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pp, op=dist.ReduceOp.MIN)
+    occ = pop / cfg["size"]
+    return {"what": "3 Gbp genome build sharded over the ranks -> merge -> %d reads x %d bp sharded over the ranks; best of 2"
+                    % (n_batches * env.n_reads, READ_LEN), "scaling": "strong",
+            "build_ms": float(tt[0]), "merge_ms": float(tt[1]), "query_ms": float(tt[2]), "total_ms": float(tt[3]),
+            "kmers_inserted": int(kk[0]), "kmers_queried": int(kk[1]),
+            "gkmers_s": float(int(kk[0]) + int(kk[1])) / (float(tt[3]) * 1e-3) / 1e9,
+            "build_gkmers_s_incl_merge": int(kk[0]) / ((float(tt[0]) + float(tt[1])) * 1e-3) / 1e9,
+            "popcount": int(pp[0]), "identical_popcount_on_all_ranks": int(pp[0]) == -int(pp[1]),
+            "occupancy": occ, "expected_occupancy": float(1.0 - np.exp(-cfg["h"] * (G_LEN - k + 1) / cfg["size"]))}
+
+
 # ---------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=42)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (the other BASELINE configs)")
+    ap.add_argument("--configs", default="cfg3,cfg4,cfg5a,cfg5b", help="which configs the `configs` block covers")
+    ap.add_argument("--config-steps", type=int, default=6)
+    ap.add_argument("--no-job", action="store_true", help="skip the strong-scaled full cfg2 job")
     ap.add_argument("--cpu-sample", type=int, default=8 << 20, help="bases per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -204,19 +762,24 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": WORKLOAD, "k": K, "hashes": H, "filter_bits": FILTER_BITS, "genome_bp": G_LEN,
+    cfg = CONFIGS[args.config]
+    W, S = max(0, args.warmup), max(1, args.steps)
+    config = {"workload": cfg["workload"], "name": args.config, "k": cfg["k"], "hashes": cfg["h"],
+              "filter_%s" % ("bits" if cfg["kind"] == "bloom" else "counters"): cfg["size"], "genome_bp": G_LEN,
               "read_len": READ_LEN, "chunk_windows": args.chunk, "query_bases_per_step": args.chunk * args.query_factor,
-              "step": "K build batches, then K query batches, all inside the timed region",
-              "l2": "inputs larger than L2 (64 MiB / 256 MiB per batch, 3.95 GB filter); no flush needed"}
+              "step": "K build batches, settle" + (", merge the per-GPU partial filters" if world > 1 else "") +
+                      ", then K query batches, all inside the timed region",
+              "l2": "inputs larger than L2 (64 MiB / 256 MiB per batch, multi-GB filter); no flush needed"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, args.steps)
-        r = cpu_reference_run(steps, min(args.warmup, 1), args.cpu_sample)
+        r = cpu_reference_run(cfg, S, min(W, 1), args.cpu_sample, HOST_THREADS)
+        if "unavailable" in r:
+            print(json.dumps({"impl": "reference", "unavailable": r["unavailable"]}))
+            return
         line = {"impl": "reference", "metric": "k-mers/s inserted+queried", "value": r["value"], "unit": "Gk-mer/s",
-                "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+                "n_gpus": args.gpus, "steps": S, "warmup": min(W, 1), "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
                 "config": config, "cpu_baseline": r,
                 "e2e": {"value": r["value"], "unit": "Gk-mer/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -229,300 +792,50 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    ctx = B.Context(local_rank)
-    # the library's kernels run on torch's current stream so that torch.cuda.Event brackets them
-    # (a non-default stream: the C ABI treats a NULL stream as "use the context's own")
-    stream = torch.cuda.Stream(device=dev, priority=args.stream_priority)
-    torch.cuda.set_stream(stream)
-    ctx.set_stream(stream.cuda_stream)
-    if args.l2_fetch:
-        ctx.set_option("l2_fetch_granularity", args.l2_fetch)
-    for kv in args.opt:
-        key, val = kv.split("=")
-        ctx.set_option(key, int(val))
-        config.setdefault("options", {})[key] = int(val)
+    env = Env(args, torch, dist, B)
+    if env.options:
+        config["options"] = env.options
+    want_job = args.config == "cfg2" and not args.no_job
+    shard = len([c for c in range(env.n_chunks) if c % world == env.rank])
+    n_genome = max(min(W + S, env.n_chunks), shard if want_job else 0)
+    n_read = max(1, min(W + S, 8, n_genome))
+    env.make_inputs(n_genome, n_read)
 
-    chunk = args.chunk // 4096 * 4096
-    n_chunks = (G_LEN + chunk - 1) // chunk
-    W, S = args.warmup, args.steps
-    n_reads = chunk * args.query_factor // READ_LEN
-    read_bases = n_reads * READ_LEN
-    filt = B.BloomFilter(FILTER_BITS, H, K, ctx=ctx)
-
-    # ---- synthetic inputs generated in HBM (replayable by the oracle: tests/test_gpu_parity.py)
-    n_buf = min(W + S, n_chunks)
-    d_genome, d_reads, g_lens = [], [], []
-    for i in range(n_buf):
-        c = (i * world + rank) % n_chunks
-        g0 = c * chunk
-        glen = min(chunk + K - 1, G_LEN - g0)
-        tg = torch.empty(chunk + 64, dtype=torch.uint8, device=dev)
-        ctx.synth_genome_device(tg.data_ptr(), g0, glen, GENOME_SEED)
-        tr = torch.empty(read_bases + 64, dtype=torch.uint8, device=dev)
-        ctx.synth_reads_device(tr.data_ptr(), 0, n_reads, READ_LEN, g0, glen, GENOME_SEED, READ_SEED + c)
-        d_genome.append(tg)
-        d_reads.append(tr)
-        g_lens.append(glen)
-    d_goff = [torch.tensor([0, gl], dtype=torch.int64, device=dev) for gl in sorted(set(g_lens))]
-    goff_of = {int(t[1]): t for t in d_goff}
-    d_roff = torch.arange(0, read_bases + 1, READ_LEN, dtype=torch.int64, device=dev)
-    d_hits = torch.zeros((read_bases + 31) // 32 + 8, dtype=torch.int32, device=dev)
-    d_stats = torch.zeros(4, dtype=torch.int64, device=dev)
-    torch.cuda.synchronize()
-
-    def build_dev(i):
-        j = i % n_buf
-        filt.insertSeqsDevice(d_genome[j].data_ptr(), g_lens[j], goff_of[g_lens[j]].data_ptr(), 1, d_stats.data_ptr())
-
-    def query_dev(i):
-        j = i % n_buf
-        filt.containsSeqsDevice(d_reads[j].data_ptr(), read_bases, d_roff.data_ptr(), n_reads, d_hits.data_ptr(), 0,
-                                d_stats[2:].data_ptr())
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    for i in range(W):
-        build_dev(i)
-    for i in range(W):
-        query_dev(i)
-    torch.cuda.synchronize()
-    d_stats.zero_()
-    ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(S)]
-    ev_q = [torch.cuda.Event(enable_timing=True) for _ in range(S)]
-    t_start, t_mid, t_end = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = ctx.launch_count
-    barrier()
-    torch.cuda.synchronize()
-    t_start.record(stream)
-    for i in range(S):
-        build_dev(W + i)
-        ev_b[i].record(stream)
-    ctx.flush()  # every k-mer parked in the partition buckets reaches the filter (pass 2) before t_mid
-    t_mid.record(stream)
-    for i in range(S):
-        query_dev(W + i)
-        ev_q[i].record(stream)
-    t_end.record(stream)
-    torch.cuda.synchronize()
-    barrier()
-    launches = ctx.launch_count - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    ms_total = t_start.elapsed_time(t_end)
-    ms_insert = t_start.elapsed_time(t_mid)
-    ms_query = t_mid.elapsed_time(t_end)
-    # per-call durations on the stream: a build call is pass 1 of its batch, plus pass 2 of the whole
-    # accumulation when that call filled the partition buckets (the median is therefore pass 1 alone)
-    d_b = [(t_start if i == 0 else ev_b[i - 1]).elapsed_time(ev_b[i]) for i in range(S)]
-    d_q = [(t_mid if i == 0 else ev_q[i - 1]).elapsed_time(ev_q[i]) for i in range(S)]
-    ms_insert_pass1 = float(np.median(d_b)) * S
-    st = d_stats.cpu().numpy()
-    k_ins, k_qry, k_hit = int(st[0]), int(st[2]), int(st[3])
-    assert k_hit == k_qry, "a k-mer of an inserted chunk was not found (%d of %d)" % (k_hit, k_qry)
-
-    # ---- the miss set: reads of independent random bases, almost every k-mer absent.  Reported next
-    # to the headline (which is the hit set: no early exit); outside the timed region of `value`.
-    miss = None
-    if rank == 0:
-        d_miss = torch.empty(read_bases + 64, dtype=torch.uint8, device=dev)
-        ctx.synth_genome_device(d_miss.data_ptr(), 0, read_bases, 43 << 40)
-        d_ms = torch.zeros(2, dtype=torch.int64, device=dev)
-        reps = 3
-        filt.containsSeqsDevice(d_miss.data_ptr(), read_bases, d_roff.data_ptr(), n_reads, d_hits.data_ptr(), 0, d_ms.data_ptr())
-        torch.cuda.synchronize()
-        d_ms.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        for _ in range(reps):
-            filt.containsSeqsDevice(d_miss.data_ptr(), read_bases, d_roff.data_ptr(), n_reads, d_hits.data_ptr(), 0,
-                                    d_ms.data_ptr())
-        b.record(stream)
-        torch.cuda.synchronize()
-        mk, mh = [int(x) for x in d_ms.cpu().numpy()]
-        ms_miss = a.elapsed_time(b) / reps
-        miss = {"gkmers_s": mk / reps / (ms_miss * 1e-3) / 1e9, "ms_per_batch": ms_miss, "kmers_per_batch": mk // reps,
-                "hit_fraction": mh / max(1, mk),
-                "path": "adaptive: sampled hit fraction on the device picks the early-exit kernel for read sets that mostly miss"}
-        del d_miss
-
-    # ---- end to end through the host-buffer C ABI (pinned inputs; H2D, kernels and D2H inside the timed region)
-    # Streaming form (btlbf_insert_seqs_async / btlbf_contains_seqs_async): every step copies its genome chunk
-    # and reads host->device, runs the kernels and copies the hit bits + counts device->host; the calls are
-    # queued back to back, so the copies of one step overlap the kernels of another, and the results are
-    # checked after the final btlbf_ctx_sync.  "e2e_sync" is the same with the blocking calls.
-    e2e = None
-    if not args.no_e2e:
-        n_host = min(n_buf, 4)
-        h_genome = [torch.empty(g_lens[j], dtype=torch.uint8).pin_memory() for j in range(n_host)]
-        h_reads = [torch.empty(read_bases, dtype=torch.uint8).pin_memory() for _ in range(n_host)]
-        for j in range(n_host):
-            h_genome[j].copy_(d_genome[j][: g_lens[j]])
-            h_reads[j].copy_(d_reads[j][:read_bases])
-        h_hits = [torch.zeros((read_bases + 31) // 32 * 4, dtype=torch.uint8).pin_memory() for _ in range(n_host)]
-        t_roff = torch.arange(0, read_bases + 1, READ_LEN, dtype=torch.int64).pin_memory()
-        h_roff = t_roff.numpy().view(np.uint64)
-        t_goff = [torch.tensor([0, g_lens[j]], dtype=torch.int64).pin_memory() for j in range(n_host)]
-        h_goff = [t.numpy().view(np.uint64) for t in t_goff]
-        S2 = min(S, 32)
-        h_counts = torch.zeros((S2 + 4, 4), dtype=torch.int64).pin_memory()
-        counts = h_counts.numpy().view(np.uint64)
-        torch.cuda.synchronize()
-
-        def step_host_sync(i):
-            j = i % n_host
-            a = filt.insertSeqs((h_genome[j].numpy(), h_goff[j]))
-            r = filt.containsSeqs((h_reads[j].numpy(), h_roff), hit_out=h_hits[j].numpy(), want_valid=False)
-            return a, r.n_kmers, r.n_hits
-
-        def build_host_async(i, slot):
-            j = i % n_host
-            filt.insertSeqsAsync((h_genome[j].numpy(), h_goff[j]), counts[slot, 0:2])
-
-        def query_host_async(i, slot):
-            j = i % n_host
-            filt.containsSeqsAsync((h_reads[j].numpy(), h_roff), h_hits[j].numpy(), counts[slot, 2:4])
-
-        for i in range(min(W, 2)):
-            step_host_sync(i)
-        # warm-up of the host path: the pinned buffers, the copy engines and the PCIe link (which trains up under
-        # traffic) -- a fresh process on a fresh box measures ~20 % low without it
-        for rep in range(3):
-            for i in range(4):
-                build_host_async(i, S2 + (i & 1))
-            for i in range(4):
-                query_host_async(i, S2 + (i & 1))
-            ctx.sync()
-        barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(S2):
-            build_host_async(i, i)
-        for i in range(S2):
-            query_host_async(i, i)
-        ctx.sync()
-        dt = time.perf_counter() - t0
-        barrier()
-        ke = int(counts[:S2, 0].sum() + counts[:S2, 2].sum())
-        assert np.array_equal(counts[:S2, 2], counts[:S2, 3]) and counts[:S2, 2].all(), "e2e: a queried k-mer was not found"
-        S3 = min(S, 6)
-        t0 = time.perf_counter()
-        ks = 0
-        for i in range(S3):
-            a, q, hq = step_host_sync(i)
-            assert hq == q
-            ks += a + q
-        dts = time.perf_counter() - t0
-        barrier()
-        e2e = {"kmers": ke, "seconds": dt, "steps": S2, "kmers_sync": ks, "seconds_sync": dts, "steps_sync": S3,
-               "h2d": int(np.mean(g_lens[:n_host])) + read_bases + (n_reads + 1) * 8 + 16,
-               "d2h": int(h_hits[0].numel()) + 32}
-
-    # ---- reductions over ranks (max time, summed work)
-    if world > 1:
-        t = torch.tensor([ms_total, ms_insert, ms_query, e2e["seconds"] if e2e else 0.0,
-                          e2e["seconds_sync"] if e2e else 0.0], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_insert, ms_query = float(t[0]), float(t[1]), float(t[2])
-        w = torch.tensor([k_ins, k_qry, e2e["kmers"] if e2e else 0, launches, e2e["kmers_sync"] if e2e else 0],
-                         dtype=torch.int64, device=dev)
-        dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        k_ins_all, k_qry_all, ke_all, launches_all, ks_all = [int(x) for x in w]
-        if e2e:
-            e2e["seconds"], e2e["seconds_sync"] = float(t[3]), float(t[4])
-            e2e["kmers"], e2e["kmers_sync"] = ke_all, ks_all
-    else:
-        k_ins_all, k_qry_all, launches_all = k_ins, k_qry, launches
-
-    merge = None
-    if world > 1:
-        from btl_bloomfilter_b200 import parallel
-        merge = parallel.bench_merge(filt, ctx, dev)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    peak, peak_src = measured_peak()
-    # rooflines per rank, algorithmic bytes of SURVEY.md 8d: build 64 B per hash (32 B sector read + 32 B dirty
-    # write-back) + 1 input byte per k-mer, query 32 B per hash + 1
-    ins_bytes = (64 * H + 1) * (k_ins / S)
-    ins_ms = ms_insert / S
-    qry_bytes = (32 * H + 1) * (k_qry / S)
-    qry_ms = ms_query / S
-    roof = {"bound": "hbm", "kernel": "BloomFilter build: bin_kernel_sort per batch + apply_bins_kernel per accumulation "
-                                      "(all durations of the build phase added)", "achieved": ins_bytes / (ins_ms * 1e-3) / 1e9,
-            "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None,
-            "bytes_per_kmer": 64 * H + 1, "kmers_per_launch": k_ins / S, "launch_ms": ins_ms,
-            "pass1_ms": ms_insert_pass1 / S, "pass2_ms": (ms_insert - ms_insert_pass1) / S,
-            "gkmers_s": k_ins / S / (ins_ms * 1e-3) / 1e9}
-    roof["frac"] = roof["achieved"] / peak
-    roof_q = {"bound": "hbm", "kernel": "BloomFilter query: bin_kernel_sort + probe_bins_kernel + finalize_hits_kernel", "achieved": qry_bytes / (qry_ms * 1e-3) / 1e9,
-              "peak": peak, "unit": "GB/s", "bytes_per_kmer": 32 * H + 1, "kmers_per_launch": k_qry / S,
-              "launch_ms": qry_ms, "call_ms_median": float(np.median(d_q)),
-              "gkmers_s": k_qry / S / (qry_ms * 1e-3) / 1e9}
-    roof_q["frac"] = roof_q["achieved"] / peak
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this
-    # same command (profiles/r1_dram_bytes_per_launch.json, written by tools/summarize_ncu.py)
-    prof = os.path.join(ROOT, "profiles", "r1_dram_bytes_per_step.json")
-    if os.path.exists(prof) and chunk == CHUNK and args.query_factor == 4 and not args.opt:
-        try:
-            t = json.load(open(prof))
-            roof["traffic"] = t["build_bytes_per_step"]
-            roof_q["traffic"] = t["query_bytes_per_step"]
-        except Exception:
-            pass
-    roof_q["peak_source"] = peak_src
-    roof_q["share_of_step"] = ms_query / ms_total
-    roof["share_of_step"] = ms_insert / ms_total
-    roof["note"] = ("a fraction above 1 is possible: the partitioned build replaces one random 32-byte sector per hash "
-                    "(the algorithmic model) by streaming traffic -- compare `traffic` with achieved x launch_ms")
-    step_bytes = ins_bytes + qry_bytes
-    roof_step = {"bound": "hbm", "kernel": "whole step (build phase + query phase)", "unit": "GB/s", "peak": peak,
-                 "achieved": step_bytes / (ms_total / S * 1e-3) / 1e9, "launch_ms": ms_total / S,
-                 "traffic": (roof["traffic"] + roof_q["traffic"]) if roof["traffic"] and roof_q["traffic"] else None}
-    roof_step["frac"] = roof_step["achieved"] / peak
-    # measured hardware ceilings for this access pattern (tools/probe_random_access.py on this GPU type)
-    probe_file = os.path.join(ROOT, "profiles", "r1_random_access_probe.jsonl")
-    if os.path.exists(probe_file):
-        try:
-            roof_q["random_access_probe"] = [json.loads(l) for l in open(probe_file) if l.strip()]
-        except Exception:
-            pass
-    line = {"metric": "k-mers/s inserted+queried", "value": (k_ins_all + k_qry_all) / (ms_total * 1e-3) / 1e9,
-            "unit": "Gk-mer/s", "n_gpus": world, "steps": S, "warmup": W, "ms_per_step": ms_total / S,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": config, "insert_gkmers_s": k_ins_all / (ms_insert * 1e-3) / 1e9,
-            "query_gkmers_s": k_qry_all / (ms_query * 1e-3) / 1e9, "kmers_per_step": (k_ins_all + k_qry_all) / S,
-            # `roofline` is the phase that dominates the step (the query, ~3/4 of it); the build and the whole step follow
-            "roofline": roof_q, "roofline_build": roof, "roofline_step": roof_step,
-            "gpu_launches": launches_all, "clocks": clocks}
-    if miss:
-        line["query_miss_set"] = miss
-    if e2e:
-        line["e2e"] = {"value": e2e["kmers"] / e2e["seconds"] / 1e9, "unit": "Gk-mer/s", "steps": e2e["steps"],
-                       "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                       "api": "btlbf_insert_seqs_async + btlbf_contains_seqs_async (streaming), pinned host buffers"}
-        line["e2e_sync"] = {"value": e2e["kmers_sync"] / e2e["seconds_sync"] / 1e9, "unit": "Gk-mer/s",
-                            "steps": e2e["steps_sync"], "api": "btlbf_insert_seqs + btlbf_contains_seqs (blocking)"}
-    if merge:
-        line["merge"] = merge
-    if numa:
-        line["config"]["host_numa_binding"] = numa
+    line = run_config(env, args.config, cfg, S, W, headline=True)
+    head = {"metric": "k-mers/s inserted+queried", "value": line.pop("value"), "unit": line.pop("unit"), "n_gpus": world,
+            "steps": S, "warmup": W, "ms_per_step": line.pop("ms_per_step"), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config}
+    for key in ("workload", "k", "hashes", "filter_bytes", "steps", "warmup"):
+        line.pop(key, None)
+    head.update(line)
+    if env.numa:
+        head["config"]["host_numa_binding"] = env.numa
     if world == 1 and not args.no_cpu_baseline:
-        cb = cpu_reference_run(2, 1, args.cpu_sample)
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "insert_gkmers_s",
-                                                   "query_gkmers_s")}
-    print(json.dumps(line))
+        cb = cpu_reference_run(cfg, 2, 1, args.cpu_sample, HOST_THREADS)
+        head["cpu_baseline"] = {key: cb[key] for key in ("value", "unit", "cores", "kind", "sample", "insert_gkmers_s",
+                                                         "query_gkmers_s", "unavailable") if key in cb}
+
+    # ---- the other BASELINE configs, same loop, fewer steps
+    if args.config == "cfg2" and not args.no_configs:
+        head["configs"] = {}
+        for name in [n for n in args.configs.split(",") if n in CONFIGS and n != args.config]:
+            c = CONFIGS[name]
+            try:
+                r = run_config(env, name, c, max(1, min(S, args.config_steps)), min(W, 3), headline=False)
+            except Exception as e:  # noqa: BLE001  (a config that fails must not take the headline line with it)
+                r = {"workload": c["workload"], "error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+            if world == 1 and not args.no_cpu_baseline and "error" not in r:
+                if c["kind"] == "counting":
+                    # the exact oracle of the counting build is the single-threaded loop; N threads race (throughput only)
+                    one = cpu_reference_run(c, 1, 0, 1 << 20, 1)
+                    r["cpu_baseline_1thread"] = {key: one[key] for key in ("value", "unit", "cores", "kind", "sample",
+                                                                          "insert_gkmers_s", "query_gkmers_s", "unavailable") if key in one}
+                cb = cpu_reference_run(c, 1, 1, args.cpu_sample, HOST_THREADS)
+                r["cpu_baseline"] = {key: cb[key] for key in ("value", "unit", "cores", "kind", "sample", "insert_gkmers_s",
+                                                              "query_gkmers_s", "unavailable") if key in cb}
+            head["configs"][name] = r
+    if rank == 0:
+        print(json.dumps(head))
     if world > 1:
         dist.destroy_process_group()
 

@@ -74,6 +74,8 @@ SIGNATURES = {
     "btlbf_filter_load": [vp, C.c_char_p, C.c_int, u32, C.POINTER(vp), C.POINTER(C.c_double), u64p, u64p],
     "btlbf_format_header": [C.c_int, u64, u64, u32, u32, C.c_double, u64, u64, C.c_char_p, C.c_size_t,
                             C.POINTER(C.c_size_t)],
+    "btlbf_parse_header": [C.c_int, C.c_char_p, C.c_size_t, u64p, u64p, C.POINTER(u32), C.POINTER(u32),
+                           C.POINTER(C.c_double), u64p, u64p, C.POINTER(C.c_size_t)],
     "btlbf_insert_seqs_dev": [vp, vp, u64, vp, u64, vp],
     "btlbf_contains_seqs_dev": [vp, vp, u64, vp, u64, vp, vp, vp],
     "btlbf_mincount_seqs_dev": [vp, vp, u64, vp, u64, vp, vp, vp],

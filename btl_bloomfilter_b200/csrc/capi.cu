@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -78,7 +79,15 @@ struct HashCfg // everything the kernels need to turn a window into its hashes
 
 struct btlbf_ctx
 {
+	// One lock per context: every entry point that touches the context (or a filter of it) holds it for the
+	// duration of the call, so the handles may be shared between host threads (the reference's insert is
+	// thread-safe by atomics, BloomFilter.hpp:171-194, and its OpenMP driver calls it concurrently,
+	// Tests/AdHoc/ParallelFilter.cpp:104-122).  Recursive: entry points call each other.
+	std::recursive_mutex mu;
 	int device = 0;
+	cudaEvent_t ev_switch = nullptr;  // orders a newly selected active stream after the old one
+	btlbf_filter* hq_owner = nullptr; // filter whose per-k-mer queue (legacy interface) holds unapplied updates
+	bool in_hq_flush = false;
 	cudaStream_t own = nullptr, active = nullptr, copy_in = nullptr, copy_out = nullptr;
 	// Background stream: pass 2 of the partitioned build (memory-bound) runs here, concurrently with
 	// whatever the active stream does next (typically the compute-bound pass 1 of the following batch).
@@ -105,7 +114,16 @@ struct btlbf_ctx
 	Slot slot[2];
 	Ticket ticket[kTickets];
 	uint64_t slot_seq = 0, ticket_seq = 0;
-	DevBuf ibin_items[2], ibin_counts[2], qbin_items, qbin_counts, q_hit, q_valid;
+	DevBuf ibin_items[2], ibin_counts[2], qbin_items[2], qbin_counts[2], q_hit, q_valid;
+	// The partitioned query runs in sub-batches: pass 1 (hash + bin, issue-bound) of sub-batch i+1 on the active
+	// stream shares the SMs with pass 2 (probe, L2-bound) of sub-batch i on the background stream.
+	cudaEvent_t ev_qp1[2] = { nullptr, nullptr }, ev_qp2[2] = { nullptr, nullptr };
+	bool qslot_used[2] = { false, false };
+	int64_t query_sub = 0;          // sub-batches per partitioned query (0 auto, 1: no overlap)
+	int64_t query_p1_ctas = 0;      // pass-1 CTAs per SM while overlapping (0 auto: one fewer than fit)
+	int64_t query_probe_unroll = 0; // item vectors in flight per thread of pass 2 (0 auto)
+	int64_t bin_wide_query = 0;     // 1: the auto rule also takes the partitioned query when the partitions had to be widened
+	int64_t bin_prefetch = -1;      // pass 2 pulls the next partition into L2: -1 auto (partitions up to 16 MiB), 0, 1
 	DevBuf ibin2_items, ibin2_counts; // level-2 buckets of the two-level pass 2 (apply2.cu)
 	int64_t bin_two_level = 0;        // 1: two-level pass 2 (apply2.cu); measured slower than the L2-atomics pass on B200
 	int64_t bin_two_level_min = (int64_t)1 << 26; // items below which the one-level pass is used
@@ -154,9 +172,19 @@ struct btlbf_filter
 	uint32_t epoch = 0;
 	uint32_t* d_ord = nullptr; // device words of the cooperative path: [0..1] list counters, [2] epoch, [3] rounds, [4] deferred
 	uint64_t deferred_total = 0, rounds_total = 0;
+	bool wrapped = false; // caller-owned memory: nothing is ever left parked when a call returns
+	// Queue of the legacy per-k-mer interface: updates that return nothing (insert / incrementAll / incrementMin
+	// without `found`) are collected in pinned host memory and applied by one kernel per kHashQueue k-mers, or as
+	// soon as anything reads or writes the filter (joined()).  Order inside the queue is the call order.
+	uint64_t* hq = nullptr; // pinned: hq_n x h hash values
+	uint64_t hq_n = 0;
+	int hq_op = -1;
 };
+constexpr uint64_t kHashQueue = 1u << 16;
 
 // ---------------------------------------------------------------- small helpers
+#define LOCKED(ctx) std::lock_guard<std::recursive_mutex> lock_((ctx)->mu)
+
 static int use(btlbf_ctx* ctx)
 {
 	if (!ctx)
@@ -168,16 +196,34 @@ static int use(btlbf_ctx* ctx)
 // The active stream, ordered after all background (aux-stream) work: every operation that reads or
 // writes filter contents on the active stream goes through this.
 static int settle(btlbf_ctx* ctx);
+static int hq_flush(btlbf_ctx* ctx);
 
 static cudaStream_t joined(btlbf_ctx* ctx)
 {
+	if (ctx->hq_owner && !ctx->in_hq_flush) {
+		int rc = hq_flush(ctx);
+		if (rc != BTLBF_OK && !ctx->settle_error)
+			ctx->settle_error = rc;
+	}
 	if (ctx->acc.f)
-		settle(ctx);
+		settle(ctx); // a failure is kept in ctx->settle_error
 	if (ctx->aux_pending) {
-		cudaStreamWaitEvent(ctx->active, ctx->ev_aux_last, 0);
+		cudaError_t e = cudaStreamWaitEvent(ctx->active, ctx->ev_aux_last, 0);
+		if (e != cudaSuccess && !ctx->settle_error)
+			ctx->settle_error = BTLBF_ERR_CUDA;
 		ctx->aux_pending = false;
 	}
 	return ctx->active;
+}
+
+static int take_settle_error(btlbf_ctx* ctx);
+
+// joined() for entry points that report: the deferred work is queued on *s, or the call fails with the
+// reason the deferred pass could not be launched (the parked k-mers are lost in that case)
+static int join(btlbf_ctx* ctx, cudaStream_t* s)
+{
+	*s = joined(ctx);
+	return take_settle_error(ctx);
 }
 
 static int ensure(DevBuf& b, size_t bytes)
@@ -321,10 +367,16 @@ extern "C" int btlbf_ctx_create(int device, btlbf_ctx** out)
 		e = cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking);
 	if (e == cudaSuccess)
 		e = cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking);
+	if (e == cudaSuccess)
+		e = cudaEventCreateWithFlags(&ctx->ev_switch, cudaEventDisableTiming);
 	for (int i = 0; i < 2 && e == cudaSuccess; i++) {
 		e = cudaEventCreateWithFlags(&ctx->ev_bin_done[i], cudaEventDisableTiming);
 		if (e == cudaSuccess)
 			e = cudaEventCreateWithFlags(&ctx->ev_apply_done[i], cudaEventDisableTiming);
+		if (e == cudaSuccess)
+			e = cudaEventCreateWithFlags(&ctx->ev_qp1[i], cudaEventDisableTiming);
+		if (e == cudaSuccess)
+			e = cudaEventCreateWithFlags(&ctx->ev_qp2[i], cudaEventDisableTiming);
 	}
 	if (e == cudaSuccess)
 		e = cudaMalloc(&ctx->d_scalars, 16 * sizeof(unsigned long long));
@@ -376,12 +428,15 @@ extern "C" int btlbf_ctx_destroy(btlbf_ctx* ctx)
 		release(ctx->ibin_counts[i]);
 		if (ctx->ev_bin_done[i]) cudaEventDestroy(ctx->ev_bin_done[i]);
 		if (ctx->ev_apply_done[i]) cudaEventDestroy(ctx->ev_apply_done[i]);
+		if (ctx->ev_qp1[i]) cudaEventDestroy(ctx->ev_qp1[i]);
+		if (ctx->ev_qp2[i]) cudaEventDestroy(ctx->ev_qp2[i]);
+		release(ctx->qbin_items[i]);
+		release(ctx->qbin_counts[i]);
 	}
-	release(ctx->qbin_items);
-	release(ctx->qbin_counts);
 	release(ctx->ibin2_items);
 	release(ctx->ibin2_counts);
 	if (ctx->aux) cudaStreamDestroy(ctx->aux);
+	if (ctx->ev_switch) cudaEventDestroy(ctx->ev_switch);
 	release(ctx->q_hit);
 	release(ctx->q_valid);
 	if (ctx->d_scalars) cudaFree(ctx->d_scalars);
@@ -396,19 +451,26 @@ extern "C" int btlbf_ctx_destroy(btlbf_ctx* ctx)
 extern "C" int btlbf_ctx_set_stream(btlbf_ctx* ctx, void* cuda_stream)
 {
 	TRY(use(ctx));
+	LOCKED(ctx);
 	cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own;
 	if (ctx->aux_pending) // both the old and the new stream are ordered after the background work
 		CU(cudaStreamWaitEvent(next, ctx->ev_aux_last, 0));
-	joined(ctx);
+	// Everything queued so far -- including the deferred pass 2 of a partitioned build, which joined() launches on
+	// the OLD stream right here -- happens before anything the caller queues on the new stream.
+	cudaStream_t prev;
+	TRY(join(ctx, &prev));
+	if (next != prev) {
+		CU(cudaEventRecord(ctx->ev_switch, prev));
+		CU(cudaStreamWaitEvent(next, ctx->ev_switch, 0));
+	}
 	ctx->active = next;
 	return BTLBF_OK;
 }
 
-static int take_settle_error(btlbf_ctx* ctx);
-
 extern "C" int btlbf_ctx_sync(btlbf_ctx* ctx)
 {
 	TRY(use(ctx));
+	LOCKED(ctx);
 	CU(cudaStreamSynchronize(ctx->copy_in));
 	CU(cudaStreamSynchronize(joined(ctx)));
 	CU(cudaStreamSynchronize(ctx->copy_out));
@@ -428,6 +490,7 @@ static int take_settle_error(btlbf_ctx* ctx)
 extern "C" int btlbf_ctx_flush(btlbf_ctx* ctx)
 {
 	TRY(use(ctx));
+	LOCKED(ctx);
 	joined(ctx);
 	return take_settle_error(ctx);
 }
@@ -465,6 +528,7 @@ extern "C" int btlbf_ctx_set_option(btlbf_ctx* ctx, const char* key, int64_t val
 {
 	if (!ctx || !key)
 		return fail(BTLBF_ERR_ARG, "null argument");
+	LOCKED(ctx);
 	std::string k(key);
 	if (k == "force_generic")
 		ctx->force_generic = value != 0;
@@ -537,6 +601,24 @@ extern "C" int btlbf_ctx_set_option(btlbf_ctx* ctx, const char* key, int64_t val
 		if (value < 1 || value > 16)
 			return fail(BTLBF_ERR_ARG, "query_chunk_factor out of range [1,16]");
 		ctx->query_chunk_factor = value;
+	} else if (k == "query_sub") {
+		if (value < 0 || value > 64)
+			return fail(BTLBF_ERR_ARG, "query_sub out of range [0,64]");
+		ctx->query_sub = value;
+	} else if (k == "query_p1_ctas") {
+		if (value < 0 || value > 32)
+			return fail(BTLBF_ERR_ARG, "query_p1_ctas out of range [0,32]");
+		ctx->query_p1_ctas = value;
+	} else if (k == "query_probe_unroll") {
+		if (value != 0 && value != 1 && value != 2 && value != 4)
+			return fail(BTLBF_ERR_ARG, "query_probe_unroll must be 0, 1, 2 or 4");
+		ctx->query_probe_unroll = value;
+	} else if (k == "bin_wide_query") {
+		ctx->bin_wide_query = value != 0;
+	} else if (k == "bin_prefetch") {
+		if (value < -1 || value > 1)
+			return fail(BTLBF_ERR_ARG, "bin_prefetch must be -1, 0 or 1");
+		ctx->bin_prefetch = value;
 	} else if (k == "bin_two_level") {
 		ctx->bin_two_level = value != 0;
 	} else if (k == "bin_two_level_min") {
@@ -566,6 +648,7 @@ static int filter_make(btlbf_ctx* ctx, int kind, uint64_t size, unsigned h, unsi
 		return fail(BTLBF_ERR_ARG, "null argument");
 	*out = nullptr;
 	TRY(use(ctx));
+	LOCKED(ctx);
 	if (kind != BTLBF_BLOOM && kind != BTLBF_COUNTING8 && kind != BTLBF_BITVECTOR)
 		return fail(BTLBF_ERR_ARG, "unknown filter kind %d", kind);
 	if (size == 0)
@@ -599,6 +682,7 @@ static int filter_make(btlbf_ctx* ctx, int kind, uint64_t size, unsigned h, unsi
 		f->d_data = (uint8_t*)wrap_ptr;
 		f->cap = wrap_cap;
 		f->owned = false;
+		f->wrapped = true;
 	} else {
 		cudaError_t e = cudaMalloc(&f->d_data, need);
 		if (e == cudaSuccess)
@@ -633,9 +717,15 @@ extern "C" int btlbf_filter_destroy(btlbf_filter* f)
 {
 	if (!f)
 		return BTLBF_OK;
+	btlbf_ctx* ctx = f->ctx;
+	LOCKED(ctx);
 	cudaSetDevice(f->ctx->device);
 	if (f->ctx->acc.f == f)
 		f->ctx->acc.f = nullptr; // parked k-mers of a filter that is going away
+	if (ctx->hq_owner == f)
+		ctx->hq_owner = nullptr;
+	if (f->hq)
+		cudaFreeHost(f->hq);
 	cudaStreamSynchronize(joined(f->ctx));
 	if (f->owned && f->d_data)
 		cudaFree(f->d_data);
@@ -656,9 +746,16 @@ extern "C" int btlbf_filter_clear(btlbf_filter* f)
 	if (!f)
 		return fail(BTLBF_ERR_ARG, "null filter");
 	TRY(use(f->ctx));
+	LOCKED(f->ctx);
 	if (f->ctx->acc.f == f)
 		f->ctx->acc.f = nullptr; // k-mers still parked in the partition buckets vanish with the rest
-	CU(cudaMemsetAsync(f->d_data, 0, (f->bytes + 15) / 16 * 16, joined(f->ctx)));
+	if (f->ctx->hq_owner == f) { // ... and so do queued per-k-mer updates
+		f->ctx->hq_owner = nullptr;
+		f->hq_n = 0;
+	}
+	cudaStream_t s;
+	TRY(join(f->ctx, &s));
+	CU(cudaMemsetAsync(f->d_data, 0, (f->bytes + 15) / 16 * 16, s));
 	return BTLBF_OK;
 }
 
@@ -692,9 +789,16 @@ extern "C" int btlbf_filter_upload(btlbf_filter* f, const void* host, uint64_t n
 		return fail(BTLBF_ERR_ARG, "upload of %llu bytes into a %llu-byte filter", (unsigned long long)nbytes,
 		            (unsigned long long)f->bytes);
 	TRY(use(f->ctx));
+	LOCKED(f->ctx);
 	if (f->ctx->acc.f == f)
 		f->ctx->acc.f = nullptr; // overwritten anyway
-	CU(cudaMemcpyAsync(f->d_data, host, nbytes, cudaMemcpyHostToDevice, joined(f->ctx)));
+	if (f->ctx->hq_owner == f) {
+		f->ctx->hq_owner = nullptr;
+		f->hq_n = 0;
+	}
+	cudaStream_t s;
+	TRY(join(f->ctx, &s));
+	CU(cudaMemcpyAsync(f->d_data, host, nbytes, cudaMemcpyHostToDevice, s));
 	uint64_t pad = (f->bytes + 15) / 16 * 16 - f->bytes;
 	if (pad)
 		CU(cudaMemsetAsync(f->d_data + f->bytes, 0, pad, f->ctx->active));
@@ -710,8 +814,11 @@ extern "C" int btlbf_filter_download(btlbf_filter* f, void* host, uint64_t nbyte
 		return fail(BTLBF_ERR_ARG, "download of %llu bytes from a %llu-byte filter", (unsigned long long)nbytes,
 		            (unsigned long long)f->bytes);
 	TRY(use(f->ctx));
-	CU(cudaMemcpyAsync(host, f->d_data, nbytes, cudaMemcpyDeviceToHost, joined(f->ctx)));
-	CU(cudaStreamSynchronize(f->ctx->active));
+	LOCKED(f->ctx);
+	cudaStream_t s;
+	TRY(join(f->ctx, &s));
+	CU(cudaMemcpyAsync(host, f->d_data, nbytes, cudaMemcpyDeviceToHost, s));
+	CU(cudaStreamSynchronize(s));
 	return BTLBF_OK;
 }
 
@@ -719,9 +826,11 @@ extern "C" int btlbf_filter_device_ptr(btlbf_filter* f, void** device_ptr, uint6
 {
 	if (!f)
 		return fail(BTLBF_ERR_ARG, "null filter");
-	if (f->ctx->acc.f == f || f->ctx->aux_pending) { // parked k-mers reach the filter now, in stream order
+	LOCKED(f->ctx);
+	if (f->ctx->acc.f == f || f->ctx->aux_pending || f->ctx->hq_owner == f) { // parked k-mers reach the filter now, in stream order
 		TRY(use(f->ctx));
-		joined(f->ctx);
+		cudaStream_t s;
+		TRY(join(f->ctx, &s));
 	}
 	if (device_ptr) *device_ptr = f->d_data;
 	if (nbytes) *nbytes = f->bytes;
@@ -734,7 +843,10 @@ static int reduce_count(btlbf_filter* f, int mode, unsigned threshold, uint64_t*
 		return fail(BTLBF_ERR_ARG, "null argument");
 	btlbf_ctx* ctx = f->ctx;
 	TRY(use(ctx));
-	CU(cudaMemsetAsync(ctx->d_scalars + 2, 0, 8, joined(ctx)));
+	LOCKED(ctx);
+	cudaStream_t s0;
+	TRY(join(ctx, &s0));
+	CU(cudaMemsetAsync(ctx->d_scalars + 2, 0, 8, s0));
 	cudaError_t e = launch_popcount(f->d_data, f->bytes, mode, threshold, ctx->d_scalars + 2, ctx->active);
 	if (e != cudaSuccess)
 		return fail(BTLBF_ERR_CUDA, "popcount launch failed: %s", cudaGetErrorString(e));
@@ -774,7 +886,12 @@ extern "C" int btlbf_filter_set_seeds(btlbf_filter* f, const char* const* seeds,
 	if (!f)
 		return fail(BTLBF_ERR_ARG, "null filter");
 	TRY(use(f->ctx));
-	CU(cudaStreamSynchronize(f->ctx->active));
+	LOCKED(f->ctx);
+	{
+		cudaStream_t s; // parked / queued k-mers were hashed (or will be applied) under the old seeds
+		TRY(join(f->ctx, &s));
+		CU(cudaStreamSynchronize(s));
+	}
 	unsigned k = f->hc.k, h = f->hc.h;
 	if (n_seeds == 0)
 		return hashcfg_init(f->hc, k, h, nullptr, 0, 0);
@@ -801,7 +918,10 @@ extern "C" int btlbf_filter_merge_from_device(btlbf_filter* f, const void* src_d
 	if ((uintptr_t)src_device & 15u)
 		return fail(BTLBF_ERR_ARG, "merge source must be 16-byte aligned");
 	TRY(use(f->ctx));
-	cudaError_t e = launch_merge(f->d_data, src_device, nbytes, f->kind == BTLBF_COUNTING8, joined(f->ctx));
+	LOCKED(f->ctx);
+	cudaStream_t s;
+	TRY(join(f->ctx, &s));
+	cudaError_t e = launch_merge(f->d_data, src_device, nbytes, f->kind == BTLBF_COUNTING8, s);
 	if (e != cudaSuccess)
 		return fail(BTLBF_ERR_CUDA, "merge launch failed: %s", cudaGetErrorString(e));
 	f->ctx->launches++;
@@ -818,7 +938,10 @@ extern "C" int btlbf_merge_device_buffers(btlbf_ctx* ctx, int kind, void* dst_de
 		return fail(BTLBF_ERR_ARG, "null argument");
 	if (((uintptr_t)dst_device | (uintptr_t)src_device) & 15u)
 		return fail(BTLBF_ERR_ARG, "merge buffers must be 16-byte aligned");
-	cudaError_t e = launch_merge(dst_device, src_device, nbytes, kind == BTLBF_COUNTING8, joined(ctx));
+	LOCKED(ctx);
+	cudaStream_t s;
+	TRY(join(ctx, &s));
+	cudaError_t e = launch_merge(dst_device, src_device, nbytes, kind == BTLBF_COUNTING8, s);
 	if (e != cudaSuccess)
 		return fail(BTLBF_ERR_CUDA, "merge launch failed: %s", cudaGetErrorString(e));
 	ctx->launches++;
@@ -845,6 +968,7 @@ extern "C" int btlbf_ipc_export(btlbf_ctx* ctx, const void* device_ptr, void* ha
 	if (!device_ptr || !handle64 || !offset)
 		return fail(BTLBF_ERR_ARG, "null argument");
 	TRY(use(ctx));
+	LOCKED(ctx);
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
 	// the handle names a whole cudaMalloc allocation: find its base (the pointer may sit inside a block of
 	// a caching allocator)
@@ -897,6 +1021,7 @@ extern "C" int btlbf_merge_peers(btlbf_ctx* ctx, int kind, void* const* bases, i
 	if (kind != BTLBF_BLOOM && kind != BTLBF_COUNTING8)
 		return fail(BTLBF_ERR_ARG, "bad filter kind");
 	TRY(use(ctx));
+	LOCKED(ctx);
 	PeerMergeParams M;
 	memset(&M, 0, sizeof M);
 	// start with the local copy, then the peers in ring order so that the ranks do not all hit one GPU at once
@@ -912,7 +1037,9 @@ extern "C" int btlbf_merge_peers(btlbf_ctx* ctx, int kind, void* const* bases, i
 	M.grid = (uint32_t)ctx->peer_grid;
 	M.mode = (uint32_t)ctx->peer_mode;
 	TRY(btlbf_merge_slice(nbytes, world, rank, &M.lo, &M.hi));
-	cudaError_t e = launch_peer_merge(M, joined(ctx));
+	cudaStream_t s;
+	TRY(join(ctx, &s));
+	cudaError_t e = launch_peer_merge(M, s);
 	if (e != cudaSuccess)
 		return fail(BTLBF_ERR_CUDA, "peer merge launch failed: %s", cudaGetErrorString(e));
 	ctx->launches++;
@@ -1120,7 +1247,8 @@ static bool bin_geometry(const btlbf_filter* f, const SeqParams& P, uint32_t* sh
 {
 	const btlbf_ctx* ctx = f->ctx;
 	auto parts_at = [&](uint32_t sh) { return (f->size + (((uint64_t)1 << sh) - 1)) >> sh; };
-	uint32_t shift = (uint32_t)ctx->bin_part_log2;
+	// bin_part_log2 is in bits; a counting filter's partition of the same byte size holds 2^(log2 - 3) counters
+	uint32_t shift = (uint32_t)(f->kind == BTLBF_COUNTING8 ? (ctx->bin_part_log2 > 11 ? ctx->bin_part_log2 - 3 : 8) : ctx->bin_part_log2);
 	while (parts_at(shift) > 4096 && shift < 31)
 		shift++;
 	if (parts_at(shift) > 4096)
@@ -1154,6 +1282,11 @@ static int bin_setup(btlbf_filter* f, SeqParams& P, bool query, uint64_t capacit
 	P.n_bins = (uint32_t)n_bins;
 	P.bin_shift = shift;
 	P.bin_mask = (uint32_t)(((uint64_t)1 << shift) - 1);
+	{
+		// prefetching the next partition pays while two partitions (plus the item stream) stay resident in L2
+		const uint64_t part_bytes = f->kind == BTLBF_COUNTING8 ? (uint64_t)1 << shift : ((uint64_t)1 << shift) >> 3;
+		P.bin_prefetch = ctx->bin_prefetch < 0 ? part_bytes <= ((uint64_t)16 << 20) : ctx->bin_prefetch != 0;
+	}
 	uint32_t writers = 0;
 	cudaError_t e = bin_plan(P, P.n_bins, query, &writers, grid, mode);
 	if (e != cudaSuccess)
@@ -1330,11 +1463,16 @@ static int binned_insert(btlbf_filter* f, SeqParams P, cudaStream_t s)
 }
 
 // Partitioned query: bin (offset, window) pairs by filter partition, test them while the partition is
-// resident in L2, clear the hit bit of every window with a missing bit.  Same booleans as the direct path.
+// resident in L2, clear the hit bit of every window with a missing bit (BloomFilter) or a counter below the
+// threshold (CountingBloomFilter::contains).  Same booleans as the direct path.
 static bool want_binned_query(const btlbf_filter* f, const SeqParams& P)
 {
 	const btlbf_ctx* ctx = f->ctx;
-	if (ctx->bin_query_mode < 0 || f->kind != BTLBF_BLOOM || P.n_windows > 0xffffffffULL)
+	if (ctx->bin_query_mode < 0 || P.n_windows > 0xffffffffULL)
+		return false;
+	if (f->kind == BTLBF_COUNTING8 && (P.counts || P.threshold == 0 || P.threshold > 255))
+		return false; // per-window minima need the gather kernel; threshold 0 / > 255 are constant answers there
+	if (!P.hit_bits && !P.stats)
 		return false;
 	if (((uintptr_t)P.hit_bits | (uintptr_t)P.valid_bits) & 3u)
 		return false;
@@ -1347,7 +1485,8 @@ static bool want_binned_query(const btlbf_filter* f, const SeqParams& P)
 		return true;
 	// auto: not for filters so large that the partitions had to be widened beyond what stays resident in L2 next
 	// to the prefetched one (measured on a 16 GiB filter: 17 Gk-mer/s partitioned against 22 direct)
-	if (shift > (uint32_t)ctx->bin_part_log2)
+	const uint32_t base_shift = (uint32_t)(f->kind == BTLBF_COUNTING8 ? ctx->bin_part_log2 - 3 : ctx->bin_part_log2);
+	if (shift > base_shift && !ctx->bin_wide_query)
 		return false;
 	return f->bytes >= ((uint64_t)96 << 20) && P.n_windows * P.h >= f->bytes / 64;
 }
@@ -1355,10 +1494,63 @@ static bool want_binned_query(const btlbf_filter* f, const SeqParams& P)
 static int binned_query(btlbf_filter* f, SeqParams P, cudaStream_t s)
 {
 	btlbf_ctx* ctx = f->ctx;
+	const bool counting = f->kind == BTLBF_COUNTING8;
+	{
+		cudaStream_t js; // parked k-mers first: the probes (and pass 1's overflow path) read the filter
+		TRY(join(ctx, &js));
+	}
+	// ---- how many pass-1 CTAs fit on an SM for this shape (0: not the sort-bin kernel)
+	int64_t fit = 0;
+	{
+		SeqParams T = P;
+		T.bin_legacy = (uint32_t)ctx->bin_kernel;
+		T.bin_ctas_per_sm = 0;
+		T.n_windows = ~0ull >> 8;
+		uint32_t w = 0, g = 0, shift = 0;
+		int m = 0;
+		if (bin_geometry(f, T, &shift)) {
+			const uint32_t nb = (uint32_t)((f->size + (((uint64_t)1 << shift) - 1)) >> shift);
+			if (bin_plan(T, nb, true, &w, &g, &m) == cudaSuccess && m == BIN_SORT) {
+				int dev = 0, sms = 1;
+				cudaGetDevice(&dev);
+				cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+				fit = w / (uint32_t)sms;
+			}
+		}
+	}
+	// ---- sub-batches: windows [c0, c0 + sub) of the chunk, whole 16384-window tiles (both CTA shapes, whole
+	// result words).  Overlapping needs the sort-bin kernel in the shape that leaves an SM room for the probe kernel.
+	uint64_t n_sub = (uint64_t)ctx->query_sub;
+	if (fit == 0 || (n_sub == 0 && fit < 3))
+		n_sub = 1;
+	if (n_sub == 0)
+		n_sub = P.n_windows >= ((uint64_t)96 << 20) ? 4 : P.n_windows >= ((uint64_t)24 << 20) ? 2 : 1;
+	const uint64_t kAlign = 16384;
+	uint64_t sub = ((P.n_windows + n_sub - 1) / n_sub + kAlign - 1) / kAlign * kAlign;
+	n_sub = (P.n_windows + sub - 1) / sub;
+	const bool overlap = n_sub > 1;
+
+	SeqParams G = P; // geometry for one sub-batch
+	G.n_windows = sub < P.n_windows ? sub : P.n_windows;
 	uint32_t grid = 0;
 	int mode = 0;
-	joined(ctx); // parked k-mers first: the probes (and pass 1's overflow path) read the filter
-	TRY(bin_setup(f, P, true, P.n_windows, &grid, &mode, ctx->qbin_items, ctx->qbin_counts));
+	if (overlap) {
+		// pass 1 leaves room on every SM for the probe kernel of the previous sub-batch
+		int64_t ctas = ctx->query_p1_ctas;
+		if (ctas == 0)
+			ctas = fit > 1 ? fit - 1 : 1;
+		G.bin_ctas_per_sm = (uint32_t)ctas;
+	}
+	TRY(bin_setup(f, G, true, G.n_windows, &grid, &mode, ctx->qbin_items[0], ctx->qbin_counts[0]));
+	const size_t item_bytes = (size_t)G.n_bins * G.bin_writers * G.bin_cap * 8, count_bytes = (size_t)G.n_bins * G.bin_writers * 4;
+	if (overlap) {
+		if (item_bytes > ctx->qbin_items[1].cap || count_bytes > ctx->qbin_counts[1].cap) {
+			CU(cudaStreamSynchronize(ctx->aux));
+			CU(cudaStreamSynchronize(ctx->active));
+		}
+		TRY(ensure(ctx->qbin_items[1], item_bytes));
+		TRY(ensure(ctx->qbin_counts[1], count_bytes));
+	}
 	const uint64_t words = P.out_words;
 	if (!P.hit_bits) {
 		TRY(ensure(ctx->q_hit, words * 4));
@@ -1376,9 +1568,10 @@ static int binned_query(btlbf_filter* f, SeqParams P, cudaStream_t s)
 	// Absent k-mers cost the early-exit kernel ~1/(1-occupancy) probes but the partitioned path all h of them
 	// (plus an atomic per missing bit), so read sets that mostly miss are faster on the direct kernel.
 	const uint64_t tiles = (P.n_windows + kTile - 1) / kTile;
-	const bool adaptive = ctx->query_adaptive && mode == BIN_SORT && tiles >= (uint64_t)ctx->query_adaptive_min_tiles &&
-	                      P.n_seeds == 0;
+	const bool adaptive = ctx->query_adaptive && !counting && mode == BIN_SORT &&
+	                      tiles >= (uint64_t)ctx->query_adaptive_min_tiles && P.n_seeds == 0;
 	CU(cudaMemsetAsync(P.hit_bits, 0xff, words * 4, s)); // the partitioned path clears the bits of missing k-mers
+	const uint32_t* gate = nullptr;
 	if (adaptive) {
 		unsigned long long* sample = ctx->d_scalars + 8; // [8] valid, [9] hits, [10] flag
 		uint32_t* flag = reinterpret_cast<uint32_t*>(ctx->d_scalars + 10);
@@ -1401,20 +1594,69 @@ static int binned_query(btlbf_filter* f, SeqParams P, cudaStream_t s)
 		D.tiles_per_cta = 8; // fewer CTAs to retire when the partitioned path is the one that runs
 		TRY(launch(ctx, OP_BF_CONTAINS, D, s));
 		ctx->launches++;
-		P.gate = flag;
-		P.gate_want = 0;
+		gate = flag;
 	}
-	if (mode == BIN_SORT)
-		CU(cudaMemsetAsync(P.bin_counts, 0, (size_t)P.n_bins * P.bin_writers * 4, s));
-	e = launch_bin(P, true, grid, s);
-	if (e == cudaSuccess)
-		e = launch_probe_bins(P, s);
-	if (e == cudaSuccess)
-		e = launch_finalize_hits(P.hit_bits, P.valid_bits, words, stats ? (unsigned long long*)(stats + 1) : nullptr, P.gate,
-		                         P.gate_want, s);
+	int unroll = (int)ctx->query_probe_unroll;
+	if (unroll == 0)
+		unroll = overlap ? 4 : 1;
+	for (uint64_t i = 0, c0 = 0; c0 < P.n_windows; i++, c0 += sub) {
+		const int b = overlap ? (int)(i & 1) : 0;
+		SeqParams Q = G;
+		Q.bases = P.bases + c0;
+		Q.n_bases = P.n_bases > c0 ? P.n_bases - c0 : 0;
+		Q.base0 = P.base0 + c0;
+		Q.n_windows = P.n_windows - c0 < sub ? P.n_windows - c0 : sub;
+		if (Q.n_bases > Q.n_windows + P.k - 1)
+			Q.n_bases = Q.n_windows + P.k - 1; // a sub-batch reads its windows + the k-1 halo, like a pipeline chunk
+		Q.hit_bits = P.hit_bits + (c0 >> 5);
+		Q.valid_bits = P.valid_bits + (c0 >> 5);
+		Q.out_words = words - (c0 >> 5);
+		Q.stats = stats;
+		Q.gate = gate;
+		Q.gate_want = 0;
+		Q.bin_items = (uint32_t*)ctx->qbin_items[b].p;
+		Q.bin_counts = (uint32_t*)ctx->qbin_counts[b].p;
+		// pass 1 on the active stream; the buffers are free once the probe kernel that last read them is done
+		if (overlap && ctx->qslot_used[b])
+			CU(cudaStreamWaitEvent(s, ctx->ev_qp2[b], 0));
+		if (mode == BIN_SORT)
+			CU(cudaMemsetAsync(Q.bin_counts, 0, count_bytes, s));
+		uint32_t g1 = grid;
+		if (mode != BIN_SORT) { // the general-shape kernels size their grid by the batch
+			uint32_t w = 0;
+			int m = 0;
+			if (bin_plan(Q, Q.n_bins, true, &w, &g1, &m) != cudaSuccess || w > Q.bin_writers)
+				g1 = grid;
+		}
+		e = launch_bin(Q, true, g1, s);
+		if (e != cudaSuccess)
+			return fail(BTLBF_ERR_CUDA, "partitioned query (pass 1) launch failed: %s", cudaGetErrorString(e));
+		// pass 2: on the background stream when overlapping
+		cudaStream_t s2 = s;
+		if (overlap) {
+			s2 = ctx->aux;
+			CU(cudaEventRecord(ctx->ev_qp1[b], s));
+			CU(cudaStreamWaitEvent(s2, ctx->ev_qp1[b], 0));
+		}
+		// the item words of a sub-batch carry window indices relative to the sub-batch
+		e = launch_probe_bins(Q, counting, unroll, s2);
+		if (e != cudaSuccess)
+			return fail(BTLBF_ERR_CUDA, "partitioned query (pass 2) launch failed: %s", cudaGetErrorString(e));
+		if (overlap) {
+			CU(cudaEventRecord(ctx->ev_qp2[b], s2));
+			ctx->qslot_used[b] = true;
+		}
+		ctx->launches += 2;
+	}
+	if (overlap) { // the results (and everything queued after this call) follow the last probes
+		CU(cudaStreamWaitEvent(s, ctx->ev_qp2[0], 0));
+		if (n_sub > 1)
+			CU(cudaStreamWaitEvent(s, ctx->ev_qp2[1], 0));
+	}
+	e = launch_finalize_hits(P.hit_bits, P.valid_bits, words, stats ? (unsigned long long*)(stats + 1) : nullptr, gate, 0, s);
 	if (e != cudaSuccess)
 		return fail(BTLBF_ERR_CUDA, "partitioned query launch failed: %s", cudaGetErrorString(e));
-	ctx->launches += 3;
+	ctx->launches++;
 	ctx->binned_launches++;
 	return BTLBF_OK;
 }
@@ -1460,10 +1702,12 @@ static int filter_op_dev(btlbf_filter* f, PublicOp op, const ChunkIO& io, cudaSt
 	SeqParams P = filter_params(f);
 	fill_io(P, io);
 	btlbf_ctx* ctx = f->ctx;
-	const bool binned = f->kind == BTLBF_BLOOM && P.n_windows &&
-	                    ((op == PUB_INSERT && want_binned(f, P)) || (op == PUB_CONTAINS && want_binned_query(f, P)));
-	if (!binned)
-		joined(ctx); // the direct kernels read / write the filter right away
+	const bool binned = P.n_windows && ((op == PUB_INSERT && f->kind == BTLBF_BLOOM && want_binned(f, P)) ||
+	                                    (op == PUB_CONTAINS && want_binned_query(f, P)));
+	if (!binned) { // the direct kernels read / write the filter right away
+		cudaStream_t js;
+		TRY(join(ctx, &js));
+	}
 	switch (op) {
 	case PUB_INSERT:
 		if (f->kind == BTLBF_BLOOM) {
@@ -1473,7 +1717,7 @@ static int filter_op_dev(btlbf_filter* f, PublicOp op, const ChunkIO& io, cudaSt
 		}
 		return ordered_apply(f, P, 0, s);
 	case PUB_CONTAINS:
-		if (f->kind == BTLBF_BLOOM && P.n_windows && want_binned_query(f, P))
+		if (P.n_windows && want_binned_query(f, P))
 			return binned_query(f, P, s);
 		return launch(ctx, f->kind == BTLBF_BLOOM ? OP_BF_CONTAINS : OP_CBF_MINCOUNT, P, s);
 	case PUB_INSERT_CHECK:
@@ -1489,6 +1733,15 @@ static int filter_op_dev(btlbf_filter* f, PublicOp op, const ChunkIO& io, cudaSt
 	default:
 		return fail(BTLBF_ERR_ARG, "bad operation");
 	}
+}
+
+// Caller-owned filter memory (btlbf_filter_wrap): the caller may read it on the active stream without going
+// through this library, so no k-mer stays parked in the partition buckets when a call returns.
+static int settle_if_wrapped(btlbf_filter* f)
+{
+	if (f->wrapped && f->ctx->acc.f == f)
+		return settle(f->ctx);
+	return BTLBF_OK;
 }
 
 static int check_dev_args(btlbf_filter* f, const void* d_bases, uint64_t n_bases, const uint64_t* d_offsets)
@@ -1512,7 +1765,9 @@ extern "C" int btlbf_insert_seqs_dev(btlbf_filter* f, const void* d_bases, uint6
 	io.d_offsets = d_offsets;
 	io.n_seqs = n_seqs;
 	io.d_stats = d_stats;
-	return filter_op_dev(f, PUB_INSERT, io, f->ctx->active);
+	LOCKED(f->ctx);
+	TRY(filter_op_dev(f, PUB_INSERT, io, f->ctx->active));
+	return settle_if_wrapped(f);
 }
 
 extern "C" int btlbf_contains_seqs_dev(btlbf_filter* f, const void* d_bases, uint64_t n_bases,
@@ -1528,6 +1783,7 @@ extern "C" int btlbf_contains_seqs_dev(btlbf_filter* f, const void* d_bases, uin
 	io.d_hit = d_hit_bits;
 	io.d_valid = d_valid_bits;
 	io.d_stats = d_stats;
+	LOCKED(f->ctx);
 	return filter_op_dev(f, PUB_CONTAINS, io, f->ctx->active);
 }
 
@@ -1544,6 +1800,7 @@ extern "C" int btlbf_mincount_seqs_dev(btlbf_filter* f, const void* d_bases, uin
 	io.d_counts = d_counts;
 	io.d_valid = d_valid_bits;
 	io.d_stats = d_stats;
+	LOCKED(f->ctx);
 	if (d_counts)
 		CU(cudaMemsetAsync(d_counts, 0, n_bases, f->ctx->active));
 	return filter_op_dev(f, PUB_MINCOUNT, io, f->ctx->active);
@@ -1583,6 +1840,7 @@ static int host_pipeline(btlbf_ctx* ctx, btlbf_filter* f, const HashCfg* hash_on
                          bool async = false, uint64_t* counts_out = nullptr)
 {
 	TRY(use(ctx));
+	LOCKED(ctx);
 	if (h.n_seqs && !h.offsets)
 		return fail(BTLBF_ERR_ARG, "null offsets");
 	if (h.n_kmers) *h.n_kmers = 0;
@@ -1696,6 +1954,8 @@ static int host_pipeline(btlbf_ctx* ctx, btlbf_filter* f, const HashCfg* hash_on
 			CU(cudaEventRecord(sl.ev_d2h, ctx->copy_out));
 			sl.used = true;
 		}
+		if (op == PUB_INSERT && f)
+			TRY(settle_if_wrapped(f));
 		// copy_out is ordered after the last kernel: the call's statistics follow its results
 		CU(cudaMemcpyAsync(async ? (void*)counts_out : (void*)ctx->h_scalars, tk.d_stats, 16, cudaMemcpyDeviceToHost,
 		                   ctx->copy_out));
@@ -1809,6 +2069,7 @@ extern "C" int btlbf_hash_seqs(btlbf_ctx* ctx, unsigned hash_num, unsigned kmer_
                                uint64_t* n_kmers)
 {
 	TRY(use(ctx));
+	LOCKED(ctx);
 	HashCfg hc;
 	int rc = hashcfg_init(hc, kmer_size, hash_num, n_seeds ? seeds : nullptr, n_seeds, h2);
 	if (rc == BTLBF_OK) {
@@ -1829,6 +2090,7 @@ extern "C" int btlbf_filter_ordered_stats(btlbf_filter* f, uint64_t* deferred, u
 	uint64_t d = f->deferred_total, r = f->rounds_total;
 	if (f->d_ord) { // the cooperative path keeps its counters on the device
 		TRY(use(f->ctx));
+		LOCKED(f->ctx);
 		uint32_t w[8];
 		CU(cudaStreamSynchronize(joined(f->ctx)));
 		CU(cudaMemcpy(w, f->d_ord, 32, cudaMemcpyDeviceToHost));
@@ -1844,6 +2106,7 @@ extern "C" int btlbf_filter_ordered_stats(btlbf_filter* f, uint64_t* deferred, u
 extern "C" int btlbf_synth_genome_dev(btlbf_ctx* ctx, void* d_out, uint64_t start, uint64_t n, uint64_t seed)
 {
 	TRY(use(ctx));
+	LOCKED(ctx);
 	if (n && !d_out)
 		return fail(BTLBF_ERR_ARG, "null output");
 	cudaError_t e = launch_synth_genome((uint8_t*)d_out, start, n, seed, ctx->active);
@@ -1858,6 +2121,7 @@ extern "C" int btlbf_synth_reads_dev(btlbf_ctx* ctx, void* d_out, uint64_t first
                                      uint64_t read_seed)
 {
 	TRY(use(ctx));
+	LOCKED(ctx);
 	if (n_reads && !d_out)
 		return fail(BTLBF_ERR_ARG, "null output");
 	if (read_len == 0 || g_len <= read_len)
@@ -1874,6 +2138,7 @@ extern "C" int btlbf_random_access_probe(btlbf_ctx* ctx, void* d_array, uint64_t
                                          float* elapsed_ms)
 {
 	TRY(use(ctx));
+	LOCKED(ctx);
 	if (!d_array || bytes < 4 || !elapsed_ms || (mode != 0 && mode != 1))
 		return fail(BTLBF_ERR_ARG, "bad probe arguments");
 	cudaEvent_t a, b;
@@ -1893,19 +2158,18 @@ extern "C" int btlbf_random_access_probe(btlbf_ctx* ctx, void* d_array, uint64_t
 }
 
 // ---------------------------------------------------------------- legacy per-k-mer interface (precomputed hashes)
-static int hashes_op(btlbf_filter* f, int op, const uint64_t* hashes, uint64_t n, uint8_t* out)
+// runs `op` over n k-mers whose hashes are in host memory; blocking
+static int hashes_run(btlbf_filter* f, int op, const uint64_t* hashes, uint64_t n, uint8_t* out)
 {
-	if (!f)
-		return fail(BTLBF_ERR_ARG, "null filter");
-	if (n == 0)
-		return BTLBF_OK;
-	if (!hashes)
-		return fail(BTLBF_ERR_ARG, "null hashes");
 	btlbf_ctx* ctx = f->ctx;
-	TRY(use(ctx));
-	cudaStream_t s = joined(ctx);
+	cudaStream_t s;
+	TRY(join(ctx, &s));
 	Slot& sl = ctx->slot[0];
 	uint32_t h = f->hc.h;
+	// slot 0 also serves the host-buffer pipeline: nothing of it may be in flight while its buffers are reused
+	CU(cudaStreamSynchronize(ctx->copy_in));
+	CU(cudaStreamSynchronize(s));
+	CU(cudaStreamSynchronize(ctx->copy_out));
 	TRY(ensure(sl.hashes, n * h * 8));
 	TRY(ensure(sl.counts, n));
 	CU(cudaMemcpyAsync(sl.hashes.p, hashes, n * h * 8, cudaMemcpyHostToDevice, s));
@@ -1918,6 +2182,54 @@ static int hashes_op(btlbf_filter* f, int op, const uint64_t* hashes, uint64_t n
 		CU(cudaMemcpyAsync(out, sl.counts.p, n, cudaMemcpyDeviceToHost, s));
 	CU(cudaStreamSynchronize(s));
 	return BTLBF_OK;
+}
+
+// applies the queued per-k-mer updates of ctx->hq_owner (joined() calls this before anything touches a filter)
+static int hq_flush(btlbf_ctx* ctx)
+{
+	btlbf_filter* f = ctx->hq_owner;
+	if (!f)
+		return BTLBF_OK;
+	ctx->hq_owner = nullptr;
+	const uint64_t n = f->hq_n;
+	f->hq_n = 0;
+	if (n == 0)
+		return BTLBF_OK;
+	ctx->in_hq_flush = true;
+	int rc = hashes_run(f, f->hq_op, f->hq, n, nullptr);
+	ctx->in_hq_flush = false;
+	return rc;
+}
+
+static int hashes_op(btlbf_filter* f, int op, const uint64_t* hashes, uint64_t n, uint8_t* out)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	if (n == 0)
+		return BTLBF_OK;
+	if (!hashes)
+		return fail(BTLBF_ERR_ARG, "null hashes");
+	btlbf_ctx* ctx = f->ctx;
+	TRY(use(ctx));
+	LOCKED(ctx);
+	const uint32_t h = f->hc.h;
+	// Updates that report nothing (a `while (itr != itr.end()) { bloom.insert(*itr); ++itr; }` loop, README.md:30-43,
+	// possibly from many OpenMP threads, ParallelFilter.cpp:104-122) are queued: one kernel per kHashQueue k-mers.
+	// The queue keeps call order, which is what the order-dependent incrementMin (op 3) needs.
+	if (!out && (op == 0 || op == 3 || op == 4) && n <= kHashQueue / 4) {
+		if (ctx->hq_owner && (ctx->hq_owner != f || f->hq_op != op || f->hq_n + n > kHashQueue))
+			TRY(hq_flush(ctx));
+		if (!f->hq)
+			CU(cudaHostAlloc(&f->hq, (size_t)kHashQueue * h * 8, cudaHostAllocDefault));
+		memcpy(f->hq + f->hq_n * h, hashes, n * h * 8);
+		f->hq_n += n;
+		f->hq_op = op;
+		ctx->hq_owner = f;
+		if (f->hq_n == kHashQueue)
+			TRY(hq_flush(ctx));
+		return BTLBF_OK;
+	}
+	return hashes_run(f, op, hashes, n, out);
 }
 
 extern "C" int btlbf_insert_hashes(btlbf_filter* f, const uint64_t* hashes, uint64_t n_kmers, uint8_t* found)
@@ -2020,16 +2332,20 @@ struct ParsedHeader
 
 // Mirrors loadHeader (BloomFilter.hpp:116-166, CountingBloomFilter.hpp:283-329): first line must be
 // "[magic]", lines are collected up to "[HeaderEnd]", and every key the reference dereferences must exist.
-static int parse_header(FILE* fp, int kind, ParsedHeader& H)
+// next(): the next byte of the header text, or EOF
+template<class Next>
+static int parse_header_from(Next&& next, int kind, ParsedHeader& H)
 {
 	const char* magic = kind == BTLBF_BLOOM ? "[BTLBloomFilter_v1]" : "[BTLCountingBloomFilter_v1]";
 	std::string line;
+	size_t consumed = 0;
 	auto getline = [&](std::string& out) -> bool {
 		out.clear();
 		int c;
 		bool any = false;
-		while ((c = fgetc(fp)) != EOF) {
+		while ((c = next()) != EOF) {
 			any = true;
+			consumed++;
 			if (c == '\n')
 				return true;
 			out.push_back((char)c);
@@ -2074,7 +2390,36 @@ static int parse_header(FILE* fp, int kind, ParsedHeader& H)
 	unsigned need = kind == BTLBF_BLOOM ? (1 | 2 | 4 | 8 | 16 | 32 | 64) : (1 | 2 | 4 | 8 | 128);
 	if ((H.seen & need) != need)
 		return fail(BTLBF_ERR_ARG, "filter header lacks a required key (mask %#x of %#x present)", H.seen & need, need);
-	H.body_offset = (size_t)ftell(fp);
+	H.body_offset = consumed;
+	return BTLBF_OK;
+}
+
+static int parse_header(FILE* fp, int kind, ParsedHeader& H)
+{
+	return parse_header_from([&]() { return fgetc(fp); }, kind, H);
+}
+
+extern "C" int btlbf_parse_header(int kind, const char* text, size_t len, uint64_t* size, uint64_t* size_bytes,
+                                  unsigned* hash_num, unsigned* kmer_size, double* dFPR, uint64_t* nEntry,
+                                  uint64_t* tEntry, size_t* header_len)
+{
+	if (kind != BTLBF_BLOOM && kind != BTLBF_COUNTING8)
+		return fail(BTLBF_ERR_ARG, "unknown filter kind %d", kind);
+	if (!text && len)
+		return fail(BTLBF_ERR_ARG, "null argument");
+	ParsedHeader H;
+	size_t at = 0;
+	TRY(parse_header_from([&]() { return at < len ? (int)(unsigned char)text[at++] : EOF; }, kind, H));
+	if (kind == BTLBF_COUNTING8 && H.bits_per_counter != 8)
+		return fail(BTLBF_ERR_ARG, "only 8-bit counting filters are supported (BitsPerCounter %u)", H.bits_per_counter);
+	if (size) *size = H.size;
+	if (size_bytes) *size_bytes = H.size_bytes;
+	if (hash_num) *hash_num = H.h;
+	if (kmer_size) *kmer_size = H.k;
+	if (dFPR) *dFPR = H.dFPR;
+	if (nEntry) *nEntry = H.nEntry;
+	if (tEntry) *tEntry = H.tEntry;
+	if (header_len) *header_len = H.body_offset;
 	return BTLBF_OK;
 }
 
@@ -2086,6 +2431,11 @@ extern "C" int btlbf_filter_store(btlbf_filter* f, const char* path, double dFPR
 		return fail(BTLBF_ERR_STATE, "a BTLBF_BITVECTOR has no file format of its own (download the words instead)");
 	btlbf_ctx* ctx = f->ctx;
 	TRY(use(ctx));
+	LOCKED(ctx);
+	{
+		cudaStream_t s; // deferred updates first: a failure there must not produce a file that lacks k-mers
+		TRY(join(ctx, &s));
+	}
 	FILE* fp = fopen(path, "wb");
 	if (!fp)
 		return fail(BTLBF_ERR_ARG, "error: `%s': %s", path, strerror(errno));
@@ -2123,6 +2473,7 @@ extern "C" int btlbf_filter_load(btlbf_ctx* ctx, const char* path, int kind, uns
 		return fail(BTLBF_ERR_ARG, "null argument");
 	*out = nullptr;
 	TRY(use(ctx));
+	LOCKED(ctx);
 	if (kind != BTLBF_BLOOM && kind != BTLBF_COUNTING8)
 		return fail(BTLBF_ERR_ARG, "unknown filter kind %d", kind);
 	FILE* fp = fopen(path, "rb");

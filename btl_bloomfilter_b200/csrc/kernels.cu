@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(kApplyThreads) apply_bins_kernel(const __grid_
 	uint32_t* region = (uint32_t*)P.filter + ((uint64_t)part << (P.bin_shift - 5));
 	// Software pipeline: while partition `part` is being updated, pull the next partition's lines into L2
 	// with full-line prefetches, so that its atomics hit in L2 instead of waiting on one HBM sector each.
-	if (part + 1 < P.n_bins) {
+	if (P.bin_prefetch && part + 1 < P.n_bins) {
 		const uint64_t next_bit0 = (uint64_t)(part + 1) << P.bin_shift;
 		uint64_t bits = P.fm.m - next_bit0;
 		if (bits > ((uint64_t)1 << P.bin_shift))
@@ -71,26 +71,43 @@ __global__ void __launch_bounds__(kApplyThreads) apply_bins_kernel(const __grid_
 
 // Partitioned query, pass 2: same schedule; every (offset, window) pair tests its bit in the L2-resident
 // region and a miss clears the window's hit bit (the hit words start as all ones and are ANDed with the
-// valid words by finalize_hits_kernel).
-__device__ __forceinline__ void probe_one(const uint32_t* region, uint32_t* hit, uint32_t off, uint32_t wid)
+// valid words by finalize_hits_kernel).  COUNTING: the region holds 8-bit counters and the test is
+// counter >= threshold (CountingBloomFilter.hpp:190-196: contains == minCount >= threshold, and a minimum is
+// >= t exactly when every counter is).
+template<bool COUNTING>
+__device__ __forceinline__ uint32_t probe_load(const void* region, uint32_t off)
 {
-	if (!((__ldg(region + (off >> 5)) >> (off & 31)) & 1u))
+	if (COUNTING)
+		return __ldg(reinterpret_cast<const uint8_t*>(region) + off);
+	return __ldg(reinterpret_cast<const uint32_t*>(region) + (off >> 5));
+}
+
+template<bool COUNTING>
+__device__ __forceinline__ void probe_test(uint32_t v, uint32_t threshold, uint32_t* hit, uint32_t off, uint32_t wid)
+{
+	const bool ok = COUNTING ? v >= threshold : ((v >> (off & 31)) & 1u) != 0;
+	if (!ok)
 		atomicAnd(hit + (wid >> 5), ~(1u << (wid & 31)));
 }
 
+// The kernel may share the SMs with pass 1 of the next sub-batch (binned_query runs the two passes of successive
+// sub-batches on two streams), which leaves it a fraction of the thread slots: every thread therefore keeps
+// 2 * UNROLL probes in flight.
+template<bool COUNTING, int UNROLL>
 __global__ void __launch_bounds__(kApplyThreads) probe_bins_kernel(const __grid_constant__ SeqParams P, uint32_t blocks_per_part)
 {
 	if (P.gate && *P.gate != P.gate_want)
 		return;
 	const uint32_t part = blockIdx.x / blocks_per_part, sub = blockIdx.x % blocks_per_part;
-	const uint32_t* region = (const uint32_t*)P.filter + ((uint64_t)part << (P.bin_shift - 5));
-	if (part + 1 < P.n_bins) {
-		const uint64_t next_bit0 = (uint64_t)(part + 1) << P.bin_shift;
-		uint64_t bits = P.fm.m - next_bit0;
-		if (bits > ((uint64_t)1 << P.bin_shift))
-			bits = (uint64_t)1 << P.bin_shift;
-		const uint64_t lines = (bits + 1023) >> 10;
-		const char* base = (const char*)P.filter + (next_bit0 >> 3);
+	const void* region = COUNTING ? (const void*)((const uint8_t*)P.filter + ((uint64_t)part << P.bin_shift))
+	                              : (const void*)((const uint32_t*)P.filter + ((uint64_t)part << (P.bin_shift - 5)));
+	if (P.bin_prefetch && part + 1 < P.n_bins) {
+		const uint64_t next0 = (uint64_t)(part + 1) << P.bin_shift; // bits, or counters
+		uint64_t units = P.fm.m - next0;
+		if (units > ((uint64_t)1 << P.bin_shift))
+			units = (uint64_t)1 << P.bin_shift;
+		const uint64_t lines = COUNTING ? (units + 127) >> 7 : (units + 1023) >> 10;
+		const char* base = (const char*)P.filter + (COUNTING ? next0 : next0 >> 3);
 		for (uint64_t l = (uint64_t)sub * kApplyThreads + threadIdx.x; l < lines; l += (uint64_t)blocks_per_part * kApplyThreads)
 			asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (l << 7)));
 	}
@@ -108,14 +125,31 @@ __global__ void __launch_bounds__(kApplyThreads) probe_bins_kernel(const __grid_
 		const uint32_t* items = P.bin_items + (((uint64_t)part * P.bin_writers + w) * P.bin_cap + lo) * 2;
 		const uint4* v = reinterpret_cast<const uint4*>(items); // two items per 16 bytes
 		const uint32_t nv = n / 2;
-		for (uint32_t i = lane; i < nv; i += 32) {
-			uint4 x = __ldcs(v + i);
-			probe_one(region, P.hit_bits, x.x, x.y);
-			probe_one(region, P.hit_bits, x.z, x.w);
+		for (uint32_t i0 = lane; i0 < nv; i0 += 32 * UNROLL) {
+			uint4 x[UNROLL];
+			uint32_t a[UNROLL], b[UNROLL];
+#pragma unroll
+			for (int j = 0; j < UNROLL; j++) {
+				const uint32_t i = i0 + 32 * j;
+				// (a slot past the end re-reads the last vector: harmless, its result is not used)
+				x[j] = __ldcs(v + (i < nv ? i : nv - 1));
+			}
+#pragma unroll
+			for (int j = 0; j < UNROLL; j++) {
+				a[j] = probe_load<COUNTING>(region, x[j].x);
+				b[j] = probe_load<COUNTING>(region, x[j].z);
+			}
+#pragma unroll
+			for (int j = 0; j < UNROLL; j++) {
+				if (i0 + 32 * j < nv) {
+					probe_test<COUNTING>(a[j], P.threshold, P.hit_bits, x[j].x, x[j].y);
+					probe_test<COUNTING>(b[j], P.threshold, P.hit_bits, x[j].z, x[j].w);
+				}
+			}
 		}
 		if ((n & 1u) && lane == 0) {
 			uint2 x = __ldcs(reinterpret_cast<const uint2*>(items) + (n - 1));
-			probe_one(region, P.hit_bits, x.x, x.y);
+			probe_test<COUNTING>(probe_load<COUNTING>(region, x.x), P.threshold, P.hit_bits, x.x, x.y);
 		}
 	}
 }
@@ -240,6 +274,8 @@ cudaError_t bin_plan(const SeqParams& P, uint32_t n_bins, bool query, uint32_t* 
 		return e;
 	if (occ < 1)
 		return cudaErrorLaunchOutOfResources;
+	if (P.bin_ctas_per_sm && (int)P.bin_ctas_per_sm < occ)
+		occ = (int)P.bin_ctas_per_sm;
 	uint64_t tiles = (P.n_windows + K.tile - 1) / K.tile;
 	uint64_t full = (uint64_t)sms * (uint64_t)occ;
 	uint64_t g = tiles < full ? (tiles ? tiles : 1) : full;
@@ -260,14 +296,31 @@ cudaError_t launch_bin(const SeqParams& P, bool query, uint32_t grid, cudaStream
 	return cudaLaunchKernel(K.fn, dim3(grid), dim3((unsigned)K.threads), args, K.smem, stream);
 }
 
-static uint32_t blocks_per_partition(const SeqParams& P)
+// number of SMs of the current device (queried once per device)
+static uint32_t sm_count()
 {
-	// enough blocks per partition to fill the GPU, never more warps than sub-buckets
-	uint32_t want = (P.bin_writers * P.bin_segs + (kApplyThreads / 32) - 1) / (kApplyThreads / 32);
-	return want < 592u ? (want ? want : 1u) : 592u;
+	static int cached[64] = { 0 };
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+		return 148;
+	if (!cached[dev]) {
+		int n = 0;
+		if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1)
+			n = 148;
+		cached[dev] = n;
+	}
+	return (uint32_t)cached[dev];
 }
 
-cudaError_t launch_probe_bins(const SeqParams& P, cudaStream_t stream)
+static uint32_t blocks_per_partition(const SeqParams& P)
+{
+	// enough blocks per partition to fill the GPU (4 per SM), never more warps than sub-buckets
+	const uint32_t full = 4u * sm_count();
+	uint32_t want = (P.bin_writers * P.bin_segs + (kApplyThreads / 32) - 1) / (kApplyThreads / 32);
+	return want < full ? (want ? want : 1u) : full;
+}
+
+cudaError_t launch_probe_bins(const SeqParams& P, bool counting, int unroll, cudaStream_t stream)
 {
 	uint32_t bpp = blocks_per_partition(P);
 	uint64_t grid = (uint64_t)P.n_bins * bpp;
@@ -275,8 +328,17 @@ cudaError_t launch_probe_bins(const SeqParams& P, cudaStream_t stream)
 		return cudaSuccess;
 	if (grid > 0x7fffffffULL)
 		return cudaErrorInvalidValue;
-	probe_bins_kernel<<<(unsigned)grid, kApplyThreads, 0, stream>>>(P, bpp);
-	return cudaGetLastError();
+	const void* fn;
+	if (counting)
+		fn = unroll >= 4 ? (const void*)probe_bins_kernel<true, 4> : unroll >= 2 ? (const void*)probe_bins_kernel<true, 2>
+		                                                                        : (const void*)probe_bins_kernel<true, 1>;
+	else
+		fn = unroll >= 4 ? (const void*)probe_bins_kernel<false, 4> : unroll >= 2 ? (const void*)probe_bins_kernel<false, 2>
+		                                                                         : (const void*)probe_bins_kernel<false, 1>;
+	// same L1/shared split as pass 1, so that the two kernels can share an SM
+	cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	void* args[2] = { (void*)&P, (void*)&bpp };
+	return cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kApplyThreads), args, 0, stream);
 }
 
 // adaptive query: picks the path from the hit fraction of a sample of the batch, on the device
@@ -298,7 +360,7 @@ cudaError_t launch_finalize_hits(uint32_t* hit, const uint32_t* valid, uint64_t 
 	if (n_words == 0)
 		return cudaSuccess;
 	uint64_t want = (n_words + 255) / 256;
-	unsigned grid = (unsigned)(want > 148 * 8 ? 148 * 8 : want);
+	unsigned grid = (unsigned)(want > sm_count() * 8 ? sm_count() * 8 : want);
 	finalize_hits_kernel<<<grid, 256, 0, stream>>>(hit, valid, n_words, hits_out, gate, gate_want);
 	return cudaGetLastError();
 }
@@ -640,7 +702,7 @@ cudaError_t launch_popcount(const void* data, uint64_t nbytes, int mode, unsigne
 {
 	uint64_t nvec = nbytes / 16;
 	uint64_t want = (nvec + 255) / 256;
-	unsigned grid = (unsigned)(want < 1 ? 1 : want > 148 * 16 ? 148 * 16 : want);
+	unsigned grid = (unsigned)(want < 1 ? 1 : want > sm_count() * 16 ? sm_count() * 16 : want);
 	popcount_kernel<<<grid, 256, 0, stream>>>((const uint8_t*)data, nbytes, mode, threshold, d_out);
 	return cudaGetLastError();
 }
@@ -742,7 +804,7 @@ cudaError_t launch_peer_merge(const PeerMergeParams& M, cudaStream_t stream)
 		return cudaSuccess;
 	const unsigned unroll = M.unroll == 2 || M.unroll == 4 ? M.unroll : 1;
 	uint64_t want = (nvec + 256 * unroll - 1) / (256 * unroll);
-	const uint64_t cap = M.grid ? M.grid : 148 * 8;
+	const uint64_t cap = M.grid ? M.grid : sm_count() * 8;
 	unsigned grid = (unsigned)(want > cap ? cap : want);
 #define BTL_PEER(W)                                                                  \
 	do {                                                                             \
@@ -764,7 +826,7 @@ cudaError_t launch_merge(void* dst, const void* src, uint64_t nbytes, int satura
 {
 	uint64_t nvec = nbytes / 16;
 	uint64_t want = (nvec + 255) / 256;
-	unsigned grid = (unsigned)(want < 1 ? 1 : want > 148 * 8 ? 148 * 8 : want);
+	unsigned grid = (unsigned)(want < 1 ? 1 : want > sm_count() * 8 ? sm_count() * 8 : want);
 	merge_kernel<<<grid, 256, 0, stream>>>((uint8_t*)dst, (const uint8_t*)src, nbytes, saturating_add);
 	return cudaGetLastError();
 }
@@ -799,7 +861,7 @@ cudaError_t launch_synth_genome(uint8_t* out, uint64_t start, uint64_t n, uint64
 	if (n == 0)
 		return cudaSuccess;
 	uint64_t want = ((n + 15) / 16 + 255) / 256;
-	unsigned grid = (unsigned)(want > 148 * 32 ? 148 * 32 : want);
+	unsigned grid = (unsigned)(want > sm_count() * 32 ? sm_count() * 32 : want);
 	synth_genome_kernel<<<grid, 256, 0, stream>>>(out, start, n, seed);
 	return cudaGetLastError();
 }
@@ -824,7 +886,7 @@ cudaError_t launch_synth_reads(uint8_t* out, uint64_t first_read, uint64_t n_rea
 	if (total == 0)
 		return cudaSuccess;
 	uint64_t want = (total + 255) / 256;
-	unsigned grid = (unsigned)(want > 148 * 64 ? 148 * 64 : want);
+	unsigned grid = (unsigned)(want > sm_count() * 64 ? sm_count() * 64 : want);
 	synth_reads_kernel<<<grid, 256, 0, stream>>>(out, first_read, n_reads, read_len, g_start, g_len, gseed, rseed);
 	return cudaGetLastError();
 }
@@ -860,7 +922,7 @@ __global__ void __launch_bounds__(256) random_probe_kernel(uint32_t* arr, uint64
 cudaError_t launch_random_probe(uint32_t* arr, uint64_t n_words, uint64_t n_access, int mode,
                                 unsigned long long* d_sink, cudaStream_t stream)
 {
-	random_probe_kernel<<<148 * 8, 256, 0, stream>>>(arr, n_words, n_access, mode, d_sink);
+	random_probe_kernel<<<sm_count() * 8, 256, 0, stream>>>(arr, n_words, n_access, mode, d_sink);
 	return cudaGetLastError();
 }
 

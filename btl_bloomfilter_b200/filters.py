@@ -120,7 +120,10 @@ class Context:
         check(self.L.btlbf_ctx_sync(self.handle))
 
     def flush(self):
-        """Order the active stream after the background (pass 2 of the partitioned build) stream."""
+        """Queue all deferred work on the active stream: pass 2 of the partitioned BloomFilter build for the k-mers
+        parked by earlier insert calls, queued per-k-mer updates, and a wait for the background stream.  Required
+        before anything outside this library (torch, NCCL, a peer GPU, your own kernel) reads filter memory
+        obtained from device_ptr(); see include/btlbf.h "DEFERRED WORK"."""
         check(self.L.btlbf_ctx_flush(self.handle))
 
     @property

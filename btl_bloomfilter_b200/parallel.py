@@ -216,6 +216,7 @@ class PeerMerge:
     def merge(self):
         """Every rank's array := reduce(all arrays).  Ranks are synchronised before and after."""
         from ._capi import check
+        self.ctx.flush()  # k-mers parked by the partitioned build reach the array before any peer reads it
         torch.cuda.synchronize()
         dist.barrier(group=self.group)  # all partial builds are complete and visible
         check(self.ctx.L.btlbf_merge_peers(self.ctx.handle, self.kind, self._bases, self.world, self.rank,
@@ -224,7 +225,8 @@ class PeerMerge:
         dist.barrier(group=self.group)  # all ranges have been written everywhere
 
     def launch(self):
-        """The kernel alone (for timing): the caller brackets it with synchronize + barrier."""
+        """The kernel alone (for timing): the caller brackets it with ctx.flush() + synchronize + barrier (the
+        flush BEFORE the barrier: parked k-mers must have reached this rank's array when the peers start)."""
         from ._capi import check
         check(self.ctx.L.btlbf_merge_peers(self.ctx.handle, self.kind, self._bases, self.world, self.rank,
                                            self.nbytes))

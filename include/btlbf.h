@@ -79,11 +79,19 @@ int btlbf_ctx_destroy(btlbf_ctx *ctx);
  * NULL restores the context's own stream (pass cudaStreamLegacy / cudaStreamPerThread for the default streams). */
 int btlbf_ctx_set_stream(btlbf_ctx *ctx, void *cuda_stream);
 int btlbf_ctx_sync(btlbf_ctx *ctx);
-/* With option "overlap" = 1 the second pass of the partitioned BloomFilter build runs on a background
- * stream so that it can overlap the next batch's first pass (default 0: everything on the active stream).
- * Every btlbf_* call that touches the filter orders itself after the background work, and so does
- * btlbf_ctx_sync.  btlbf_ctx_flush makes the ACTIVE stream wait for it without blocking the host: call it
- * before other work on that stream (or an event recorded on it) depends on filter contents. */
+/* DEFERRED WORK.  Two things may still be pending when an insert call has returned AND its stream work has
+ * finished: (1) the partitioned BloomFilter build (filters >= 96 MB) parks the hashed k-mers of successive
+ * insert calls in partition buckets and ORs them into the filter (pass 2) only when the buckets are full or
+ * when the filter is next touched through this library; (2) the legacy per-k-mer calls queue updates on the
+ * host.  Every btlbf_* call that reads or writes a filter applies the deferred work first, so through this
+ * ABI the deferral is not observable.  It IS observable to anything that reads the filter memory directly --
+ * a pointer from btlbf_filter_device_ptr kept across later inserts, your own kernel, NCCL, a peer GPU: call
+ * btlbf_ctx_flush (queues the deferred work on the active stream, does not block the host) or btlbf_ctx_sync
+ * BEFORE every such access, whatever the "overlap" setting.  Filters over caller-owned memory
+ * (btlbf_filter_wrap) are the exception: nothing stays parked for them when an insert call returns.
+ * With option "overlap" = 1 pass 2 runs on a background stream (default 0: on the active stream);
+ * btlbf_ctx_flush also makes the active stream wait for that.  A deferred pass that fails to launch is
+ * reported by the call that triggered it. */
 int btlbf_ctx_flush(btlbf_ctx *ctx);
 int btlbf_ctx_aux_stream(btlbf_ctx *ctx, void **cuda_stream); /* the background cudaStream_t (for timing) */
 /* number of kernels this context has launched so far (for accounting / tests) */
@@ -243,6 +251,13 @@ int btlbf_filter_load(btlbf_ctx *ctx, const char *path, int kind, unsigned thres
 /* the header text alone (no device needed); *len = strlen, buf may be NULL to query the length */
 int btlbf_format_header(int kind, uint64_t size, uint64_t size_bytes, unsigned hash_num, unsigned kmer_size,
                         double dFPR, uint64_t nEntry, uint64_t tEntry, char *buf, size_t cap, size_t *len);
+/* the inverse (no device needed): loadHeader of BloomFilter.hpp:118-166 / CountingBloomFilter.hpp:283-329 on
+ * header text held in memory -- the "[magic]" line through "[HeaderEnd]\n".  *header_len = bytes consumed (where
+ * the raw array starts).  Fails like the reference does: wrong magic, missing "[HeaderEnd]", missing key.
+ * Outputs may be NULL; dFPR / nEntry / tEntry are only meaningful for BTLBF_BLOOM. */
+int btlbf_parse_header(int kind, const char *text, size_t len, uint64_t *size, uint64_t *size_bytes,
+                       unsigned *hash_num, unsigned *kmer_size, double *dFPR, uint64_t *nEntry,
+                       uint64_t *tEntry, size_t *header_len);
 
 /* ---- the same operations on DEVICE-resident batches (asynchronous on the context's stream) ---- */
 /* d_bases: n_bases bytes, 16-byte aligned; d_offsets: n_seqs+1 uint64; d_hit_bits / d_valid_bits:

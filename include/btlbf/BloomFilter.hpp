@@ -11,6 +11,7 @@
 #include <cassert>
 #include <cmath>
 #include <fstream>
+#include <istream>
 #include <ostream>
 #include <string>
 #include <vector>
@@ -62,6 +63,34 @@ class BloomFilter
 		btlbf_filter_destroy(m_f);
 		m_f = f;
 		refreshInfo();
+	}
+
+	// Reads the header ("[BTLBloomFilter_v1]" ... "[HeaderEnd]") from the stream, which is left at the first byte
+	// of the raw array, sets the members from it and allocates a zeroed filter of that size (initSize).  :118-166
+	void loadHeader(std::istream& file)
+	{
+		if (!m_ctx)
+			m_ctx = btlbf::defaultContext(0);
+		std::string text, line;
+		bool headerEnd = false;
+		while (std::getline(file, line)) {
+			text.append(line + "\n");
+			if (line == "[HeaderEnd]") {
+				headerEnd = true;
+				break;
+			}
+			if (text.size() == line.size() + 1 && line != "[BTLBloomFilter_v1]")
+				break; // wrong magic: no need to read on
+		}
+		(void)headerEnd; // the parser reports a missing header end like the reference does
+		uint64_t size = 0, bytes = 0;
+		unsigned h = 0, k = 0;
+		btlbf::check(btlbf_parse_header(BTLBF_BLOOM, text.data(), text.size(), &size, &bytes, &h, &k, &m_dFPR, &m_nEntry,
+		                                &m_tEntry, nullptr),
+		             "loadHeader");
+		btlbf_filter_destroy(m_f);
+		m_f = nullptr;
+		create(size, h, k);
 	}
 
 	// ---- per-k-mer interface: the caller supplies the m_hashNum hash values (e.g. *ntHashIterator)

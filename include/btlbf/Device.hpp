@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <iostream>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -34,6 +35,8 @@ inline btlbf_ctx*
 defaultContext(int device = 0)
 {
 	static btlbf_ctx* ctxs[64] = { nullptr };
+	static std::mutex mu; // filters may be constructed from several host threads
+	std::lock_guard<std::mutex> lock(mu);
 	if (device < 0 || device >= 64) {
 		std::cerr << "ERROR: bad device index " << device << std::endl;
 		exit(EXIT_FAILURE);

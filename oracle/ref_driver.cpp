@@ -601,4 +601,41 @@ ref_bench_cbf(void* f, const char* bases, const uint64_t* off, uint64_t n_seqs, 
 	return std::chrono::duration<double>(t1 - t0).count();
 }
 
+/* Spaced seeds (stHashIterator.hpp:53-57 + BloomFilter insert/contains), same OpenMP pattern. */
+double
+ref_bench_st_bf(void* f, const char* const* seeds, unsigned n_seeds, unsigned h2, const char* bases,
+                const uint64_t* off, uint64_t n_seqs, int do_insert, int threads, uint64_t* n_kmers,
+                uint64_t* n_hits)
+{
+	RefBF& bloom = *(RefBF*)f;
+	auto ss = parse(seeds, n_seeds);
+	unsigned k = bloom.getKmerSize();
+	uint64_t n = 0, hits = 0;
+#ifdef _OPENMP
+	if (threads > 0)
+		omp_set_num_threads(threads);
+#endif
+	(void)threads;
+	auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : n, hits)
+	for (int64_t s = 0; s < (int64_t)n_seqs; s++) {
+		std::string seq(bases + off[s], off[s + 1] - off[s]);
+		stHashIterator itr(seq, ss, n_seeds, h2, k);
+		while (itr != itr.end()) {
+			if (do_insert)
+				bloom.insert(*itr);
+			else
+				hits += bloom.contains(*itr);
+			++n;
+			++itr;
+		}
+	}
+	auto t1 = std::chrono::steady_clock::now();
+	if (n_kmers)
+		*n_kmers = n;
+	if (n_hits)
+		*n_hits = hits;
+	return std::chrono::duration<double>(t1 - t0).count();
+}
+
 } // extern "C"

@@ -313,6 +313,8 @@ class Ref:
         L.ref_bench_bf.argtypes = [vp, u8p, u64p, u64, C.c_int, C.c_int, u64p, u64p]
         L.ref_bench_cbf.restype = C.c_double
         L.ref_bench_cbf.argtypes = [vp, u8p, u64p, u64, C.c_int, C.c_int, u64p, u64p]
+        L.ref_bench_st_bf.restype = C.c_double
+        L.ref_bench_st_bf.argtypes = [vp, cpp, u32, u32, u8p, u64p, u64, C.c_int, C.c_int, u64p, u64p]
         L.ref_max_threads.restype = C.c_int
 
     @staticmethod

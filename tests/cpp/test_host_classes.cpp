@@ -2,10 +2,12 @@
 // Tests/Unit/CountingBloomFilterTests.cpp:54-246) and README usage, written against the GPU-backed
 // drop-in classes in include/btlbf/.  Hash values come from the test oracle (plain-C restatement),
 // which plays the role of the reference's ntHashIterator here.  Run by tests/test_cpp_host.py on a GPU.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <iterator>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -197,12 +199,82 @@ countingScenario(const std::string& tmp)
 	printf("counting scenario ok (%llu k-mers)\n", (unsigned long long)n);
 }
 
+// BloomFilter::loadHeader(std::istream&) (BloomFilter.hpp:118-166): members from the header, a zeroed filter of
+// that size, the stream left at the first byte of the raw array.
+static void
+loadHeaderScenario(const std::string& tmp)
+{
+	BloomFilter a(8 * 5003, 3, 9);
+	insertSeq(a, "TAGAATCACCCAAAGATTTACCAGGATACCA", 3, 9);
+	a.setnEntry(23);
+	a.settEntry(24);
+	a.storeFilter(tmp + "/hdr.bf");
+	std::ifstream in(tmp + "/hdr.bf", std::ios::binary);
+	BloomFilter b;
+	b.loadHeader(in);
+	CHECK(b.getFilterSize() == a.getFilterSize() && b.sizeInBytes() == a.sizeInBytes());
+	CHECK(b.getHashNum() == 3 && b.getKmerSize() == 9 && b.getnEntry() == 23 && b.gettEntry() == 24);
+	CHECK(b.getPop() == 0);
+	std::vector<char> body((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+	CHECK(body.size() == a.sizeInBytes());
+	std::ostringstream oa;
+	oa << a;
+	CHECK(oa.str().size() > body.size() && oa.str().compare(oa.str().size() - body.size(), body.size(), body.data(), body.size()) == 0);
+	printf("loadHeader scenario ok\n");
+}
+
+// The reference's parallel build (Tests/AdHoc/ParallelFilter.cpp:104-122): OpenMP threads share one filter and call
+// the per-k-mer insert (README.md:30-43) concurrently.  Same bytes as the batched build of the same sequence.
+static void
+threadedLoopScenario()
+{
+	const unsigned k = 25, h = 4;
+	const size_t bits = 1 << 23, n = 1000000, piece = 65536;
+	std::string genome(n, 'A');
+	ora_synth_genome(&genome[0], 0, n, 42);
+	BloomFilter shared(bits, h, k), batched(bits, h, k);
+	std::vector<std::string> whole(1, genome);
+	const uint64_t expect = batched.insertSeqs(whole);
+	uint64_t total = 0;
+	auto t0 = std::chrono::steady_clock::now();
+	const long pieces = (long)((n + piece - 1) / piece);
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total)
+	for (long p = 0; p < pieces; p++) {
+		size_t lo = (size_t)p * piece, hi = lo + piece + k - 1;
+		if (hi > n)
+			hi = n;
+		ora_nt_iter it;
+		for (ora_nt_iter_init(&it, genome.data() + lo, hi - lo, h, k); it.pos != ORA_END; ora_nt_iter_next(&it)) {
+			shared.insert(it.hv);
+			total++;
+		}
+	}
+	const uint64_t pop = shared.getPop(); // applies whatever is still queued
+	const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	CHECK(total == expect);
+	CHECK(pop == batched.getPop());
+	std::ostringstream oa, ob;
+	oa << shared;
+	ob << batched;
+	CHECK(oa.str() == ob.str());
+	// the query twin (README.md:46-57), one k-mer per call (a device round trip each): a sample of the k-mers
+	ora_nt_iter it;
+	size_t seen = 0;
+	for (ora_nt_iter_init(&it, genome.data(), 3000, h, k); it.pos != ORA_END; ora_nt_iter_next(&it), seen++)
+		CHECK(shared.contains(it.hv));
+	CHECK(seen == 3000 - k + 1);
+	printf("threaded per-k-mer insert loop ok: %llu k-mers, %.2f Mk-mer/s\n", (unsigned long long)total, total / sec / 1e6);
+	CHECK(total / sec > 1e6);
+}
+
 int
 main(int argc, char** argv)
 {
 	std::string tmp = argc > 1 ? argv[1] : "/tmp";
 	bloomScenario(tmp);
 	countingScenario(tmp);
+	loadHeaderScenario(tmp);
+	threadedLoopScenario();
 	printf("ALL OK\n");
 	return 0;
 }

@@ -15,7 +15,7 @@ def _build():
     _oracle.build_oracle()
     B.lib()
     pkg = os.path.join(ROOT, "btl_bloomfilter_b200")
-    cmd = ["g++", "-std=c++11", "-O1", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"),
+    cmd = ["g++", "-std=c++11", "-O1", "-fopenmp", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"),
            os.path.join(ROOT, "tests", "cpp", "test_host_classes.cpp"), "-o", EXE,
            "-L" + pkg, "-lbtlbf_cuda", "-L" + os.path.join(ROOT, "oracle"), "-loracle",
            "-Wl,-rpath," + pkg, "-Wl,-rpath," + os.path.join(ROOT, "oracle")]
