@@ -122,7 +122,7 @@ struct btlbf_ctx
 	int64_t query_sub = 0;          // sub-batches per partitioned query (0 auto, 1: no overlap)
 	int64_t query_p1_ctas = 0;      // pass-1 CTAs per SM while overlapping (0 auto: one fewer than fit)
 	int64_t query_probe_unroll = 0; // item vectors in flight per thread of pass 2 (0 auto)
-	int64_t bin_wide_query = 0;     // 1: the auto rule also takes the partitioned query when the partitions had to be widened
+	int64_t probe_ld = 0, probe_carveout = -1; // experiment knobs of the probe kernel (load flavour; L1 split: -1 auto, 0 large L1, 1 small)
 	int64_t bin_prefetch = -1;      // pass 2 pulls the next partition into L2: -1 auto (partitions up to 16 MiB), 0, 1
 	DevBuf ibin2_items, ibin2_counts; // level-2 buckets of the two-level pass 2 (apply2.cu)
 	int64_t bin_two_level = 0;        // 1: two-level pass 2 (apply2.cu); measured slower than the L2-atomics pass on B200
@@ -613,8 +613,10 @@ extern "C" int btlbf_ctx_set_option(btlbf_ctx* ctx, const char* key, int64_t val
 		if (value != 0 && value != 1 && value != 2 && value != 4)
 			return fail(BTLBF_ERR_ARG, "query_probe_unroll must be 0, 1, 2 or 4");
 		ctx->query_probe_unroll = value;
-	} else if (k == "bin_wide_query") {
-		ctx->bin_wide_query = value != 0;
+	} else if (k == "probe_ld") {
+		ctx->probe_ld = value < 0 || value > 2 ? 0 : value;
+	} else if (k == "probe_carveout") {
+		ctx->probe_carveout = value < -1 || value > 1 ? -1 : value;
 	} else if (k == "bin_prefetch") {
 		if (value < -1 || value > 1)
 			return fail(BTLBF_ERR_ARG, "bin_prefetch must be -1, 0 or 1");
@@ -1282,10 +1284,13 @@ static int bin_setup(btlbf_filter* f, SeqParams& P, bool query, uint64_t capacit
 	P.n_bins = (uint32_t)n_bins;
 	P.bin_shift = shift;
 	P.bin_mask = (uint32_t)(((uint64_t)1 << shift) - 1);
+	P.bin_counting = f->kind == BTLBF_COUNTING8;
 	{
-		// prefetching the next partition pays while two partitions (plus the item stream) stay resident in L2
+		// Prefetching the next partition: always for the build (16 GiB filter, 32 MiB partitions: 16.9 against 15.7
+		// Gk-mer/s); for the query only while two partitions plus the item stream stay resident in L2 (32 MiB
+		// partitions: 21.3 with, 24.2 without; counting filter 20.6 / 24.7).
 		const uint64_t part_bytes = f->kind == BTLBF_COUNTING8 ? (uint64_t)1 << shift : ((uint64_t)1 << shift) >> 3;
-		P.bin_prefetch = ctx->bin_prefetch < 0 ? part_bytes <= ((uint64_t)16 << 20) : ctx->bin_prefetch != 0;
+		P.bin_prefetch = ctx->bin_prefetch < 0 ? (!query || part_bytes <= ((uint64_t)16 << 20)) : ctx->bin_prefetch != 0;
 	}
 	uint32_t writers = 0;
 	cudaError_t e = bin_plan(P, P.n_bins, query, &writers, grid, mode);
@@ -1483,11 +1488,8 @@ static bool want_binned_query(const btlbf_filter* f, const SeqParams& P)
 		return false;
 	if (ctx->bin_query_mode > 0)
 		return true;
-	// auto: not for filters so large that the partitions had to be widened beyond what stays resident in L2 next
-	// to the prefetched one (measured on a 16 GiB filter: 17 Gk-mer/s partitioned against 22 direct)
-	const uint32_t base_shift = (uint32_t)(f->kind == BTLBF_COUNTING8 ? ctx->bin_part_log2 - 3 : ctx->bin_part_log2);
-	if (shift > base_shift && !ctx->bin_wide_query)
-		return false;
+	// auto (widened partitions included: without the prefetch of the next partition a 16 GiB filter answers 24.2
+	// Gk-mer/s partitioned against 22.3 direct, the 16e9-counter filter 24.7 against 11.3)
 	return f->bytes >= ((uint64_t)96 << 20) && P.n_windows * P.h >= f->bytes / 64;
 }
 
@@ -1524,7 +1526,8 @@ static int binned_query(btlbf_filter* f, SeqParams P, cudaStream_t s)
 	if (fit == 0 || (n_sub == 0 && fit < 3))
 		n_sub = 1;
 	if (n_sub == 0)
-		n_sub = P.n_windows >= ((uint64_t)96 << 20) ? 4 : P.n_windows >= ((uint64_t)24 << 20) ? 2 : 1;
+		n_sub = 1; // measured on B200 (cfg2): 15.0 ms in one pass, 16.6 / 18.0 / 19.4 ms in 2 / 4 / 8 overlapped sub-batches
+		           // (same L1 configuration) -- the pass-1 CTAs' shared memory leaves pass 2 too small an L1
 	const uint64_t kAlign = 16384;
 	uint64_t sub = ((P.n_windows + n_sub - 1) / n_sub + kAlign - 1) / kAlign * kAlign;
 	n_sub = (P.n_windows + sub - 1) / sub;
@@ -1614,6 +1617,7 @@ static int binned_query(btlbf_filter* f, SeqParams P, cudaStream_t s)
 		Q.stats = stats;
 		Q.gate = gate;
 		Q.gate_want = 0;
+		Q.probe_ld = (uint32_t)ctx->probe_ld;
 		Q.bin_items = (uint32_t*)ctx->qbin_items[b].p;
 		Q.bin_counts = (uint32_t*)ctx->qbin_counts[b].p;
 		// pass 1 on the active stream; the buffers are free once the probe kernel that last read them is done
@@ -1639,7 +1643,7 @@ static int binned_query(btlbf_filter* f, SeqParams P, cudaStream_t s)
 			CU(cudaStreamWaitEvent(s2, ctx->ev_qp1[b], 0));
 		}
 		// the item words of a sub-batch carry window indices relative to the sub-batch
-		e = launch_probe_bins(Q, counting, unroll, s2);
+		e = launch_probe_bins(Q, counting, unroll, ctx->probe_carveout < 0 ? overlap : ctx->probe_carveout != 0, s2);
 		if (e != cudaSuccess)
 			return fail(BTLBF_ERR_CUDA, "partitioned query (pass 2) launch failed: %s", cudaGetErrorString(e));
 		if (overlap) {

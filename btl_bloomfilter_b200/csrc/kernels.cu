@@ -74,12 +74,30 @@ __global__ void __launch_bounds__(kApplyThreads) apply_bins_kernel(const __grid_
 // valid words by finalize_hits_kernel).  COUNTING: the region holds 8-bit counters and the test is
 // counter >= threshold (CountingBloomFilter.hpp:190-196: contains == minCount >= threshold, and a minimum is
 // >= t exactly when every counter is).
+// ld_mode (experiment knob "probe_ld"): 0 = read-only path (ld.global.nc), 1 = ld.global.cg, 2 = L1::no_allocate
 template<bool COUNTING>
-__device__ __forceinline__ uint32_t probe_load(const void* region, uint32_t off)
+__device__ __forceinline__ uint32_t probe_load(const void* region, uint32_t off, uint32_t ld_mode)
 {
-	if (COUNTING)
-		return __ldg(reinterpret_cast<const uint8_t*>(region) + off);
-	return __ldg(reinterpret_cast<const uint32_t*>(region) + (off >> 5));
+	if (COUNTING) {
+		const uint8_t* a = reinterpret_cast<const uint8_t*>(region) + off;
+		if (ld_mode == 1)
+			return __ldcg(a);
+		if (ld_mode == 2) {
+			uint32_t v;
+			asm volatile("ld.global.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(a));
+			return v;
+		}
+		return __ldg(a);
+	}
+	const uint32_t* a = reinterpret_cast<const uint32_t*>(region) + (off >> 5);
+	if (ld_mode == 1)
+		return __ldcg(a);
+	if (ld_mode == 2) {
+		uint32_t v;
+		asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(a));
+		return v;
+	}
+	return __ldg(a);
 }
 
 template<bool COUNTING>
@@ -136,8 +154,8 @@ __global__ void __launch_bounds__(kApplyThreads) probe_bins_kernel(const __grid_
 			}
 #pragma unroll
 			for (int j = 0; j < UNROLL; j++) {
-				a[j] = probe_load<COUNTING>(region, x[j].x);
-				b[j] = probe_load<COUNTING>(region, x[j].z);
+				a[j] = probe_load<COUNTING>(region, x[j].x, P.probe_ld);
+				b[j] = probe_load<COUNTING>(region, x[j].z, P.probe_ld);
 			}
 #pragma unroll
 			for (int j = 0; j < UNROLL; j++) {
@@ -149,7 +167,7 @@ __global__ void __launch_bounds__(kApplyThreads) probe_bins_kernel(const __grid_
 		}
 		if ((n & 1u) && lane == 0) {
 			uint2 x = __ldcs(reinterpret_cast<const uint2*>(items) + (n - 1));
-			probe_test<COUNTING>(probe_load<COUNTING>(region, x.x), P.threshold, P.hit_bits, x.x, x.y);
+			probe_test<COUNTING>(probe_load<COUNTING>(region, x.x, P.probe_ld), P.threshold, P.hit_bits, x.x, x.y);
 		}
 	}
 }
@@ -320,7 +338,7 @@ static uint32_t blocks_per_partition(const SeqParams& P)
 	return want < full ? (want ? want : 1u) : full;
 }
 
-cudaError_t launch_probe_bins(const SeqParams& P, bool counting, int unroll, cudaStream_t stream)
+cudaError_t launch_probe_bins(const SeqParams& P, bool counting, int unroll, bool maxshared, cudaStream_t stream)
 {
 	uint32_t bpp = blocks_per_partition(P);
 	uint64_t grid = (uint64_t)P.n_bins * bpp;
@@ -335,8 +353,11 @@ cudaError_t launch_probe_bins(const SeqParams& P, bool counting, int unroll, cud
 	else
 		fn = unroll >= 4 ? (const void*)probe_bins_kernel<false, 4> : unroll >= 2 ? (const void*)probe_bins_kernel<false, 2>
 		                                                                         : (const void*)probe_bins_kernel<false, 1>;
-	// same L1/shared split as pass 1, so that the two kernels can share an SM
-	cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	// The gathers need the large L1 (every outstanding miss holds a line there: with the small one the kernel runs
+	// at half speed, measured).  maxshared != 0 (overlapped sub-batches): the pass-1 kernel's split instead, without
+	// which the two kernels cannot be co-resident at all.
+	cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+	                     maxshared ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault);
 	void* args[2] = { (void*)&P, (void*)&bpp };
 	return cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kApplyThreads), args, 0, stream);
 }

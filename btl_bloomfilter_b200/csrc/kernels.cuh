@@ -68,6 +68,8 @@ struct SeqParams
 	uint32_t bin_segs;    // pass 2 splits every sub-bucket into this many segments (work units)
 	uint32_t bin_legacy;  // knob: never use the sort-bin kernel
 	uint32_t bin_rot;     // sort-bin kernel: tile t goes to writer (t + bin_rot) % bin_writers
+	uint32_t bin_counting;    // partitioned query of a counting filter: an item is a counter index, the test is >= threshold
+	uint32_t probe_ld;        // pass 2 of the query, experiment knob: 0 ld.global.nc, 1 ld.global.cg, 2 L1::no_allocate
 	uint32_t bin_prefetch;    // pass 2: pull the next partition into L2 while this one is processed
 	uint32_t bin_ctas_per_sm; // pass 1 (query): persistent CTAs per SM (0 = as many as fit); fewer leave room for a
 	                          // concurrent pass 2
@@ -106,7 +108,7 @@ cudaError_t bin_plan(const SeqParams& P, uint32_t n_bins, bool query, uint32_t* 
 cudaError_t launch_bin(const SeqParams& P, bool query, uint32_t grid, cudaStream_t stream);
 cudaError_t launch_apply_bins(const SeqParams& P, cudaStream_t stream);
 // counting: the filter holds 8-bit counters, the test is counter >= P.threshold; unroll: item vectors in flight per thread
-cudaError_t launch_probe_bins(const SeqParams& P, bool counting, int unroll, cudaStream_t stream);
+cudaError_t launch_probe_bins(const SeqParams& P, bool counting, int unroll, bool maxshared, cudaStream_t stream);
 cudaError_t launch_finalize_hits(uint32_t* hit, const uint32_t* valid, uint64_t n_words, unsigned long long* hits_out,
                                  const uint32_t* gate, uint32_t gate_want, cudaStream_t stream);
 // *flag = 1 (direct early-exit kernel) when fewer than pct percent of the sampled k-mers {stats[0] valid,

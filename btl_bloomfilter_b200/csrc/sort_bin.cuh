@@ -53,7 +53,9 @@ __device__ __forceinline__ void bin_direct_or(const SeqParams& P, uint32_t part,
 __device__ __forceinline__ void bin_direct_probe(const SeqParams& P, uint32_t part, uint32_t off, uint32_t wid)
 {
 	uint64_t n = ((uint64_t)part << P.bin_shift) | off;
-	if (!((__ldg((const uint32_t*)P.filter + (n >> 5)) >> (uint32_t)(n & 31)) & 1u))
+	const bool ok = P.bin_counting ? __ldg((const uint8_t*)P.filter + n) >= P.threshold // CountingBloomFilter.hpp:190-196
+	                               : ((__ldg((const uint32_t*)P.filter + (n >> 5)) >> (uint32_t)(n & 31)) & 1u) != 0;
+	if (!ok)
 		atomicAnd(P.hit_bits + (wid >> 5), ~(1u << (wid & 31)));
 }
 

@@ -2,7 +2,7 @@
 # round 2, GPU call 1: tests, option sweeps (query overlap, prefetch), first bench line
 mkdir -p gpurun_out
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
 SKIP_BUILD=1 timeout 300 python tools/r2_sweep.py cfg2 "query_sub=1" "query_sub=1,query_probe_unroll=4" \
   "query_sub=2" "query_sub=4" "query_sub=8" "query_sub=4,query_p1_ctas=4" "query_sub=4,query_p1_ctas=2" \
