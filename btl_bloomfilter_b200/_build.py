@@ -7,7 +7,7 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libbtlbf_cuda.so")
-SOURCES = ["kernels.cu", "capi.cu", "sort_bin_build_256.cu", "sort_bin_build_512.cu", "sort_bin_query_256.cu", "sort_bin_query_512.cu", "ingest.cu", "apply2.cu", "seq_commit_cbf.cu", "seq_commit_bfchk.cu", "seq_ops_bloom.cu", "bin_legacy.cu"]
+SOURCES = ["kernels.cu", "capi.cu", "sort_bin_build_256.cu", "sort_bin_build_512.cu", "sort_bin_query_256.cu", "sort_bin_query_512.cu", "ingest.cu", "pack.cu", "apply2.cu", "seq_commit_cbf.cu", "seq_commit_bfchk.cu", "seq_ops_bloom.cu", "bin_legacy.cu"]
 HEADERS = ["kernels.cuh", "tile_core.cuh", "sort_bin.cuh", "seq_kernel.cuh", "nthash_dev.cuh", "host_params.hpp", os.path.join("..", "..", "include", "btlbf.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]

@@ -62,6 +62,13 @@ SIGNATURES = {
     "btlbf_contains_seqs": [vp, vp, u64p, u64, vp, vp, u64p, u64p],
     "btlbf_insert_seqs_async": [vp, vp, u64p, u64, vp],
     "btlbf_contains_seqs_async": [vp, vp, u64p, u64, vp, vp, vp],
+    "btlbf_pack_seqs": [vp, u64, vp, vp, C.c_int, u64p],
+    "btlbf_insert_seqs_packed": [vp, vp, vp, u64p, u64, u64p],
+    "btlbf_contains_seqs_packed": [vp, vp, vp, u64p, u64, vp, vp, u64p, u64p],
+    "btlbf_insert_seqs_packed_async": [vp, vp, vp, u64p, u64, vp],
+    "btlbf_contains_seqs_packed_async": [vp, vp, vp, u64p, u64, vp, vp, vp],
+    "btlbf_insert_seqs_packed_dev": [vp, vp, vp, u64, vp, u64, vp],
+    "btlbf_contains_seqs_packed_dev": [vp, vp, vp, u64, vp, u64, vp, vp, vp],
     "btlbf_insert_and_check_seqs": [vp, vp, u64p, u64, vp, vp, u64p],
     "btlbf_mincount_seqs": [vp, vp, u64p, u64, vp, vp, u64p],
     "btlbf_increment_all_seqs": [vp, vp, u64p, u64, u64p],

@@ -53,7 +53,7 @@ struct DevBuf
 
 struct Slot // one stage of the host-buffer pipeline (H2D copy | kernel | D2H copy)
 {
-	DevBuf bases, hit, valid, counts, hashes, strands;
+	DevBuf bases, invalid, hit, valid, counts, hashes, strands;
 	cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_d2h = nullptr;
 	bool used = false;
 };
@@ -307,6 +307,15 @@ static SeqParams filter_params(btlbf_filter* f)
 	return P;
 }
 
+// the part of chunk C that starts at its window b0 (a multiple of 32): input pointers and positions of P
+static void advance_input(SeqParams& P, const SeqParams& C, uint64_t b0)
+{
+	P.bases = C.bases + (C.packed ? b0 >> 2 : b0);
+	P.invalid = C.invalid ? C.invalid + (b0 >> 3) : nullptr;
+	P.n_bases = C.n_bases > b0 ? C.n_bases - b0 : 0;
+	P.base0 = C.base0 + b0;
+}
+
 // ---------------------------------------------------------------- misc entry points
 extern "C" int btlbf_set_error(int code, const char* msg) // used by ingest.cu
 {
@@ -413,7 +422,7 @@ extern "C" int btlbf_ctx_destroy(btlbf_ctx* ctx)
 	cudaDeviceSynchronize();
 	for (int i = 0; i < 2; i++) {
 		Slot& s = ctx->slot[i];
-		release(s.bases); release(s.hit); release(s.valid); release(s.counts); release(s.hashes); release(s.strands);
+		release(s.bases); release(s.invalid); release(s.hit); release(s.valid); release(s.counts); release(s.hashes); release(s.strands);
 		if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
 		if (s.ev_kernel) cudaEventDestroy(s.ev_kernel);
 		if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
@@ -1127,9 +1136,7 @@ static int ordered_apply(btlbf_filter* f, const SeqParams& chunk, int kind, cuda
 	for (uint64_t b0 = 0; b0 < chunk.n_windows; b0 += batch) {
 		SeqParams P = chunk;
 		uint64_t bw = chunk.n_windows - b0 < batch ? chunk.n_windows - b0 : batch;
-		P.bases = chunk.bases + b0;
-		P.n_bases = chunk.n_bases > b0 ? chunk.n_bases - b0 : 0;
-		P.base0 = chunk.base0 + b0;
+		advance_input(P, chunk, b0);
 		P.n_windows = bw;
 		if (chunk.hit_bits) P.hit_bits = chunk.hit_bits + (b0 >> 5);
 		if (chunk.valid_bits) P.valid_bits = chunk.valid_bits + (b0 >> 5);
@@ -1605,9 +1612,7 @@ static int binned_query(btlbf_filter* f, SeqParams P, cudaStream_t s)
 	for (uint64_t i = 0, c0 = 0; c0 < P.n_windows; i++, c0 += sub) {
 		const int b = overlap ? (int)(i & 1) : 0;
 		SeqParams Q = G;
-		Q.bases = P.bases + c0;
-		Q.n_bases = P.n_bases > c0 ? P.n_bases - c0 : 0;
-		Q.base0 = P.base0 + c0;
+		advance_input(Q, P, c0);
 		Q.n_windows = P.n_windows - c0 < sub ? P.n_windows - c0 : sub;
 		if (Q.n_bases > Q.n_windows + P.k - 1)
 			Q.n_bases = Q.n_windows + P.k - 1; // a sub-batch reads its windows + the k-1 halo, like a pipeline chunk
@@ -1671,7 +1676,9 @@ enum PublicOp { PUB_INSERT, PUB_CONTAINS, PUB_INSERT_CHECK, PUB_MINCOUNT, PUB_IN
 struct ChunkIO
 {
 	const uint8_t* d_bases = nullptr;
-	uint64_t n_bases = 0;   // bytes readable at d_bases
+	const uint8_t* d_invalid = nullptr; // packed input: the invalid plane (may be null)
+	bool packed = false;    // d_bases holds 2-bit codes
+	uint64_t n_bases = 0;   // bases readable at d_bases
 	uint64_t base0 = 0;     // flat position of d_bases[0]
 	uint64_t n_windows = 0; // windows of this chunk
 	const uint64_t* d_offsets = nullptr;
@@ -1687,6 +1694,10 @@ struct ChunkIO
 static void fill_io(SeqParams& P, const ChunkIO& io)
 {
 	P.bases = io.d_bases;
+	P.invalid = io.packed ? io.d_invalid : nullptr;
+	P.packed = io.packed;
+	if (io.packed)
+		P.force_generic = 0; // the byte-class path needs the ASCII tile
 	P.n_bases = io.n_bases;
 	P.base0 = io.base0;
 	P.n_windows = io.n_windows;
@@ -1814,6 +1825,8 @@ extern "C" int btlbf_mincount_seqs_dev(btlbf_filter* f, const void* d_bases, uin
 struct HostIO
 {
 	const char* bases = nullptr;
+	const uint8_t* invalid = nullptr; // packed input: one bit per base (may be null)
+	bool packed = false;              // bases holds 2-bit codes, 4 per byte
 	const uint64_t* offsets = nullptr;
 	uint64_t n_seqs = 0;
 	uint8_t* hit_bits = nullptr;   // ceil(n/32)*4 bytes each
@@ -1913,13 +1926,22 @@ static int host_pipeline(btlbf_ctx* ctx, btlbf_filter* f, const HashCfg* hash_on
 			// the slot is free once its previous results have left the device
 			if (sl.used)
 				CU(cudaStreamWaitEvent(ctx->copy_in, sl.ev_d2h, 0));
-			CU(cudaMemcpyAsync(sl.bases.p, h.bases + c0, cb, cudaMemcpyHostToDevice, ctx->copy_in));
+			if (h.packed) { // c0 is a multiple of the tile size: the chunk starts on a byte of both planes
+				CU(cudaMemcpyAsync(sl.bases.p, h.bases + (c0 >> 2), (cb + 3) >> 2, cudaMemcpyHostToDevice, ctx->copy_in));
+				if (h.invalid) {
+					TRY(ensure_idle(ctx, sl.invalid, (size_t)chunk / 8 + k + 64));
+					CU(cudaMemcpyAsync(sl.invalid.p, h.invalid + (c0 >> 3), (cb + 7) >> 3, cudaMemcpyHostToDevice, ctx->copy_in));
+				}
+			} else
+				CU(cudaMemcpyAsync(sl.bases.p, h.bases + c0, cb, cudaMemcpyHostToDevice, ctx->copy_in));
 			CU(cudaEventRecord(sl.ev_h2d, ctx->copy_in));
 			CU(cudaStreamWaitEvent(s, sl.ev_h2d, 0)); // also orders the offsets upload before the kernels
 			if (sl.used)
 				CU(cudaStreamWaitEvent(s, sl.ev_d2h, 0));
 			ChunkIO io;
 			io.d_bases = (const uint8_t*)sl.bases.p;
+			io.packed = h.packed;
+			io.d_invalid = h.packed && h.invalid ? (const uint8_t*)sl.invalid.p : nullptr;
 			io.n_bases = cb;
 			io.base0 = c0;
 			io.n_windows = cw;
@@ -2028,6 +2050,88 @@ extern "C" int btlbf_contains_seqs_async(btlbf_filter* f, const char* bases, con
 	HostIO h;
 	h.bases = bases; h.offsets = offsets; h.n_seqs = n_seqs; h.hit_bits = hit_bits; h.valid_bits = valid_bits;
 	return host_pipeline(f->ctx, f, nullptr, PUB_CONTAINS, h, true, counts_out);
+}
+
+// ---------------------------------------------------------------- 2-bit packed input
+// The same calls for callers that hold their reads as 2 bits per base (codes A0 C1 G2 T3 + an optional invalid
+// plane; btlbf_pack_seqs in pack.cu produces both from ASCII): a quarter to three eighths of the host->device
+// bytes, and the kernels skip the classification of the input (tile_phase_a copies the planes as they are).
+static int packed_host_call(btlbf_filter* f, PublicOp op, const uint8_t* codes, const uint8_t* invalid, const uint64_t* offsets,
+                            uint64_t n_seqs, uint8_t* hit_bits, uint8_t* valid_bits, uint64_t* n_kmers, uint64_t* n_hits,
+                            bool async, uint64_t* counts_out)
+{
+	if (!f)
+		return fail(BTLBF_ERR_ARG, "null filter");
+	HostIO h;
+	h.bases = (const char*)codes; h.invalid = invalid; h.packed = true; h.offsets = offsets; h.n_seqs = n_seqs;
+	h.hit_bits = hit_bits; h.valid_bits = valid_bits; h.n_kmers = n_kmers; h.n_hits = n_hits;
+	return host_pipeline(f->ctx, f, nullptr, op, h, async, counts_out);
+}
+
+extern "C" int btlbf_insert_seqs_packed(btlbf_filter* f, const uint8_t* codes, const uint8_t* invalid, const uint64_t* offsets,
+                                        uint64_t n_seqs, uint64_t* n_kmers)
+{
+	return packed_host_call(f, PUB_INSERT, codes, invalid, offsets, n_seqs, nullptr, nullptr, n_kmers, nullptr, false, nullptr);
+}
+
+extern "C" int btlbf_contains_seqs_packed(btlbf_filter* f, const uint8_t* codes, const uint8_t* invalid, const uint64_t* offsets,
+                                          uint64_t n_seqs, uint8_t* hit_bits, uint8_t* valid_bits, uint64_t* n_kmers,
+                                          uint64_t* n_hits)
+{
+	return packed_host_call(f, PUB_CONTAINS, codes, invalid, offsets, n_seqs, hit_bits, valid_bits, n_kmers, n_hits, false, nullptr);
+}
+
+extern "C" int btlbf_insert_seqs_packed_async(btlbf_filter* f, const uint8_t* codes, const uint8_t* invalid,
+                                              const uint64_t* offsets, uint64_t n_seqs, uint64_t* counts_out)
+{
+	uint64_t dummy[2];
+	return packed_host_call(f, PUB_INSERT, codes, invalid, offsets, n_seqs, nullptr, nullptr, nullptr, nullptr,
+	                        counts_out != nullptr, counts_out ? counts_out : dummy);
+}
+
+extern "C" int btlbf_contains_seqs_packed_async(btlbf_filter* f, const uint8_t* codes, const uint8_t* invalid,
+                                                const uint64_t* offsets, uint64_t n_seqs, uint8_t* hit_bits,
+                                                uint8_t* valid_bits, uint64_t* counts_out)
+{
+	if (!counts_out)
+		return fail(BTLBF_ERR_ARG, "counts_out is required (2 host words: n_kmers, n_hits)");
+	return packed_host_call(f, PUB_CONTAINS, codes, invalid, offsets, n_seqs, hit_bits, valid_bits, nullptr, nullptr, true,
+	                        counts_out);
+}
+
+static int packed_dev_call(btlbf_filter* f, PublicOp op, const void* d_codes, const void* d_invalid, uint64_t n_bases,
+                           const uint64_t* d_offsets, uint64_t n_seqs, uint32_t* d_hit_bits, uint32_t* d_valid_bits,
+                           uint64_t* d_stats)
+{
+	TRY(check_dev_args(f, d_codes, n_bases, d_offsets));
+	if ((uintptr_t)d_invalid & 15u)
+		return fail(BTLBF_ERR_ARG, "the device invalid plane must be 16-byte aligned");
+	ChunkIO io;
+	io.d_bases = (const uint8_t*)d_codes;
+	io.d_invalid = (const uint8_t*)d_invalid;
+	io.packed = true;
+	io.n_bases = io.n_windows = n_bases;
+	io.d_offsets = d_offsets;
+	io.n_seqs = n_seqs;
+	io.d_hit = d_hit_bits;
+	io.d_valid = d_valid_bits;
+	io.d_stats = d_stats;
+	LOCKED(f->ctx);
+	TRY(filter_op_dev(f, op, io, f->ctx->active));
+	return op == PUB_INSERT ? settle_if_wrapped(f) : BTLBF_OK;
+}
+
+extern "C" int btlbf_insert_seqs_packed_dev(btlbf_filter* f, const void* d_codes, const void* d_invalid, uint64_t n_bases,
+                                            const uint64_t* d_offsets, uint64_t n_seqs, uint64_t* d_stats)
+{
+	return packed_dev_call(f, PUB_INSERT, d_codes, d_invalid, n_bases, d_offsets, n_seqs, nullptr, nullptr, d_stats);
+}
+
+extern "C" int btlbf_contains_seqs_packed_dev(btlbf_filter* f, const void* d_codes, const void* d_invalid, uint64_t n_bases,
+                                              const uint64_t* d_offsets, uint64_t n_seqs, uint32_t* d_hit_bits,
+                                              uint32_t* d_valid_bits, uint64_t* d_stats)
+{
+	return packed_dev_call(f, PUB_CONTAINS, d_codes, d_invalid, n_bases, d_offsets, n_seqs, d_hit_bits, d_valid_bits, d_stats);
 }
 
 extern "C" int btlbf_insert_and_check_seqs(btlbf_filter* f, const char* bases, const uint64_t* offsets,

@@ -36,6 +36,11 @@ struct SeqParams
 	uint64_t n_windows;      // windows [0, n_windows) of this chunk are processed by this launch
 	const uint64_t* offsets; // n_seqs + 1 flat sequence offsets of the whole batch
 	uint64_t n_seqs;
+	// 2-bit packed input (btlbf_*_seqs_packed): `bases` then holds 4 bases per byte (base i = bits 2*(i&3) of byte
+	// i>>2, A0 C1 G2 T3) and `invalid` one bit per base (bit i&7 of byte i>>3; may be null: every base valid);
+	// n_bases, base0, n_windows keep counting bases
+	const uint8_t* invalid;
+	uint32_t packed;
 	// hashing
 	uint32_t k, h;           // k-mer size, hashes per k-mer
 	uint32_t n_seeds, h2;    // spaced seeds: h == n_seeds*h2

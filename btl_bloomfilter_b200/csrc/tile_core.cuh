@@ -189,11 +189,29 @@ BTL_HD void tile_phase_a(const SeqParams& P, const TileSmem& sm, uint64_t t0, in
 	if (tid == 0)
 		sm.scratch[1] = 0;
 
+	uint64_t avail = P.n_bases > t0 ? P.n_bases - t0 : 0;
+	if (P.packed) {
+		// 2-bit packed input: the code words and the invalid plane are the caller's, copied as they are (t0 is a
+		// multiple of 32, so both start on a word; the buffers are padded to whole 16 bytes).  Bases beyond the end
+		// of the chunk are marked invalid here; phase B then has nothing to classify.
+		const uint32_t* csrc = reinterpret_cast<const uint32_t*>(P.bases + (t0 >> 2));
+		const uint32_t* vsrc = P.invalid ? reinterpret_cast<const uint32_t*>(P.invalid + (t0 >> 3)) : nullptr;
+		for (uint32_t v = tid; v < sm.nb / 16; v += ntid)
+			sm.codes[v] = (uint64_t)v * 16 < avail ? csrc[v] : 0u;
+		for (uint32_t g = tid; g < sm.nb / 32; g += ntid) {
+			const uint64_t p = (uint64_t)g * 32;
+			uint32_t bad = (vsrc && p < avail) ? vsrc[g] : 0u;
+			if (p >= avail)
+				bad = 0xffffffffu;
+			else if (avail - p < 32)
+				bad |= 0xffffffffu << (uint32_t)(avail - p);
+			sm.badw[g] = bad;
+		}
+	}
 	// ASCII bytes [t0, t0+nb) of the chunk, zero (= invalid) beyond its end
 	const uint8_t* src = P.bases + t0;
-	uint64_t avail = P.n_bases > t0 ? P.n_bases - t0 : 0;
 	bool aligned = (((uintptr_t)src) & 15u) == 0;
-	uint32_t nvec = sm.nb / 16;
+	uint32_t nvec = P.packed ? 0u : sm.nb / 16;
 	for (uint32_t v = tid; v < nvec; v += ntid) {
 		uint64_t off = (uint64_t)v * 16;
 		uint4 val;
@@ -230,7 +248,7 @@ BTL_HD void tile_phase_b(const SeqParams& P, const TileSmem& sm, uint64_t t0, in
 	uint32_t ngroups = sm.nb / 32;
 	uint32_t* tile32 = reinterpret_cast<uint32_t*>(sm.tile);
 	bool exotic = false;
-	for (uint32_t g = tid; g < ngroups; g += ntid) {
+	for (uint32_t g = tid; g < (P.packed ? 0u : ngroups); g += ntid) {
 		uint32_t clo = 0, chi = 0, bad = 0;
 #pragma unroll
 		for (int w = 0; w < 8; w++) {
@@ -947,10 +965,18 @@ BTL_HD void list_for_each_hash(const SeqParams& P, uint32_t w, Fn&& fn)
 	}
 	const uint8_t* s = P.bases + w;
 	const uint32_t k = P.k;
+	// class of base i of the window (a deferred window is valid: no invalid base inside)
+	auto cls = [&](uint32_t i) -> unsigned {
+		if (P.packed) {
+			const uint64_t q = (uint64_t)w + i;
+			return (P.bases[q >> 2] >> (2 * (uint32_t)(q & 3))) & 3u;
+		}
+		return base_class(s[i]);
+	};
 	uint64_t F = 0, RC = 0;
 	for (uint32_t i = 0; i < k; i++) {
-		F = srol(F) ^ class_fseed(base_class(s[i]));
-		RC = srol(RC) ^ class_rseed(base_class(s[k - 1 - i]));
+		F = srol(F) ^ class_fseed(cls(i));
+		RC = srol(RC) ^ class_rseed(cls(k - 1 - i));
 	}
 	if (P.n_seeds == 0) {
 		uint64_t b = RC < F ? RC : F;
@@ -966,7 +992,7 @@ BTL_HD void list_for_each_hash(const SeqParams& P, uint32_t w, Fn&& fn)
 			uint64_t fs = F, rs = RC;
 			for (uint32_t t = P.st_dc_off[j]; t < P.st_dc_off[j + 1]; t++) {
 				uint32_t pos = P.st_dc[t];
-				uint32_t c = base_class(s[pos]) & 7u;
+				uint32_t c = cls(pos) & 7u;
 				fs ^= TF[pos * 8 + c];
 				rs ^= TR[pos * 8 + c];
 			}

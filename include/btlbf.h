@@ -191,6 +191,31 @@ int btlbf_insert_seqs_async(btlbf_filter *f, const char *bases, const uint64_t *
                             uint64_t *counts_out);
 int btlbf_contains_seqs_async(btlbf_filter *f, const char *bases, const uint64_t *offsets, uint64_t n_seqs,
                               uint8_t *hit_bits, uint8_t *valid_bits, uint64_t *counts_out);
+/* ---- 2-bit packed input.  For callers that keep reads as 2 bits per base: base i of the flat stream is
+ * (codes[i >> 2] >> (2 * (i & 3))) & 3 with A = 0, C = 1, G = 2, T/U = 3 (the order of vendor/nthash.hpp:51), and
+ * bit (i & 7) of invalid[i >> 3] is set when base i is not a base (N, IUPAC codes, anything seedTab maps to 0:
+ * vendor/nthash.hpp:189-228); invalid may be NULL when every base is valid.  Same results as the ASCII calls on the
+ * same sequences (the five raw bytes 1 3 4 5 7 that the reference also hashes have no packed form; btlbf_pack_seqs
+ * refuses them).  offsets, outputs and the window convention are those of the ASCII calls and keep counting BASES.
+ * Host buffers: ceil(n_bases / 4) and ceil(n_bases / 8) bytes.  Device buffers (_dev): 16-byte aligned and padded to
+ * a multiple of 16 bytes.  A quarter to three eighths of the host->device bytes of the ASCII calls. ---- */
+int btlbf_pack_seqs(const char *bases, uint64_t n_bases, uint8_t *codes, uint8_t *invalid, int threads,
+                    uint64_t *n_invalid); /* host packer (threads = 0: all cores); invalid may be NULL if the input has none */
+int btlbf_insert_seqs_packed(btlbf_filter *f, const uint8_t *codes, const uint8_t *invalid, const uint64_t *offsets,
+                             uint64_t n_seqs, uint64_t *n_kmers);
+int btlbf_contains_seqs_packed(btlbf_filter *f, const uint8_t *codes, const uint8_t *invalid, const uint64_t *offsets,
+                               uint64_t n_seqs, uint8_t *hit_bits, uint8_t *valid_bits, uint64_t *n_kmers,
+                               uint64_t *n_hits);
+int btlbf_insert_seqs_packed_async(btlbf_filter *f, const uint8_t *codes, const uint8_t *invalid,
+                                   const uint64_t *offsets, uint64_t n_seqs, uint64_t *counts_out);
+int btlbf_contains_seqs_packed_async(btlbf_filter *f, const uint8_t *codes, const uint8_t *invalid,
+                                     const uint64_t *offsets, uint64_t n_seqs, uint8_t *hit_bits,
+                                     uint8_t *valid_bits, uint64_t *counts_out);
+int btlbf_insert_seqs_packed_dev(btlbf_filter *f, const void *d_codes, const void *d_invalid, uint64_t n_bases,
+                                 const uint64_t *d_offsets, uint64_t n_seqs, uint64_t *d_stats);
+int btlbf_contains_seqs_packed_dev(btlbf_filter *f, const void *d_codes, const void *d_invalid, uint64_t n_bases,
+                                   const uint64_t *d_offsets, uint64_t n_seqs, uint32_t *d_hit_bits,
+                                   uint32_t *d_valid_bits, uint64_t *d_stats);
 int btlbf_insert_and_check_seqs(btlbf_filter *f, const char *bases, const uint64_t *offsets,
                                 uint64_t n_seqs, uint8_t *found_bits, uint8_t *valid_bits,
                                 uint64_t *n_kmers);
