@@ -6,8 +6,8 @@ CUDA kernels).  Importing the classes requires the built CUDA library; there is 
 """
 from ._build import build_library  # noqa: F401
 from ._capi import BLOOM, COUNTING8, BtlbfError, lib  # noqa: F401
-from .filters import (BitVector, BloomFilter, Context, CountingBloomFilter, KmerBloomFilter, QueryResult,  # noqa: F401
-                      as_batch, insertSeq, unpack_bits)
+from .filters import (BitVector, BloomFilter, Context, CountingBloomFilter, KmerBloomFilter, PackedBatch,  # noqa: F401
+                      QueryResult, as_batch, insertSeq, pack_seqs, unpack_bits)
 
 __all__ = ["BitVector", "BloomFilter", "CountingBloomFilter", "KmerBloomFilter", "Context", "QueryResult", "insertSeq", "as_batch",
-           "unpack_bits", "build_library", "lib", "BtlbfError", "BLOOM", "COUNTING8"]
+           "unpack_bits", "PackedBatch", "pack_seqs", "build_library", "lib", "BtlbfError", "BLOOM", "COUNTING8"]

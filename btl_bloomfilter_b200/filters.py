@@ -37,6 +37,34 @@ def _ptr(a):
     return None if a is None or a.size == 0 else C.c_void_p(a.ctypes.data)
 
 
+class PackedBatch:
+    """A flat batch as 2 bits per base (include/btlbf.h "2-bit packed input"): codes (4 bases per byte, A0 C1 G2 T3,
+    the order of vendor/nthash.hpp:51), invalid (one bit per base, or None when every base is one of ACGTUacgtu) and
+    the offsets of the ASCII batch (they keep counting bases)."""
+
+    def __init__(self, codes, invalid, offsets, n_invalid=0):
+        self.codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        self.invalid = None if invalid is None else np.ascontiguousarray(invalid, dtype=np.uint8)
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self.n_bases = int(self.offsets[-1]) if self.offsets.size else 0
+        self.n_invalid = int(n_invalid)
+
+
+def pack_seqs(seqs, threads=0, codes_out=None, invalid_out=None, keep_invalid=False):
+    """ASCII batch -> PackedBatch through the library's host packer (btlbf_pack_seqs; `threads` 0 = all cores).
+    codes_out / invalid_out: optional preallocated (e.g. pinned) uint8 arrays of ceil(n/4) / ceil(n/8) bytes.
+    The invalid plane is dropped when the input has no invalid base (unless keep_invalid)."""
+    bases, off = as_batch(seqs)
+    n = int(bases.size)
+    codes = np.zeros((n + 3) // 4, np.uint8) if codes_out is None else codes_out
+    invalid = np.zeros((n + 7) // 8, np.uint8) if invalid_out is None else invalid_out
+    if codes.size < (n + 3) // 4 or invalid.size < (n + 7) // 8:
+        raise ValueError("packed outputs need %d and %d bytes" % ((n + 3) // 4, (n + 7) // 8))
+    bad = C.c_uint64()
+    check(lib().btlbf_pack_seqs(_ptr(bases), n, _ptr(codes), _ptr(invalid), int(threads), C.byref(bad)))
+    return PackedBatch(codes, invalid if (bad.value or keep_invalid) else None, off, bad.value)
+
+
 def _p64(a):
     return a.ctypes.data_as(_capi.u64p)
 
@@ -323,6 +351,46 @@ class _DeviceFilter:
         check(self._L.btlbf_contains_seqs_async(self._h, _ptr(bases), _p64(off), off.size - 1, _ptr(hit_out),
                                                 _ptr(valid_out), _ptr(counts_out)))
         return bases, off
+
+    # -- 2-bit packed input (btlbf_*_seqs_packed): same results as the ASCII calls on the same sequences
+    def insertSeqsPacked(self, pk):
+        nk = C.c_uint64()
+        check(self._L.btlbf_insert_seqs_packed(self._h, _ptr(pk.codes), _ptr(pk.invalid), _p64(pk.offsets),
+                                               pk.offsets.size - 1, C.byref(nk)))
+        return nk.value
+
+    def containsSeqsPacked(self, pk, hit_out=None, valid_out=None, want_valid=True):
+        n = pk.n_bases
+        hits = np.zeros(bit_bytes(n), np.uint8) if hit_out is None else hit_out
+        valid = valid_out if valid_out is not None else (np.zeros(bit_bytes(n), np.uint8) if want_valid else None)
+        if hits.size < bit_bytes(n) or (valid is not None and valid.size < bit_bytes(n)):
+            raise ValueError("output arrays need %d bytes" % bit_bytes(n))
+        nk, nh = C.c_uint64(), C.c_uint64()
+        check(self._L.btlbf_contains_seqs_packed(self._h, _ptr(pk.codes), _ptr(pk.invalid), _p64(pk.offsets),
+                                                 pk.offsets.size - 1, _ptr(hits), _ptr(valid), C.byref(nk), C.byref(nh)))
+        return QueryResult(n, pk.offsets, self.getKmerSize(), hits, valid, nk.value, nh.value)
+
+    def insertSeqsPackedAsync(self, pk, counts_out):
+        """Queue insertSeqsPacked; the batch and counts_out stay alive and untouched until Context.sync()."""
+        check(self._L.btlbf_insert_seqs_packed_async(self._h, _ptr(pk.codes), _ptr(pk.invalid), _p64(pk.offsets),
+                                                     pk.offsets.size - 1, _ptr(counts_out)))
+
+    def containsSeqsPackedAsync(self, pk, hit_out, counts_out, valid_out=None):
+        if hit_out.size < bit_bytes(pk.n_bases):
+            raise ValueError("hit_out needs %d bytes" % bit_bytes(pk.n_bases))
+        check(self._L.btlbf_contains_seqs_packed_async(self._h, _ptr(pk.codes), _ptr(pk.invalid), _p64(pk.offsets),
+                                                       pk.offsets.size - 1, _ptr(hit_out), _ptr(valid_out),
+                                                       _ptr(counts_out)))
+
+    def insertSeqsPackedDevice(self, d_codes, d_invalid, n_bases, d_offsets, n_seqs, d_stats=0):
+        check(self._L.btlbf_insert_seqs_packed_dev(self._h, C.c_void_p(d_codes), C.c_void_p(d_invalid or 0), n_bases,
+                                                   C.c_void_p(d_offsets), n_seqs, C.c_void_p(d_stats or 0)))
+
+    def containsSeqsPackedDevice(self, d_codes, d_invalid, n_bases, d_offsets, n_seqs, d_hit_bits=0, d_valid_bits=0,
+                                 d_stats=0):
+        check(self._L.btlbf_contains_seqs_packed_dev(self._h, C.c_void_p(d_codes), C.c_void_p(d_invalid or 0), n_bases,
+                                                     C.c_void_p(d_offsets), n_seqs, C.c_void_p(d_hit_bits or 0),
+                                                     C.c_void_p(d_valid_bits or 0), C.c_void_p(d_stats or 0)))
 
     # -- device-resident batches (asynchronous on the context's stream; pointers are raw device addresses)
     def insertSeqsDevice(self, d_bases, n_bases, d_offsets, n_seqs, d_stats=0):

@@ -55,7 +55,7 @@ class _EmuFilter:
         stats = np.zeros(2, np.uint64)
         info = np.zeros(3, np.uint64)
         self.be._call(op, self.kind, self.size, self.h, self.k, self.thr, self.seeds, self.h2, self.data, bases, off,
-                      hit, valid, counts, None, None, stats, info)
+                      hit, valid, counts, None, None, stats, info, packed=self.be.packed and op in (0, 1))
         self.deferred += int(info[0])
         self.rounds += int(info[1])
         self.be.bin_overflow = int(info[2])
@@ -98,18 +98,24 @@ class EmuBackend:
     name = "emu"
 
     def __init__(self, chunk=1 << 20, batch=1 << 20, resv_log2=16, list_log2=10, force_generic=0, query_mode=0,
-                 bin_shift=0, bin_writers=3, bin_slack_pct=20):
+                 bin_shift=0, bin_writers=3, bin_slack_pct=20, packed=False):
         build_emu()
         self.L = C.CDLL(EMU_SO)
+        self.packed = packed  # insert / contains read the batch as 2-bit codes + invalid plane (btlbf_pack_seqs)
         self.bin_overflow = 0
         self.opts = dict(chunk=chunk, batch=batch, resv_log2=resv_log2, list_log2=list_log2,
                          force_generic=force_generic, query_mode=query_mode, bin_shift=bin_shift,
                          bin_writers=bin_writers, bin_slack_pct=bin_slack_pct)
 
     def _call(self, op, kind, size, h, k, thr, seeds, h2, filt, bases, off, hit, valid, counts, hashes, strands, stats,
-              info):
+              info, packed=False):
         def p(a):
             return None if a is None else C.c_void_p(a.ctypes.data)
+        invalid = None
+        if packed and bases.size:
+            from btl_bloomfilter_b200 import pack_seqs  # the product's host packer (host code only)
+            pk = pack_seqs((bases, off))
+            bases, invalid = pk.codes, pk.invalid
         sp = (C.c_char_p * len(seeds))(*[s.encode() for s in seeds]) if seeds else None
         msg = C.create_string_buffer(256)
         o = self.opts
@@ -119,7 +125,8 @@ class EmuBackend:
                                p(valid), p(counts), p(hashes), p(strands), p(stats), C.c_int(o["force_generic"]),
                                C.c_int(o["query_mode"]), C.c_uint64(o["chunk"]), C.c_uint64(o["batch"]),
                                C.c_uint(o["resv_log2"]), C.c_uint(o["list_log2"]), p(info), msg, C.c_size_t(256),
-                               C.c_uint(o["bin_shift"]), C.c_uint(o["bin_writers"]), C.c_uint(o["bin_slack_pct"]))
+                               C.c_uint(o["bin_shift"]), C.c_uint(o["bin_writers"]), C.c_uint(o["bin_slack_pct"]),
+                               p(invalid), C.c_int(1 if packed and bases.size else 0))
         if rc != 0:
             raise ValueError(msg.value.decode())
 
@@ -141,14 +148,20 @@ class EmuBackend:
 
 
 class _GpuFilter:
-    def __init__(self, f):
+    def __init__(self, f, packed=False):
         self.f = f
+        self.packed = packed
 
     def insert(self, seqs):
+        if self.packed:
+            return self.f.insertSeqsPacked(self.f._pack(_batch(seqs)))
         return self.f.insertSeqs(_batch(seqs))
 
     def contains(self, seqs):
-        r = self.f.containsSeqs(_batch(seqs))
+        if self.packed:
+            r = self.f.containsSeqsPacked(self.f._pack(_batch(seqs)))
+        else:
+            r = self.f.containsSeqs(_batch(seqs))
         return r.n_kmers, r.n_hits, r.hit_bits, r.valid_bits
 
     def insert_and_check(self, seqs):
@@ -183,9 +196,10 @@ class _GpuFilter:
 class GpuBackend:
     name = "gpu"
 
-    def __init__(self, **opts):
+    def __init__(self, packed=False, **opts):
         import btl_bloomfilter_b200 as B
         self.B = B
+        self.packed = packed  # insert / contains go through btlbf_pack_seqs + the *_seqs_packed entry points
         self.ctx = B.Context(0)
         # translate the emulator's option names
         m = {"chunk": "chunk_bases", "batch": "cbf_batch", "bin_shift": "bin_part_log2"}
@@ -206,4 +220,5 @@ class GpuBackend:
             f = B.CountingBloomFilter(size, h, k, thr, ctx=self.ctx)
         if seeds:
             f.setSeeds(seeds, h2)
-        return _GpuFilter(f)
+        f._pack = B.pack_seqs
+        return _GpuFilter(f, self.packed)

@@ -140,7 +140,8 @@ void ordered_apply(Ordered& st, const SeqParams& chunk, int kind, uint64_t batch
 	for (uint64_t b0 = 0; b0 < chunk.n_windows; b0 += batch) {
 		SeqParams P = chunk;
 		uint64_t bw = chunk.n_windows - b0 < batch ? chunk.n_windows - b0 : batch;
-		P.bases = chunk.bases + b0;
+		P.bases = chunk.bases + (chunk.packed ? b0 >> 2 : b0); // advance_input() of capi.cu
+		P.invalid = chunk.invalid ? chunk.invalid + (b0 >> 3) : nullptr;
 		P.n_bases = chunk.n_bases > b0 ? chunk.n_bases - b0 : 0;
 		P.base0 = chunk.base0 + b0;
 		P.n_windows = bw;
@@ -212,8 +213,11 @@ int emu_seq_op(int pub_op, int kind, uint64_t size, unsigned h, unsigned k, unsi
                const uint64_t* offsets, uint64_t n_seqs, uint32_t* hit, uint32_t* valid, uint8_t* counts,
                uint64_t* hashes, uint8_t* strands, uint64_t* stats, int force_generic, int query_mode,
                uint64_t chunk, uint64_t batch, unsigned resv_log2, unsigned list_log2, uint64_t* info,
-               char* msg, size_t msg_cap, unsigned bin_shift, unsigned bin_writers, unsigned bin_slack_pct)
+               char* msg, size_t msg_cap, unsigned bin_shift, unsigned bin_writers, unsigned bin_slack_pct,
+               const uint8_t* invalid, int packed)
 {
+	// packed != 0: `bases` holds 2-bit codes (4 per byte) and `invalid` one bit per base or null (btlbf.h,
+	// "2-bit packed input"); offsets keep counting bases
 	SeqParams proto;
 	HostSeedTables t;
 	std::string err = build_hash_proto(proto, t, k, h, n_seeds ? seeds : nullptr, n_seeds, h2);
@@ -246,10 +250,20 @@ int emu_seq_op(int pub_op, int kind, uint64_t size, unsigned h, unsigned k, unsi
 		uint64_t cw = n_bases - c0 < chunk ? n_bases - c0 : chunk;
 		uint64_t cb = n_bases - c0 < cw + k - 1 ? n_bases - c0 : cw + k - 1;
 		// the device chunk buffer is a private copy: reads past cb must not see the caller's bytes
-		std::vector<uint8_t> dev(cb + 16);
-		memcpy(dev.data() + 0, bases + c0, cb);
-		memset(dev.data() + cb, 'A', 16);
+		std::vector<uint8_t> dev(cb + 32), inv(cb / 8 + 32);
+		if (packed) { // whole 16-byte words of both planes, the bytes past the copies hold junk
+			memset(dev.data(), 0xb7, dev.size());
+			memset(inv.data(), 0x00, inv.size());
+			memcpy(dev.data(), bases + (c0 >> 2), (cb + 3) >> 2);
+			if (invalid) memcpy(inv.data(), invalid + (c0 >> 3), (cb + 7) >> 3);
+		} else {
+			memcpy(dev.data() + 0, bases + c0, cb);
+			memset(dev.data() + cb, 'A', 16);
+		}
 		SeqParams P = proto;
+		P.packed = packed ? 1 : 0;
+		P.invalid = packed && invalid ? inv.data() : nullptr;
+		if (packed) P.force_generic = 0;
 		P.bases = dev.data();
 		P.n_bases = cb;
 		P.base0 = c0;

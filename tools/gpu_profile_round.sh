@@ -6,7 +6,7 @@
 tag=$1
 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err || { echo "bench failed"; tail -5 gpurun_out/bench_$tag.err; exit 1; }
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$tag.json 2>> gpurun_out/bench_$tag.err
-args="--steps 8 --warmup 3 --no-e2e --no-cpu-baseline"
+args="--steps 8 --warmup 3 --no-e2e --no-cpu-baseline --no-configs --no-job"
 python bench.py $args > gpurun_out/prof_plain_$tag.json 2>> gpurun_out/bench_$tag.err || { echo "short bench failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/launches_$tag.csv python bench.py $args > gpurun_out/ncu_list_$tag.log 2>&1
