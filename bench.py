@@ -280,6 +280,9 @@ class Env:
         self.read_bases = self.n_reads * READ_LEN
         self.token = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.host = None
+        self.no_multicast = None  # why the in-switch merge is not used (set on first failure)
+        if self.world > 1:
+            self.ctx.set_option("wrap_accumulate", 1)  # symmetric-memory filters keep the build's accumulation
 
     def barrier(self):
         if self.world > 1:
@@ -341,9 +344,40 @@ class Env:
         H["roff"] = t_roff.numpy().view(np.uint64)
         H["counts_t"] = torch.zeros((64, 4), dtype=torch.int64).pin_memory()
         H["counts"] = H["counts_t"].numpy().view(np.uint64)
+        # the same batches as 2 bits per base (btlbf_pack_seqs: the library's host packer), in pinned memory; the
+        # synthetic batches hold no invalid base, so the invalid plane is dropped (as the packer's caller would)
+        if not self.args.no_packed:
+            B = self.B
+            H["genome_pk_t"], H["reads_pk_t"], H["genome_pk"], H["reads_pk"] = [], [], {}, []
+            scratch = np.zeros((max(max(self.g_len[:n_host]), self.read_bases) + 7) // 8, np.uint8)
+            t0 = time.perf_counter()
+            nb = 0
+            for j in range(n_host):
+                tr = torch.empty((self.read_bases + 3) // 4 + 16, dtype=torch.uint8).pin_memory()
+                pk = B.pack_seqs((H["reads"][j].numpy(), H["roff"]), codes_out=tr.numpy(), invalid_out=scratch)
+                assert pk.invalid is None
+                H["reads_pk_t"].append(tr)
+                H["reads_pk"].append(pk)
+                tg = torch.empty((self.g_len[j] + 3) // 4 + 16, dtype=torch.uint8).pin_memory()
+                H["genome_pk_t"].append(tg)
+                nb += self.read_bases
+            H["pack_reads_gbases_s"] = nb / (time.perf_counter() - t0) / 1e9
         torch.cuda.synchronize()
         self.host = H
         return H
+
+    def packed_genome(self, j, n):
+        """PackedBatch of the first n bases of host genome chunk j (k differs between the configs)."""
+        H = self.host
+        key = (j, n)
+        if key not in H["genome_pk"]:
+            scratch = np.zeros((n + 7) // 8, np.uint8)
+            pk = self.B.pack_seqs((H["genome"][j].numpy()[:n], np.array([0, n], np.uint64)),
+                                  codes_out=H["genome_pk_t"][j].numpy(), invalid_out=scratch)
+            assert pk.invalid is None
+            H["genome_pk"] = {kk: v for kk, v in H["genome_pk"].items() if kk[0] != j}
+            H["genome_pk"][key] = pk
+        return H["genome_pk"][key]
 
 
 def make_filter(env, cfg):
@@ -354,6 +388,36 @@ def make_filter(env, cfg):
     if cfg.get("seeds"):
         f.setSeeds(cfg["seeds"], cfg.get("h2", 1))
     return f
+
+
+def make_sharded_filter(env, cfg):
+    """N > 1: this rank's partial filter + the object that merges the N of them.  BloomFilters go into symmetric memory
+    and are merged inside NVSwitch (btlbf_merge_multimem) where the box has NVLS multicast; otherwise -- and for counting
+    filters, whose saturating add has no multimem form -- the library's own allocation and the peer-memory kernel."""
+    from btl_bloomfilter_b200 import parallel
+    B, want = env.B, env.args.merge
+    if cfg["kind"] == "bloom" and want in ("auto", "multimem") and not env.no_multicast:
+        try:
+            f, hdl = parallel.symmetric_filter(B.BloomFilter, cfg["size"], cfg["h"], cfg["k"], env.ctx)
+            if parallel.MultimemMerge.available(hdl):
+                if cfg.get("seeds"):
+                    f.setSeeds(cfg["seeds"], cfg.get("h2", 1))
+                return f, parallel.MultimemMerge(env.ctx, hdl, filter_bytes(cfg)), "multimem"
+            env.no_multicast = "multicast_ptr == 0"
+            del f, hdl
+        except Exception as e:  # noqa: BLE001  (symmetric memory unavailable: every rank takes the same branch)
+            env.no_multicast = "%s: %s" % (type(e).__name__, str(e)[:120])
+        if want == "multimem":
+            raise SystemExit("--merge multimem: " + str(env.no_multicast))
+    f = make_filter(env, cfg)
+    return f, parallel.PeerMerge(env.ctx, *f.device_ptr(), f.KIND), "peer"
+
+
+MERGE_HOW = {
+    "multimem": "btlbf_merge_multimem: one kernel per GPU, multimem.ld_reduce.or + multimem.st over an NVLS multicast mapping "
+                "of the partial filters (symmetric memory); the OR happens inside NVSwitch",
+    "peer": "btlbf_merge_peers: one kernel per GPU over NVLink peer memory (reduce-scatter + all-gather in one pass)",
+}
 
 
 def filter_view(env, filt):
@@ -371,11 +435,10 @@ def merge_parity(env, cfg):
     from btl_bloomfilter_b200._capi import check
     torch, ctx = env.torch, env.ctx
     k = cfg["k"]
-    a = make_filter(env, cfg)
+    a, pm, how = make_sharded_filter(env, cfg)
     st = torch.zeros(2, dtype=torch.int64, device=env.dev)
     n0 = env.insert_len(0, k)
     a.insertSeqsDevice(env.g[0].data_ptr(), n0, env.goff(n0).data_ptr(), 1, st.data_ptr())
-    pm = parallel.PeerMerge(ctx, *a.device_ptr(), a.KIND)
     pm.merge()
     pm.close()
     b = make_filter(env, cfg)
@@ -396,8 +459,8 @@ def merge_parity(env, cfg):
     pop = a.getPop() if cfg["kind"] == "bloom" else a.popCount()
     t = torch.tensor([1 if same else 0, pop, -pop], dtype=torch.int64, device=env.dev)
     env.dist.all_reduce(t, op=env.dist.ReduceOp.MIN)
-    del a, b, part, tmp
-    return {"merge_parity": bool(t[0] == 1), "identical_popcount_on_all_ranks": bool(int(t[1]) == -int(t[2])),
+    del a, b, part, tmp, pm
+    return {"merge_parity": bool(t[0] == 1), "merge": how, "identical_popcount_on_all_ranks": bool(int(t[1]) == -int(t[2])),
             "popcount": int(t[1]), "chunks": env.world,
             "how": "sharded build + fused merge == the same chunks built on one GPU (byte-compared on the device)"}
 
@@ -409,14 +472,14 @@ def run_config(env, name, cfg, S, W, headline):
     counting = kind == "counting"
     n_g, n_r = len(env.g), len(env.r)
     n_q = max(1, min(n_r, S))  # the read buffers the timed queries cycle over: their chunks are inserted by then
-    filt = make_filter(env, cfg)
     out = {"workload": cfg["workload"], "k": k, "hashes": h, "filter_bytes": filter_bytes(cfg)}
-    pm = None
+    pm, merge_how = None, None
     if world > 1:
-        from btl_bloomfilter_b200 import parallel
         if headline or counting:
             out["merge_check"] = merge_parity(env, cfg)
-        pm = parallel.PeerMerge(ctx, *filt.device_ptr(), filt.KIND)
+        filt, pm, merge_how = make_sharded_filter(env, cfg)
+    else:
+        filt = make_filter(env, cfg)
     d_stats = torch.zeros(4, dtype=torch.int64, device=env.dev)
 
     def build_dev(i):
@@ -566,6 +629,49 @@ def run_config(env, name, cfg, S, W, headline):
             assert np.array_equal(counts[:S2, 2], counts[:S2, 3]) and counts[:S2, 2].all(), "e2e: a queried k-mer was not found"
         e2e = {"kmers": ke, "seconds": dt, "steps": S2,
                "h2d": int(goffs[0][1]) + env.read_bases + (env.n_reads + 1) * 8 + 16, "d2h": int(Hh["hits"][0].numel()) + 32}
+        if not env.args.no_packed:
+            # the same steps from 2-bit packed host buffers (btlbf_*_seqs_packed_async): a quarter of the H2D bytes
+            gpk = [env.packed_genome(j, int(goffs[j][1])) for j in range(n_host)]
+
+            def build_host_packed(i, slot):
+                filt.insertSeqsPackedAsync(gpk[i % n_host], counts[slot, 0:2])
+
+            def query_host_packed(i, slot):
+                j = i % nh_q
+                filt.containsSeqsPackedAsync(Hh["reads_pk"][j], Hh["hits"][j].numpy(), counts[slot, 2:4])
+
+            if not counting:
+                filt.clear()
+            for i in range(min(2, S2)):
+                build_host_packed(i, 60 + (i & 1))
+            ctx.sync()
+            if not counting:
+                merge_host()
+            for i in range(min(2, S2)):
+                query_host_packed(i, 60 + (i & 1))
+            ctx.sync()
+            if not counting:
+                filt.clear()
+            counts[:] = 0
+            env.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(S2):
+                build_host_packed(i, i)
+            if pm is not None:
+                ctx.sync()
+                merge_host()
+            for i in range(S2):
+                query_host_packed(i, i)
+            ctx.sync()
+            dtp = time.perf_counter() - t0
+            env.barrier()
+            kp = int(counts[:S2, 0].sum() + counts[:S2, 2].sum())
+            assert kp == ke, "packed e2e: %d k-mers, the ASCII calls saw %d" % (kp, ke)
+            if kind == "bloom":
+                assert np.array_equal(counts[:S2, 2], counts[:S2, 3]), "packed e2e: a queried k-mer was not found"
+            e2e.update({"kmers_packed": kp, "seconds_packed": dtp,
+                        "h2d_packed": (int(goffs[0][1]) + 3) // 4 + (env.read_bases + 3) // 4 + (env.n_reads + 1) * 8 + 16})
         if headline:
             def step_host_sync(i):
                 j = i % n_host
@@ -584,17 +690,20 @@ def run_config(env, name, cfg, S, W, headline):
     # ---- reductions over ranks (max time, summed work)
     if world > 1:
         t = torch.tensor([ms_total, ms_build, ms_merge, ms_query, e2e["seconds"] if e2e else 0.0,
-                          e2e.get("seconds_sync", 0.0) if e2e else 0.0], dtype=torch.float64, device=env.dev)
+                          e2e.get("seconds_sync", 0.0) if e2e else 0.0, e2e.get("seconds_packed", 0.0) if e2e else 0.0],
+                         dtype=torch.float64, device=env.dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, ms_build, ms_merge, ms_query = (float(x) for x in t[:4])
-        w = torch.tensor([k_ins, k_qry, e2e["kmers"] if e2e else 0, launches, e2e.get("kmers_sync", 0) if e2e else 0],
-                         dtype=torch.int64, device=env.dev)
+        w = torch.tensor([k_ins, k_qry, e2e["kmers"] if e2e else 0, launches, e2e.get("kmers_sync", 0) if e2e else 0,
+                          e2e.get("kmers_packed", 0) if e2e else 0], dtype=torch.int64, device=env.dev)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        k_ins_all, k_qry_all, ke_all, launches_all, ks_all = [int(x) for x in w]
+        k_ins_all, k_qry_all, ke_all, launches_all, ks_all, kp_all = [int(x) for x in w]
         if e2e:
             e2e["seconds"], e2e["kmers"] = float(t[4]), ke_all
             if "seconds_sync" in e2e:
                 e2e["seconds_sync"], e2e["kmers_sync"] = float(t[5]), ks_all
+            if "seconds_packed" in e2e:
+                e2e["seconds_packed"], e2e["kmers_packed"] = float(t[6]), kp_all
     else:
         k_ins_all, k_qry_all, launches_all = k_ins, k_qry, launches
 
@@ -613,14 +722,25 @@ def run_config(env, name, cfg, S, W, headline):
     if world > 1:
         # what the ranks do when nothing connects them: the same phases without the merge
         out["per_gpu_rate"] = (k_ins + k_qry) / ((ms_build + ms_query) * 1e-3) / 1e9
-        out["merge"] = {"ms": ms_merge, "filter_bytes": filter_bytes(cfg), "how": "btlbf_merge_peers: one kernel per GPU over "
-                        "NVLink peer memory (reduce-scatter + all-gather in one pass), two stream-ordered barriers",
-                        "link_GBps_per_gpu_per_direction": 2.0 * (world - 1) / world * filter_bytes(cfg) / (ms_merge * 1e-3) / 1e9}
+        per_dir = filter_bytes(cfg) * (1.0 if merge_how == "multimem" else 2.0 * (world - 1) / world)
+        out["merge"] = {"ms": ms_merge, "filter_bytes": filter_bytes(cfg), "kind": merge_how,
+                        "how": MERGE_HOW[merge_how] + ", two stream-ordered barriers",
+                        "link_bytes_per_gpu_per_direction": per_dir,
+                        "link_GBps_per_gpu_per_direction": per_dir / (ms_merge * 1e-3) / 1e9}
+        if env.no_multicast:
+            out["merge"]["multimem_unavailable"] = str(env.no_multicast)
     if e2e:
         out["e2e"] = {"value": e2e["kmers"] / e2e["seconds"] / 1e9, "unit": "Gk-mer/s", "steps": e2e["steps"],
                       "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                       "api": "btlbf_insert_seqs_async + btlbf_contains_seqs_async (streaming), pinned host buffers"
                              + (", btlbf_merge_peers between the phases" if world > 1 else "")}
+        if "seconds_packed" in e2e:
+            out["e2e_packed"] = {"value": e2e["kmers_packed"] / e2e["seconds_packed"] / 1e9, "unit": "Gk-mer/s",
+                                 "steps": e2e["steps"], "h2d_bytes_per_step": e2e["h2d_packed"],
+                                 "d2h_bytes_per_step": e2e["d2h"],
+                                 "api": "btlbf_insert_seqs_packed_async + btlbf_contains_seqs_packed_async: the same batches "
+                                        "held by the caller as 2 bits per base (packed once, outside the timed region, by "
+                                        "btlbf_pack_seqs at %.2f Gbase/s on this host)" % env.host.get("pack_reads_gbases_s", 0.0)}
         if "seconds_sync" in e2e:
             out["e2e_sync"] = {"value": e2e["kmers_sync"] / e2e["seconds_sync"] / 1e9, "unit": "Gk-mer/s",
                                "steps": e2e["steps_sync"], "api": "btlbf_insert_seqs + btlbf_contains_seqs (blocking)"}
@@ -753,7 +873,10 @@ def main():
     ap.add_argument("--no-job", action="store_true", help="skip the strong-scaled full cfg2 job")
     ap.add_argument("--cpu-sample", type=int, default=8 << 20, help="bases per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--merge", default="auto", choices=["auto", "multimem", "peer"],
+                    help="N > 1 BloomFilter merge: in NVSwitch (multimem) when available, or the peer-memory kernel")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-packed", action="store_true", help="skip the 2-bit packed host-buffer leg (e2e_packed)")
     ap.add_argument("--chunk", type=int, default=CHUNK)
     ap.add_argument("--query-factor", type=int, default=4, help="read bases per query batch, in units of --chunk")
     ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity (0: leave as is)")

@@ -143,6 +143,8 @@ struct btlbf_ctx
 	int64_t bin_max_parts = 512;                // the sort-bin path widens the partitions until there are at most this many
 	int settle_error = 0;
 	int64_t peer_unroll = 1, peer_grid = 0, peer_mode = 0; // fused multi-GPU merge: vectors in flight per thread and peer, CTAs
+	int64_t mm_unroll = 4, mm_grid = 0;                    // in-switch (multimem) merge: 8-byte words in flight per thread, CTAs
+	int64_t wrap_accumulate = 0; // 1: filters over caller-owned memory may park k-mers too (the caller flushes before reading)
 	int64_t query_adaptive = 1;      // partitioned query: sample the batch, fall back to the early-exit kernel when few k-mers hit
 	int64_t query_adaptive_pct = 20; // ... fewer than this percentage of the sampled k-mers
 	int64_t query_adaptive_min_tiles = 256; // batches below this many 4096-window tiles are not sampled
@@ -596,6 +598,12 @@ extern "C" int btlbf_ctx_set_option(btlbf_ctx* ctx, const char* key, int64_t val
 		ctx->peer_mode = value;
 	} else if (k == "peer_grid") {
 		ctx->peer_grid = value < 0 ? 0 : value;
+	} else if (k == "mm_unroll") {
+		ctx->mm_unroll = value;
+	} else if (k == "mm_grid") {
+		ctx->mm_grid = value < 0 ? 0 : value;
+	} else if (k == "wrap_accumulate") {
+		ctx->wrap_accumulate = value != 0;
 	} else if (k == "query_adaptive") {
 		ctx->query_adaptive = value != 0;
 	} else if (k == "query_adaptive_min_tiles") {
@@ -1053,6 +1061,30 @@ extern "C" int btlbf_merge_peers(btlbf_ctx* ctx, int kind, void* const* bases, i
 	cudaError_t e = launch_peer_merge(M, s);
 	if (e != cudaSuccess)
 		return fail(BTLBF_ERR_CUDA, "peer merge launch failed: %s", cudaGetErrorString(e));
+	ctx->launches++;
+	return BTLBF_OK;
+}
+
+// The OR merge inside NVSwitch.  mc_base: a multicast (NVLS) address that maps the SAME byte range of every rank's
+// partial filter (e.g. torch.distributed._symmetric_memory: rendezvous(...).multicast_ptr of the tensor the filter
+// was wrapped around with btlbf_filter_wrap).  This rank reduces bytes btlbf_merge_slice(nbytes, world, rank) of all
+// replicas with multimem.ld_reduce.or and broadcasts them with multimem.st.  The caller brackets the launches of
+// all ranks with barriers, exactly as for btlbf_merge_peers.
+extern "C" int btlbf_merge_multimem(btlbf_ctx* ctx, int kind, void* mc_base, int world, int rank, uint64_t nbytes)
+{
+	if (kind != BTLBF_BLOOM)
+		return fail(BTLBF_ERR_ARG, "the in-switch merge is an OR: counting filters (saturating add) use btlbf_merge_peers");
+	if (!mc_base || ((uintptr_t)mc_base & 15u) || world < 1 || rank < 0 || rank >= world)
+		return fail(BTLBF_ERR_ARG, "bad multicast base / world / rank");
+	TRY(use(ctx));
+	LOCKED(ctx);
+	uint64_t lo, hi;
+	TRY(btlbf_merge_slice(nbytes, world, rank, &lo, &hi));
+	cudaStream_t s;
+	TRY(join(ctx, &s));
+	cudaError_t e = launch_multimem_or(mc_base, lo, hi, (unsigned)ctx->mm_unroll, (unsigned)ctx->mm_grid, s);
+	if (e != cudaSuccess)
+		return fail(BTLBF_ERR_CUDA, "multimem merge launch failed: %s", cudaGetErrorString(e));
 	ctx->launches++;
 	return BTLBF_OK;
 }
@@ -1754,7 +1786,7 @@ static int filter_op_dev(btlbf_filter* f, PublicOp op, const ChunkIO& io, cudaSt
 // through this library, so no k-mer stays parked in the partition buckets when a call returns.
 static int settle_if_wrapped(btlbf_filter* f)
 {
-	if (f->wrapped && f->ctx->acc.f == f)
+	if (f->wrapped && !f->ctx->wrap_accumulate && f->ctx->acc.f == f)
 		return settle(f->ctx);
 	return BTLBF_OK;
 }

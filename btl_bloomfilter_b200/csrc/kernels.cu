@@ -843,6 +843,57 @@ cudaError_t launch_peer_merge(const PeerMergeParams& M, cudaStream_t stream)
 	return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- K7 in the switch: OR merge over an NVLS multicast mapping
+// `mc` is a multicast address of the N partial filters (one replica per GPU, bound to one NVSwitch multicast
+// object).  multimem.ld_reduce.or returns the OR of all N replicas of a word -- the reduction happens inside the
+// switch, so this GPU receives 1/N of the filter instead of (N-1)/N -- and multimem.st writes the result to all N
+// replicas (the switch fans it out).  Per NVLink direction a GPU moves ~|filter| bytes instead of the
+// 2 (N-1)/N |filter| of the peer-memory kernel plus its own loads.  Bitwise reductions exist for .b32 / .b64
+// only (vector forms are floating point), so a thread moves UNROLL independent 8-byte words per iteration.
+// Saturating add has no multimem form: counting filters stay on peer_merge_kernel.
+template<int UNROLL>
+__global__ void __launch_bounds__(512) multimem_or_kernel(uint64_t* __restrict__ mc, uint64_t n_words)
+{
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * UNROLL;
+	for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x * UNROLL + threadIdx.x; i0 < n_words; i0 += stride) {
+		uint64_t v[UNROLL];
+#pragma unroll
+		for (int u = 0; u < UNROLL; u++) {
+			const uint64_t i = i0 + (uint64_t)u * blockDim.x;
+			v[u] = 0;
+			if (i < n_words)
+				asm volatile("multimem.ld_reduce.relaxed.sys.global.or.b64 %0, [%1];" : "=l"(v[u]) : "l"(mc + i) : "memory");
+		}
+#pragma unroll
+		for (int u = 0; u < UNROLL; u++) {
+			const uint64_t i = i0 + (uint64_t)u * blockDim.x;
+			if (i < n_words)
+				asm volatile("multimem.st.relaxed.sys.global.b64 [%0], %1;" ::"l"(mc + i), "l"(v[u]) : "memory");
+		}
+	}
+}
+
+cudaError_t launch_multimem_or(void* mc_base, uint64_t lo, uint64_t hi, unsigned unroll, unsigned grid_ctas, cudaStream_t stream)
+{
+	if (!mc_base || lo > hi || ((lo | hi | (uint64_t)(uintptr_t)mc_base) & 15u))
+		return cudaErrorInvalidValue;
+	const uint64_t n_words = (hi - lo) / 8;
+	if (n_words == 0)
+		return cudaSuccess;
+	uint64_t* p = reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(mc_base) + lo);
+	const unsigned u = unroll == 1 || unroll == 2 || unroll == 8 ? unroll : 4;
+	uint64_t want = (n_words + 512ull * u - 1) / (512ull * u);
+	const uint64_t cap = grid_ctas ? grid_ctas : sm_count() * 4;
+	const unsigned grid = (unsigned)(want > cap ? cap : want);
+	switch (u) {
+	case 1: multimem_or_kernel<1><<<grid, 512, 0, stream>>>(p, n_words); break;
+	case 2: multimem_or_kernel<2><<<grid, 512, 0, stream>>>(p, n_words); break;
+	case 8: multimem_or_kernel<8><<<grid, 512, 0, stream>>>(p, n_words); break;
+	default: multimem_or_kernel<4><<<grid, 512, 0, stream>>>(p, n_words); break;
+	}
+	return cudaGetLastError();
+}
+
 cudaError_t launch_merge(void* dst, const void* src, uint64_t nbytes, int saturating_add, cudaStream_t stream)
 {
 	uint64_t nvec = nbytes / 16;

@@ -189,6 +189,8 @@ struct PeerMergeParams
 	uint32_t mode;   // 0: the merge; measurement only: 1 = peer loads without peer stores, 2 = peer stores without peer loads
 };
 cudaError_t launch_peer_merge(const PeerMergeParams& M, cudaStream_t stream);
+// OR of all replicas of bytes [lo, hi) of an NVLS multicast mapping, written back to all replicas
+cudaError_t launch_multimem_or(void* mc_base, uint64_t lo, uint64_t hi, unsigned unroll, unsigned grid_ctas, cudaStream_t stream);
 cudaError_t launch_synth_genome(uint8_t* out, uint64_t start, uint64_t n, uint64_t seed,
                                 cudaStream_t stream);
 cudaError_t launch_synth_reads(uint8_t* out, uint64_t first_read, uint64_t n_reads,

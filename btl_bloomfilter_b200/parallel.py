@@ -15,6 +15,10 @@ Two implementations of that merge:
                                   stores): each rank reduces its 1/N byte range of all N partial filters
                                   in registers and writes the result into all N of them -- no staging
                                   buffer, no separate reduce pass (btlbf_merge_peers)
+  MultimemMerge                   the OR merge INSIDE NVSwitch: the partial filters live in symmetric memory
+                                  bound to one multicast object; multimem.ld_reduce.or pulls the OR of all N
+                                  replicas of this rank's byte range through the switch and multimem.st fans
+                                  the result out to all N (btlbf_merge_multimem).  BloomFilter only.
 """
 import ctypes as C
 import os
@@ -248,3 +252,58 @@ def fused_merge_filter(filt, group=None):
         pm.merge()
     finally:
         pm.close()
+
+
+# ---------------------------------------------------------------- in-switch (NVLS multicast) merge
+def symmetric_filter(cls, size, hashNum, kmerSize, ctx, group=None, threshold=0):
+    """A filter of class `cls` whose array lives in symmetric memory (torch.distributed._symmetric_memory: one
+    allocation per rank, mapped into every peer and -- where NVSwitch multicast is available -- bound to one
+    multicast object).  Collective.  Returns (filter, rendezvous handle); handle.multicast_ptr is 0 without NVLS.
+    The array is zeroed.  Context option wrap_accumulate=1 keeps the partitioned build's accumulation for it."""
+    import torch.distributed._symmetric_memory as symm_mem
+    nbytes = size // 8 if cls.KIND == 0 else size
+    pad = padded_bytes((nbytes + 15) // 16 * 16, dist.get_world_size(group))
+    dev = torch.device("cuda", ctx.device)
+    t = symm_mem.empty(pad, dtype=torch.uint8, device=dev)
+    t.zero_()
+    hdl = symm_mem.rendezvous(t, group if group is not None else dist.group.WORLD)
+    f = cls.from_device_memory(t, size, hashNum, kmerSize, threshold=threshold, ctx=ctx)
+    return f, hdl
+
+
+class MultimemMerge:
+    """OR merge of per-rank partial BloomFilters held in symmetric memory, reduced inside NVSwitch.
+
+    hdl: the rendezvous handle of the symmetric tensor the filter wraps (symmetric_filter()).  Collective:
+    every rank of the group constructs it and calls merge() / launch() together."""
+
+    def __init__(self, ctx, hdl, nbytes, kind=0, group=None):
+        if kind != 0:
+            raise ValueError("the in-switch merge is an OR: counting filters use PeerMerge")
+        mc = int(hdl.multicast_ptr)
+        if mc == 0:
+            raise RuntimeError("no NVLS multicast mapping on this system (multicast_ptr == 0)")
+        self.ctx, self.hdl, self.mc, self.nbytes, self.group = ctx, hdl, mc, int(nbytes), group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    @staticmethod
+    def available(hdl):
+        return int(getattr(hdl, "multicast_ptr", 0) or 0) != 0
+
+    def launch(self):
+        """The kernel alone; the caller brackets it (ctx.flush() before the first barrier, see PeerMerge.launch)."""
+        from ._capi import check
+        check(self.ctx.L.btlbf_merge_multimem(self.ctx.handle, 0, C.c_void_p(self.mc), self.world, self.rank, self.nbytes))
+
+    def merge(self):
+        self.ctx.flush()
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        self.launch()
+        self.ctx.sync()
+        dist.barrier(group=self.group)
+
+    def close(self):
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)

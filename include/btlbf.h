@@ -169,6 +169,17 @@ int btlbf_ipc_export(btlbf_ctx *ctx, const void *device_ptr, void *handle64, uin
 int btlbf_ipc_open(btlbf_ctx *ctx, const void *handle64, void **mapped_base);
 int btlbf_ipc_close(btlbf_ctx *ctx, void *mapped_base);
 int btlbf_merge_peers(btlbf_ctx *ctx, int kind, void *const *bases, int world, int rank, uint64_t nbytes);
+/* The same merge for BLOOM filters with the reduction done INSIDE NVSwitch (NVLS).  mc_base is a multicast
+ * address mapping the same byte range of every rank's partial filter (one replica per GPU bound to one multicast
+ * object -- cuMulticastCreate / cuMulticastBindMem, or torch.distributed._symmetric_memory whose rendezvous
+ * handle carries multicast_ptr; the filters are then btlbf_filter_wrap'ed around that symmetric allocation).
+ * ONE kernel per GPU: multimem.ld_reduce.or of byte range `rank` over all replicas, multimem.st of the result to
+ * all replicas; each NVLink direction of a GPU carries ~nbytes instead of 2 (world-1)/world nbytes + the loads.
+ * Same bracketing by the caller as btlbf_merge_peers.  COUNTING8 is refused (saturating add has no multimem
+ * reduction): use btlbf_merge_peers.  Context options "mm_unroll" (1, 2, 4, 8) and "mm_grid" tune the kernel;
+ * "wrap_accumulate" = 1 lets wrapped filters defer pass 2 of the partitioned build like owned ones (the caller
+ * then calls btlbf_ctx_flush before the merge, as PeerMerge / MultimemMerge in parallel.py do). */
+int btlbf_merge_multimem(btlbf_ctx *ctx, int kind, void *mc_base, int world, int rank, uint64_t nbytes);
 /* order-dependent updates (counting insert, insert_and_check): number of k-mers that had to wait for
  * the index-ordered residual rounds, and the number of such rounds, since the filter was created */
 int btlbf_filter_ordered_stats(btlbf_filter *f, uint64_t *deferred, uint64_t *rounds);

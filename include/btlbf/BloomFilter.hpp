@@ -133,6 +133,12 @@ class BloomFilter
 		btlbf::check(btlbf_insert_seqs(m_f, bases, offsets, nSeqs, &n), "insertSeqs");
 		return n;
 	}
+	uint64_t insertSeqs(const btlbf::PackedSeqBatch& b) // 2-bit packed input: same filter bytes as the ASCII batch
+	{
+		uint64_t n = 0;
+		btlbf::check(btlbf_insert_seqs_packed(m_f, b.codes.data(), b.invalidPlane(), b.offsets.data(), b.size(), &n), "insertSeqs");
+		return n;
+	}
 	// The query twin (README.md:46-57): one hit bit and one valid bit per window.
 	// FASTA / FASTQ files: the record loop of swig/writeBloom_rolling.cpp:19-59 (read a record, insertSeq) as one
 	// call; threads = 0 picks the number of parser threads.  Returns the k-mers inserted / found.
@@ -163,6 +169,16 @@ class BloomFilter
 		btlbf::check(
 		    btlbf_contains_seqs(m_f, bases, offsets, nSeqs, r.hitBits.data(), r.validBits.data(), &r.nKmers, &r.nHits),
 		    "containsSeqs");
+		return r;
+	}
+	btlbf::SeqHits containsSeqs(const btlbf::PackedSeqBatch& b) const
+	{
+		btlbf::SeqHits r;
+		r.hitBits.assign(btlbf::bitBytes(b.nBases()), 0);
+		r.validBits.assign(btlbf::bitBytes(b.nBases()), 0);
+		btlbf::check(btlbf_contains_seqs_packed(m_f, b.codes.data(), b.invalidPlane(), b.offsets.data(), b.size(),
+		                                        r.hitBits.data(), r.validBits.data(), &r.nKmers, &r.nHits),
+		             "containsSeqs");
 		return r;
 	}
 	// insertAndCheck of every k-mer in the reference's order: hit bit = "was already present".

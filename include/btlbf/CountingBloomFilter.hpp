@@ -96,6 +96,22 @@ class CountingBloomFilter
 		return n;
 	}
 	uint64_t insertSeqs(const std::vector<std::string>& seqs) { return insertSeqs(btlbf::SeqBatch(seqs)); }
+	uint64_t insertSeqs(const btlbf::PackedSeqBatch& b) // 2-bit packed input: same counters as the ASCII batch
+	{
+		uint64_t n = 0;
+		btlbf::check(btlbf_insert_seqs_packed(m_f, b.codes.data(), b.invalidPlane(), b.offsets.data(), b.size(), &n), "insertSeqs");
+		return n;
+	}
+	btlbf::SeqHits containsSeqs(const btlbf::PackedSeqBatch& b) const
+	{
+		btlbf::SeqHits r;
+		r.hitBits.assign(btlbf::bitBytes(b.nBases()), 0);
+		r.validBits.assign(btlbf::bitBytes(b.nBases()), 0);
+		btlbf::check(btlbf_contains_seqs_packed(m_f, b.codes.data(), b.invalidPlane(), b.offsets.data(), b.size(),
+		                                        r.hitBits.data(), r.validBits.data(), &r.nKmers, &r.nHits),
+		             "containsSeqs");
+		return r;
+	}
 	btlbf::SeqHits containsSeqs(const btlbf::SeqBatch& b) const
 	{
 		btlbf::SeqHits r;

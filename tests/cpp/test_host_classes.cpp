@@ -125,6 +125,18 @@ bloomScenario(const std::string& tmp)
 	for (size_t s = 0; s < seqs.size(); s++)
 		for (ora_nt_iter_init(&it, seqs[s].data(), seqs[s].size(), 4, 7); it.pos != ORA_END; ora_nt_iter_next(&it))
 			CHECK(h.valid(batch.offsets[s] + it.pos) && h.hit(batch.offsets[s] + it.pos));
+	{
+		// the same batch as 2 bits per base: same filter bytes, same per-window results
+		btlbf::PackedSeqBatch pk(batch);
+		CHECK(!pk.invalid.empty() && pk.codes.size() == (batch.bases.size() + 3) / 4);
+		BloomFilter p(8 * 1237, 4, 7);
+		CHECK(p.insertSeqs(pk) == n);
+		std::ostringstream op;
+		op << p;
+		CHECK(op.str() == oa.str());
+		btlbf::SeqHits hp = p.containsSeqs(pk);
+		CHECK(hp.nKmers == n && hp.nHits == n && hp.hitBits == h.hitBits && hp.validBits == h.validBits);
+	}
 	// KmerBloomFilter: text k-mers, consistent with the iterator path (swig/test.pl scenario: 20-mers)
 	KmerBloomFilter kb(8 * 4099, 4, 21), kb2(8 * 4099, 4, 21);
 	const char* kmers[4] = { "ATCGGGTCATCAACCAATATA", "ATCGGGTCATCAACCAATATT", "ATCGGGTCATCAACCAATAAA", "ATCGGGTCATCAACCAATAGG" };

@@ -59,6 +59,41 @@ def main():
     pm.close()
     assert np.array_equal(f3.to_numpy(), filt)
 
+    # ---- the partitioned build parks k-mers until the filter is next touched (forced here on a small filter): the
+    # merges must see them -- NCCL path through a stream switch (set_stream), peer path through flush()
+    ctx2 = B.Context(local)
+    for key, val in (("bin_mode", 1), ("bin_part_log2", 14)):
+        ctx2.set_option(key, val)
+    f4 = B.BloomFilter(bits, h, k, ctx=ctx2)
+    f4.insertSeqs(my)
+    assert ctx2.counter("binned_launches") > 0
+    pm4 = parallel.PeerMerge(ctx2, *f4.device_ptr(), f4.KIND)
+    pm4.merge()
+    pm4.close()
+    assert np.array_equal(f4.to_numpy(), filt), "rank %d: parked k-mers were lost by the peer merge" % rank
+    ctx2.set_option("wrap_accumulate", 1)
+    t5 = torch.zeros(parallel.padded_bytes(nbytes, world), dtype=torch.uint8, device=dev)
+    f5 = B.BloomFilter.from_device_memory(t5, bits, h, k, ctx=ctx2)
+    f5.insertSeqs(my)
+    parallel.merge_filter(f5)
+    torch.cuda.synchronize()
+    assert np.array_equal(f5.to_numpy(), filt), "rank %d: parked k-mers were lost across the stream switch" % rank
+
+    # ---- the OR merge inside NVSwitch (multimem.ld_reduce.or / multimem.st over a multicast mapping of symmetric
+    # memory), where the system offers NVLS multicast
+    f6, hdl = parallel.symmetric_filter(B.BloomFilter, bits, h, k, ctx2)
+    mm_ok = parallel.MultimemMerge.available(hdl)
+    if mm_ok:
+        f6.insertSeqs(my)
+        mm = parallel.MultimemMerge(ctx2, hdl, nbytes)
+        mm.merge()
+        assert np.array_equal(f6.to_numpy(), filt), "rank %d: in-switch merge differs from the oracle" % rank
+        mm.merge()  # idempotent
+        assert np.array_equal(f6.to_numpy(), filt)
+        mm.close()
+        r6 = f6.containsSeqs(my)
+        assert r6.n_hits == r6.n_kmers
+
     # ---- query: filter replicated (after the merge), reads sharded, no collective
     r = f.containsSeqs(my)
     nq, nh, hits, valid = orc.bf_contains_seqs(filt, bits, h, k, my[0], my[1])
@@ -89,7 +124,7 @@ def main():
     assert np.array_equal(c2.to_numpy(), exp), "rank %d: fused saturating-add merge differs" % rank
     dist.barrier()
     if rank == 0:
-        print("MULTI-GPU OK world=%d" % world)
+        print("MULTI-GPU OK world=%d multimem=%s" % (world, "yes" if mm_ok else "unavailable"))
     dist.destroy_process_group()
 
 
