@@ -280,7 +280,8 @@ class Env:
         self.read_bases = self.n_reads * READ_LEN
         self.token = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.host = None
-        self.no_multicast = None  # why the in-switch merge is not used (set on first failure)
+        self.no_symm = None      # why symmetric memory is not used (set on first failure)
+        self.merge_choice = {}   # (kind, size) -> (kernel, calibration) of the N > 1 merge
         if self.world > 1:
             self.ctx.set_option("wrap_accumulate", 1)  # symmetric-memory filters keep the build's accumulation
 
@@ -391,24 +392,33 @@ def make_filter(env, cfg):
 
 
 def make_sharded_filter(env, cfg):
-    """N > 1: this rank's partial filter + the object that merges the N of them.  BloomFilters go into symmetric memory
-    and are merged inside NVSwitch (btlbf_merge_multimem) where the box has NVLS multicast; otherwise -- and for counting
-    filters, whose saturating add has no multimem form -- the library's own allocation and the peer-memory kernel."""
+    """N > 1: this rank's partial filter + the object that merges the N of them.  The filters live in symmetric memory
+    (torch.distributed._symmetric_memory: peer pointers, and an NVLS multicast mapping where the box has one).
+    BloomFilters are merged by whichever kernel the box runs faster at this N -- the OR inside NVSwitch
+    (btlbf_merge_multimem) or the peer-memory kernel (btlbf_merge_peers); timed once per filter size, before
+    anything else is -- counting filters by the peer-memory kernel (saturating add has no multimem form).  Without
+    symmetric memory: the library's own allocation, CUDA IPC and the peer-memory kernel."""
     from btl_bloomfilter_b200 import parallel
     B, want = env.B, env.args.merge
-    if cfg["kind"] == "bloom" and want in ("auto", "multimem") and not env.no_multicast:
+    cls = B.BloomFilter if cfg["kind"] == "bloom" else B.CountingBloomFilter
+    if want != "ipc" and not env.no_symm:
         try:
-            f, hdl = parallel.symmetric_filter(B.BloomFilter, cfg["size"], cfg["h"], cfg["k"], env.ctx)
-            if parallel.MultimemMerge.available(hdl):
-                if cfg.get("seeds"):
-                    f.setSeeds(cfg["seeds"], cfg.get("h2", 1))
-                return f, parallel.MultimemMerge(env.ctx, hdl, filter_bytes(cfg)), "multimem"
-            env.no_multicast = "multicast_ptr == 0"
-            del f, hdl
-        except Exception as e:  # noqa: BLE001  (symmetric memory unavailable: every rank takes the same branch)
-            env.no_multicast = "%s: %s" % (type(e).__name__, str(e)[:120])
-        if want == "multimem":
-            raise SystemExit("--merge multimem: " + str(env.no_multicast))
+            f, hdl = parallel.symmetric_filter(cls, cfg["size"], cfg["h"], cfg["k"], env.ctx, threshold=cfg.get("threshold", 1))
+            if cfg.get("seeds"):
+                f.setSeeds(cfg["seeds"], cfg.get("h2", 1))
+            pm = parallel.MultimemMerge(env.ctx, hdl, filter_bytes(cfg), f.KIND, mode=None if want == "auto" else want)
+            key = (cfg["kind"], cfg["size"])
+            if want == "auto" and cfg["kind"] == "bloom":
+                if key not in env.merge_choice:
+                    pm.calibrate()
+                    env.merge_choice[key] = (pm.mode, pm.calibration)
+                    f.clear()
+                pm.mode, pm.calibration = env.merge_choice[key]
+            return f, pm, pm.mode
+        except RuntimeError as e:  # symmetric memory unavailable: every rank takes the same branch
+            if want in ("multimem", "peer"):
+                raise SystemExit("--merge %s: %s" % (want, str(e)[:200]))
+            env.no_symm = "%s: %s" % (type(e).__name__, str(e)[:120])
     f = make_filter(env, cfg)
     return f, parallel.PeerMerge(env.ctx, *f.device_ptr(), f.KIND), "peer"
 
@@ -727,8 +737,10 @@ def run_config(env, name, cfg, S, W, headline):
                         "how": MERGE_HOW[merge_how] + ", two stream-ordered barriers",
                         "link_bytes_per_gpu_per_direction": per_dir,
                         "link_GBps_per_gpu_per_direction": per_dir / (ms_merge * 1e-3) / 1e9}
-        if env.no_multicast:
-            out["merge"]["multimem_unavailable"] = str(env.no_multicast)
+        if getattr(pm, "calibration", None):
+            out["merge"]["calibration_ms"] = pm.calibration
+        if env.no_symm:
+            out["merge"]["symmetric_memory_unavailable"] = str(env.no_symm)
     if e2e:
         out["e2e"] = {"value": e2e["kmers"] / e2e["seconds"] / 1e9, "unit": "Gk-mer/s", "steps": e2e["steps"],
                       "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
@@ -869,12 +881,14 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (the other BASELINE configs)")
     ap.add_argument("--configs", default="cfg3,cfg4,cfg5a,cfg5b", help="which configs the `configs` block covers")
-    ap.add_argument("--config-steps", type=int, default=6)
+    ap.add_argument("--config-steps", type=int, default=16,
+                    help="steps of the other configs (16 chunks = 1 Gi k-mers: one full accumulation of the 16 GiB filter)")
     ap.add_argument("--no-job", action="store_true", help="skip the strong-scaled full cfg2 job")
     ap.add_argument("--cpu-sample", type=int, default=8 << 20, help="bases per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--merge", default="auto", choices=["auto", "multimem", "peer"],
-                    help="N > 1 BloomFilter merge: in NVSwitch (multimem) when available, or the peer-memory kernel")
+    ap.add_argument("--merge", default="auto", choices=["auto", "multimem", "peer", "ipc"],
+                    help="N > 1 merge kernel: auto = the faster of the in-switch OR (multimem) and the peer-memory kernel, timed "
+                         "once on this box; ipc = own allocations + CUDA IPC + the peer-memory kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-packed", action="store_true", help="skip the 2-bit packed host-buffer leg (e2e_packed)")
     ap.add_argument("--chunk", type=int, default=CHUNK)

@@ -272,29 +272,71 @@ def symmetric_filter(cls, size, hashNum, kmerSize, ctx, group=None, threshold=0)
 
 
 class MultimemMerge:
-    """OR merge of per-rank partial BloomFilters held in symmetric memory, reduced inside NVSwitch.
+    """Merge of per-rank partial filters held in symmetric memory (symmetric_filter()).  Two kernels serve it:
+      "multimem"  BloomFilter only, where the handle carries an NVLS multicast mapping: the OR happens inside NVSwitch
+                  (btlbf_merge_multimem: multimem.ld_reduce.or + multimem.st); a GPU moves ~(1 + 1/N) of the filter per
+                  NVLink direction
+      "peer"      the peer-memory kernel (btlbf_merge_peers) over the handle's peer pointers (no CUDA IPC plumbing
+                  needed); 2 (N-1)/N of the filter per direction; also the saturating-add merge of counting filters
+    Which one is faster depends on N (measured on B200 at N = 2: peer 6.5 ms, multimem 12.2 ms for a 3.95 GB filter,
+    because multimem pulls the local replica through the switch too); calibrate() times both once on the box and keeps
+    the faster.  Collective: every rank of the group constructs it and calls its methods together."""
 
-    hdl: the rendezvous handle of the symmetric tensor the filter wraps (symmetric_filter()).  Collective:
-    every rank of the group constructs it and calls merge() / launch() together."""
-
-    def __init__(self, ctx, hdl, nbytes, kind=0, group=None):
-        if kind != 0:
-            raise ValueError("the in-switch merge is an OR: counting filters use PeerMerge")
-        mc = int(hdl.multicast_ptr)
-        if mc == 0:
-            raise RuntimeError("no NVLS multicast mapping on this system (multicast_ptr == 0)")
-        self.ctx, self.hdl, self.mc, self.nbytes, self.group = ctx, hdl, mc, int(nbytes), group
+    def __init__(self, ctx, hdl, nbytes, kind=0, group=None, mode=None):
+        self.ctx, self.hdl, self.nbytes, self.kind, self.group = ctx, hdl, int(nbytes), int(kind), group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self.mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if kind == 0 else 0
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        assert len(ptrs) == self.world
+        self._bases = (C.c_void_p * self.world)(*ptrs)
+        self.modes = (["multimem"] if self.mc else []) + ["peer"]
+        if mode is not None and mode not in self.modes:
+            raise RuntimeError("merge mode %r is not available here (have %s)" % (mode, self.modes))
+        self.mode = mode or self.modes[0]
+        self.calibration = None
 
     @staticmethod
     def available(hdl):
         return int(getattr(hdl, "multicast_ptr", 0) or 0) != 0
 
-    def launch(self):
+    def launch(self, mode=None):
         """The kernel alone; the caller brackets it (ctx.flush() before the first barrier, see PeerMerge.launch)."""
         from ._capi import check
-        check(self.ctx.L.btlbf_merge_multimem(self.ctx.handle, 0, C.c_void_p(self.mc), self.world, self.rank, self.nbytes))
+        L, ctx = self.ctx.L, self.ctx
+        if (mode or self.mode) == "multimem":
+            check(L.btlbf_merge_multimem(ctx.handle, 0, C.c_void_p(self.mc), self.world, self.rank, self.nbytes))
+        else:
+            check(L.btlbf_merge_peers(ctx.handle, self.kind, self._bases, self.world, self.rank, self.nbytes))
+
+    def calibrate(self, repeats=2):
+        """Times every available kernel on this box (max over ranks) and keeps the fastest.  BloomFilter only: OR is
+        idempotent, so the trial merges leave a filter that is still correct -- merged -- for whatever was inserted
+        before; call it on an empty or throw-away filter state when the unmerged partials matter."""
+        if self.kind != 0 or len(self.modes) < 2:
+            return self.mode
+        dev = torch.device("cuda", self.ctx.device)
+        res = {}
+        self.ctx.flush()
+        for mode in self.modes:
+            best = None
+            for _ in range(repeats + 1):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                dist.barrier(group=self.group)
+                a.record(torch.cuda.current_stream())
+                self.launch(mode)
+                b.record(torch.cuda.current_stream())
+                torch.cuda.synchronize()
+                dist.barrier(group=self.group)
+                ms = a.elapsed_time(b)
+                best = ms if best is None else min(best, ms)
+            t = torch.tensor([best], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            res[mode] = float(t[0])
+        self.calibration = res
+        self.mode = min(res, key=res.get)
+        return self.mode
 
     def merge(self):
         self.ctx.flush()

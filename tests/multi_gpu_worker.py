@@ -93,6 +93,16 @@ def main():
         mm.close()
         r6 = f6.containsSeqs(my)
         assert r6.n_hits == r6.n_kmers
+    # the peer-memory kernel over the symmetric handle's peer pointers (no CUDA IPC), and the calibrated choice
+    f7, hdl7 = parallel.symmetric_filter(B.BloomFilter, bits, h, k, ctx2)
+    f7.insertSeqs(my)
+    m7 = parallel.MultimemMerge(ctx2, hdl7, nbytes, mode="peer")
+    m7.merge()
+    assert np.array_equal(f7.to_numpy(), filt), "rank %d: peer merge over symmetric memory differs" % rank
+    assert m7.calibrate() in m7.modes
+    m7.merge()
+    assert np.array_equal(f7.to_numpy(), filt)
+    m7.close()
 
     # ---- query: filter replicated (after the merge), reads sharded, no collective
     r = f.containsSeqs(my)

@@ -34,7 +34,11 @@ while time.time() < t_end:
                         bin_slack_pct=int(rng.choice([0, 20, 100])),
                         query_adaptive=int(rng.random() < 0.7), query_adaptive_pct=int(rng.choice([0, 20, 50, 101])),
                         query_adaptive_min_tiles=1, chunk=int(rng.choice([4096, 1 << 16, 1 << 20])))
-    be = GpuBackend(**opts)
+    if counting and rng.random() < 0.5:  # the partitioned threshold query of counting filters
+        opts.update(bin_query_mode=1, bin_part_log2=int(rng.integers(11, 21)), query_adaptive=int(rng.random() < 0.5),
+                    query_adaptive_min_tiles=1)
+    packed = rng.random() < 0.4  # insert / contains through btlbf_pack_seqs + the 2-bit packed entry points
+    be = GpuBackend(packed=bool(packed), **opts)
     seeds, h2 = None, 1
     if rng.random() < 0.3:  # spaced seeds (stHashIterator): masks with cared-for ends, h = n_seeds * h2
         n_seeds, h2 = int(rng.integers(1, 5)), int(rng.integers(1, 3))
@@ -44,7 +48,8 @@ while time.time() < t_end:
             mk[0] = mk[-1] = True
             seeds.append("".join("1" if x else "0" for x in mk))
         h = n_seeds * h2
-    f = be.filter(1 if counting else 0, m, h, k, thr=int(rng.integers(1, 4)), seeds=seeds, h2=h2)
+    thr = int(rng.integers(1, 4))
+    f = be.filter(1 if counting else 0, m, h, k, thr=thr, seeds=seeds, h2=h2)
     if seeds:
         ins = (lambda b, off: orc.st_cbf_insert_seqs(ref, m, seeds, h2, k, b, off)) if counting else \
               (lambda b, off: orc.st_bf_insert_seqs(ref, m, seeds, h2, k, b, off))
@@ -52,7 +57,7 @@ while time.time() < t_end:
     try:
         for rnd in range(int(rng.integers(2, 6))):
             b, off = S.rand_batch(rng, int(rng.integers(1, 40)), int(rng.integers(k + 1, 6000)),
-                                  p_n=float(rng.choice([0, 0.002, 0.02])), exotic=float(rng.choice([0, 0, 0.001])))
+                                  p_n=float(rng.choice([0, 0.002, 0.02])), exotic=0.0 if packed else float(rng.choice([0, 0, 0.001])))
             if rng.random() < 0.3:  # repetitive input: skew, dependency chains
                 rep = np.frombuffer((b"ACGT" * 2000 + b"A" * 3000), np.uint8)
                 b = np.concatenate([b, rep]); off = np.concatenate([off, [off[-1] + rep.size]]).astype(np.uint64)
@@ -71,6 +76,8 @@ while time.time() < t_end:
                     assert np.array_equal(f.bytes(), ref), "counters"
                 e = orc.cbf_mincount_seqs(ref, m, h, k, b, off); g = f.mincount((b, off))
                 assert e[0] == g[0] and np.array_equal(e[1], g[1]) and np.array_equal(e[2], g[2]), "mincount"
+                e = orc.cbf_contains_seqs(ref, m, h, k, thr, b, off); g = f.contains((b, off))
+                assert e[:2] == g[:2] and np.array_equal(e[2], g[2]), "counting contains"
             else:
                 if rng.random() < 0.25:
                     e = orc.bf_insert_and_check_seqs(ref, m, h, k, b, off); g = f.insert_and_check((b, off))
@@ -83,6 +90,6 @@ while time.time() < t_end:
                     assert e[:2] == g[:2] and np.array_equal(e[2], g[2]) and np.array_equal(e[3], g[3]), "contains"
         assert np.array_equal(f.bytes(), ref), "final array"
     except AssertionError as err:
-        print("FUZZ FAILURE seed %d iteration %d: %s  kind=%s m=%d h=%d k=%d opts=%s" % (seed, it, err, "cbf" if counting else "bf", m, h, k, opts))
+        print("FUZZ FAILURE seed %d iteration %d: %s  kind=%s m=%d h=%d k=%d packed=%s opts=%s" % (seed, it, err, "cbf" if counting else "bf", m, h, k, packed, opts))
         sys.exit(1)
 print("fuzz ok: %d random configurations in %.0f s" % (it, budget))

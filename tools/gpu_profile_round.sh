@@ -4,6 +4,7 @@
 #   2. ncu launch list of a short run of the same command (gpu__time_duration + DRAM bytes per launch)
 #   3. one ncu --set full capture of the four kernels of a step (pass 1 build, pass 2 build, pass 1 query, pass 2 query)
 tag=$1
+python -c "import bench; print(bench.source_sha())" > gpurun_out/source_sha_$tag.txt
 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err || { echo "bench failed"; tail -5 gpurun_out/bench_$tag.err; exit 1; }
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$tag.json 2>> gpurun_out/bench_$tag.err
 args="--steps 8 --warmup 3 --no-e2e --no-cpu-baseline --no-configs --no-job"

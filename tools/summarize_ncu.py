@@ -119,7 +119,14 @@ def main():
         query = sum(v for k, v in dram.items() if "probe_bins" in k or "finalize" in k or "seq_kernel<2" in k or
                     "query_gate" in k or ("bin_kernel" in k and ", 1>" in k[-6:]))
         with open(os.path.join(ROOT, "profiles", "%s_dram_bytes_per_step.json" % tag), "w") as fh:
+            # the hash of the kernel sources the capture was taken from (recorded on the GPU box by
+            # tools/gpu_profile_round.sh next to the launch list; bench.py attaches `traffic` only when it still matches)
+            sha = None
+            sha_file = os.path.join(os.path.dirname(os.path.abspath(launches)), "source_sha_%s.txt" % os.environ.get("RUN_TAG", tag))
+            if os.path.exists(sha_file):
+                sha = open(sha_file).read().strip()
             json.dump({"build_bytes_per_step": build / S, "query_bytes_per_step": query / S, "steps": S,
+                       "source_sha": sha,
                        "source": "ncu launch list, dram__bytes_read.sum + dram__bytes_write.sum of the timed launches"},
                       fh, indent=1)
     print(json.dumps(tj, indent=1))
