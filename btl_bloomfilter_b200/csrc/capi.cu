@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 #include "host_params.hpp"
 
+#include <atomic>
 #include <cerrno>
 #include <cstdarg>
 #include <cstdio>
@@ -75,6 +76,31 @@ struct HashCfg // everything the kernels need to turn a window into its hashes
 	SeqParams proto;
 };
 
+// Per (host thread, filter) staging of the legacy per-k-mer updates: a thread appends to its own queue under the queue's
+// own flag (uncontended in the normal case) and takes the context lock only once per kTlCap k-mers, so that an OpenMP
+// loop of bloom.insert(*itr) over one shared filter (Tests/AdHoc/ParallelFilter.cpp:104-122) does not serialise on the
+// context.  Any thread that touches the filter drains all of its queues first (joined()).
+struct TlQueue
+{
+	std::atomic<int> busy{ 0 };
+	uint32_t n = 0;
+	int op = -1;
+	uint64_t* data = nullptr; // kTlCap x h hash values, in call order
+};
+constexpr uint32_t kTlCap = 512;
+
+struct TlGuard
+{
+	TlQueue* q;
+	explicit TlGuard(TlQueue* q_) : q(q_)
+	{
+		int expect = 0;
+		while (!q->busy.compare_exchange_weak(expect, 1, std::memory_order_acquire))
+			expect = 0;
+	}
+	~TlGuard() { q->busy.store(0, std::memory_order_release); }
+};
+
 } // namespace
 
 struct btlbf_ctx
@@ -88,6 +114,8 @@ struct btlbf_ctx
 	cudaEvent_t ev_switch = nullptr;  // orders a newly selected active stream after the old one
 	btlbf_filter* hq_owner = nullptr; // filter whose per-k-mer queue (legacy interface) holds unapplied updates
 	bool in_hq_flush = false;
+	std::atomic<uint64_t> tl_pending{ 0 };  // per-thread queues (TlQueue) of this context's filters that hold updates
+	std::vector<btlbf_filter*> tl_filters;  // filters that own per-thread queues
 	cudaStream_t own = nullptr, active = nullptr, copy_in = nullptr, copy_out = nullptr;
 	// Background stream: pass 2 of the partitioned build (memory-bound) runs here, concurrently with
 	// whatever the active stream does next (typically the compute-bound pass 1 of the following batch).
@@ -181,6 +209,8 @@ struct btlbf_filter
 	uint64_t* hq = nullptr; // pinned: hq_n x h hash values
 	uint64_t hq_n = 0;
 	int hq_op = -1;
+	std::vector<TlQueue*> tlq; // the host threads' private queues in front of hq (registered under the context lock)
+	uint64_t uid = 0;          // never reused: keys the threads' queue caches
 };
 constexpr uint64_t kHashQueue = 1u << 16;
 
@@ -200,8 +230,16 @@ static int use(btlbf_ctx* ctx)
 static int settle(btlbf_ctx* ctx);
 static int hq_flush(btlbf_ctx* ctx);
 
+static int tl_drain_all(btlbf_ctx* ctx);
+static void tl_discard(btlbf_filter* f, bool destroy);
+
 static cudaStream_t joined(btlbf_ctx* ctx)
 {
+	if (!ctx->in_hq_flush && ctx->tl_pending.load(std::memory_order_acquire) != 0) {
+		int rc = tl_drain_all(ctx);
+		if (rc != BTLBF_OK && !ctx->settle_error)
+			ctx->settle_error = rc;
+	}
 	if (ctx->hq_owner && !ctx->in_hq_flush) {
 		int rc = hq_flush(ctx);
 		if (rc != BTLBF_OK && !ctx->settle_error)
@@ -678,6 +716,10 @@ static int filter_make(btlbf_ctx* ctx, int kind, uint64_t size, unsigned h, unsi
 	if (kind == BTLBF_BLOOM && !bitvector && size % 8 != 0) // BloomFilter.hpp:389-394
 		return fail(BTLBF_ERR_ARG, "Filter Size \"%llu\" is not a multiple of 8", (unsigned long long)size);
 	btlbf_filter* f = new (std::nothrow) btlbf_filter();
+	if (f) {
+		static std::atomic<uint64_t> next_uid{ 1 };
+		f->uid = next_uid.fetch_add(1);
+	}
 	if (!f)
 		return fail(BTLBF_ERR_NOMEM, "out of host memory");
 	f->ctx = ctx;
@@ -741,6 +783,7 @@ extern "C" int btlbf_filter_destroy(btlbf_filter* f)
 	cudaSetDevice(f->ctx->device);
 	if (f->ctx->acc.f == f)
 		f->ctx->acc.f = nullptr; // parked k-mers of a filter that is going away
+	tl_discard(f, true);
 	if (ctx->hq_owner == f)
 		ctx->hq_owner = nullptr;
 	if (f->hq)
@@ -768,7 +811,8 @@ extern "C" int btlbf_filter_clear(btlbf_filter* f)
 	LOCKED(f->ctx);
 	if (f->ctx->acc.f == f)
 		f->ctx->acc.f = nullptr; // k-mers still parked in the partition buckets vanish with the rest
-	if (f->ctx->hq_owner == f) { // ... and so do queued per-k-mer updates
+	tl_discard(f, false); // ... and so do queued per-k-mer updates
+	if (f->ctx->hq_owner == f) {
 		f->ctx->hq_owner = nullptr;
 		f->hq_n = 0;
 	}
@@ -811,6 +855,7 @@ extern "C" int btlbf_filter_upload(btlbf_filter* f, const void* host, uint64_t n
 	LOCKED(f->ctx);
 	if (f->ctx->acc.f == f)
 		f->ctx->acc.f = nullptr; // overwritten anyway
+	tl_discard(f, false);
 	if (f->ctx->hq_owner == f) {
 		f->ctx->hq_owner = nullptr;
 		f->hq_n = 0;
@@ -846,7 +891,7 @@ extern "C" int btlbf_filter_device_ptr(btlbf_filter* f, void** device_ptr, uint6
 	if (!f)
 		return fail(BTLBF_ERR_ARG, "null filter");
 	LOCKED(f->ctx);
-	if (f->ctx->acc.f == f || f->ctx->aux_pending || f->ctx->hq_owner == f) { // parked k-mers reach the filter now, in stream order
+	if (f->ctx->acc.f == f || f->ctx->aux_pending || f->ctx->hq_owner == f || f->ctx->tl_pending.load() != 0) { // parked k-mers reach the filter now, in stream order
 		TRY(use(f->ctx));
 		cudaStream_t s;
 		TRY(join(f->ctx, &s));
@@ -2341,6 +2386,107 @@ static int hq_flush(btlbf_ctx* ctx)
 	return rc;
 }
 
+// appends n k-mers (n x h hash values) to the filter's queue; context lock held
+static int hq_append(btlbf_filter* f, int op, const uint64_t* hashes, uint64_t n)
+{
+	btlbf_ctx* ctx = f->ctx;
+	const uint32_t h = f->hc.h;
+	while (n) {
+		if (ctx->hq_owner && (ctx->hq_owner != f || f->hq_op != op || f->hq_n == kHashQueue))
+			TRY(hq_flush(ctx));
+		if (!f->hq)
+			CU(cudaHostAlloc(&f->hq, (size_t)kHashQueue * h * 8, cudaHostAllocDefault));
+		const uint64_t take = kHashQueue - f->hq_n < n ? kHashQueue - f->hq_n : n;
+		memcpy(f->hq + f->hq_n * h, hashes, take * h * 8);
+		f->hq_n += take;
+		f->hq_op = op;
+		ctx->hq_owner = f;
+		hashes += take * h;
+		n -= take;
+		if (f->hq_n == kHashQueue)
+			TRY(hq_flush(ctx));
+	}
+	return BTLBF_OK;
+}
+
+// moves one thread's queue into the filter's queue; context lock held
+static int tl_drain_one(btlbf_filter* f, TlQueue* q)
+{
+	TlGuard g(q);
+	if (q->n == 0)
+		return BTLBF_OK;
+	const uint32_t n = q->n;
+	q->n = 0;
+	f->ctx->tl_pending.fetch_sub(1, std::memory_order_acq_rel);
+	return hq_append(f, q->op, q->data, n);
+}
+
+static int tl_drain_all(btlbf_ctx* ctx)
+{
+	int rc = BTLBF_OK;
+	for (btlbf_filter* f : ctx->tl_filters)
+		for (TlQueue* q : f->tlq) {
+			int r = tl_drain_one(f, q);
+			if (r != BTLBF_OK && rc == BTLBF_OK)
+				rc = r;
+		}
+	return rc;
+}
+
+// drops what the threads' queues of f hold (clear / upload / destroy); context lock held
+static void tl_discard(btlbf_filter* f, bool destroy)
+{
+	btlbf_ctx* ctx = f->ctx;
+	for (TlQueue* q : f->tlq) {
+		{
+			TlGuard g(q);
+			if (q->n) {
+				q->n = 0;
+				ctx->tl_pending.fetch_sub(1, std::memory_order_acq_rel);
+			}
+		}
+		if (destroy) {
+			free(q->data);
+			delete q;
+		}
+	}
+	if (destroy) {
+		f->tlq.clear();
+		for (size_t i = 0; i < ctx->tl_filters.size(); i++)
+			if (ctx->tl_filters[i] == f) {
+				ctx->tl_filters.erase(ctx->tl_filters.begin() + (long)i);
+				break;
+			}
+	}
+}
+
+// this thread's queue in front of filter f (created and registered on first use)
+static TlQueue* tl_queue(btlbf_filter* f)
+{
+	struct Entry { uint64_t uid; TlQueue* q; };
+	static thread_local Entry cache[4] = { { 0, nullptr }, { 0, nullptr }, { 0, nullptr }, { 0, nullptr } };
+	static thread_local unsigned next = 0;
+	for (const Entry& e : cache)
+		if (e.uid == f->uid)
+			return e.q;
+	TlQueue* q = new (std::nothrow) TlQueue;
+	if (!q)
+		return nullptr;
+	q->data = (uint64_t*)malloc((size_t)kTlCap * f->hc.h * 8);
+	if (!q->data) {
+		delete q;
+		return nullptr;
+	}
+	{
+		LOCKED(f->ctx);
+		if (f->tlq.empty())
+			f->ctx->tl_filters.push_back(f);
+		f->tlq.push_back(q);
+	}
+	cache[next++ & 3u] = { f->uid, q };
+	return q;
+}
+
 static int hashes_op(btlbf_filter* f, int op, const uint64_t* hashes, uint64_t n, uint8_t* out)
 {
 	if (!f)
@@ -2350,25 +2496,45 @@ static int hashes_op(btlbf_filter* f, int op, const uint64_t* hashes, uint64_t n
 	if (!hashes)
 		return fail(BTLBF_ERR_ARG, "null hashes");
 	btlbf_ctx* ctx = f->ctx;
-	TRY(use(ctx));
-	LOCKED(ctx);
 	const uint32_t h = f->hc.h;
 	// Updates that report nothing (a `while (itr != itr.end()) { bloom.insert(*itr); ++itr; }` loop, README.md:30-43,
-	// possibly from many OpenMP threads, ParallelFilter.cpp:104-122) are queued: one kernel per kHashQueue k-mers.
-	// The queue keeps call order, which is what the order-dependent incrementMin (op 3) needs.
+	// possibly from many OpenMP threads, ParallelFilter.cpp:104-122) are queued: first in the calling thread's own
+	// queue, kTlCap k-mers at a time in the filter's, one kernel per kHashQueue k-mers.  A thread's updates keep their
+	// call order, which is what the order-dependent incrementMin (op 3) needs.
 	if (!out && (op == 0 || op == 3 || op == 4) && n <= kHashQueue / 4) {
-		if (ctx->hq_owner && (ctx->hq_owner != f || f->hq_op != op || f->hq_n + n > kHashQueue))
-			TRY(hq_flush(ctx));
-		if (!f->hq)
-			CU(cudaHostAlloc(&f->hq, (size_t)kHashQueue * h * 8, cudaHostAllocDefault));
-		memcpy(f->hq + f->hq_n * h, hashes, n * h * 8);
-		f->hq_n += n;
-		f->hq_op = op;
-		ctx->hq_owner = f;
-		if (f->hq_n == kHashQueue)
-			TRY(hq_flush(ctx));
-		return BTLBF_OK;
+		TlQueue* q = n <= 64 ? tl_queue(f) : nullptr;
+		if (q) {
+			for (;;) {
+				bool full = false, done = false;
+				{
+					TlGuard g(q);
+					if (q->n == 0 || (q->op == op && q->n + n <= kTlCap)) {
+						if (q->n == 0)
+							ctx->tl_pending.fetch_add(1, std::memory_order_acq_rel);
+						memcpy(q->data + (size_t)q->n * h, hashes, n * h * 8);
+						q->n += (uint32_t)n;
+						q->op = op;
+						full = q->n == kTlCap;
+						done = true;
+					}
+				}
+				if (done && !full)
+					return BTLBF_OK;
+				TRY(use(ctx));
+				LOCKED(ctx);
+				TRY(tl_drain_one(f, q));
+				if (done)
+					return BTLBF_OK;
+			}
+		}
+		TRY(use(ctx));
+		LOCKED(ctx);
+		for (TlQueue* t : f->tlq) // larger batches go straight to the filter's queue, behind what the threads queued
+			TRY(tl_drain_one(f, t));
+		return hq_append(f, op, hashes, n);
 	}
+	TRY(use(ctx));
+	LOCKED(ctx);
 	return hashes_run(f, op, hashes, n, out);
 }
 

@@ -180,19 +180,21 @@ __global__ void __launch_bounds__(THREADS, sort_ctas_per_sm(THREADS)) bin_kernel
 			}
 			__syncthreads();
 			// ---- S: exclusive scan over the partitions (two per thread), cursors, gdelta
-			uint32_t v0 = 0, v1 = 0;
-			if (2u * tid < nbr) {
-				v0 = hist[2 * tid];
-				v1 = hist[2 * tid + 1];
-				hist[2 * tid] = 0;
-				hist[2 * tid + 1] = 0;
-			}
-			uint32_t incl = v0 + v1;
+			uint32_t v0 = 0, v1 = 0, incl = 0;
+			if (64u * (uint32_t)warp < nbr) { // warps whose 64 partitions do not exist skip the scan (warp-uniform)
+				if (2u * tid < nbr) {
+					v0 = hist[2 * tid];
+					v1 = hist[2 * tid + 1];
+					hist[2 * tid] = 0;
+					hist[2 * tid + 1] = 0;
+				}
+				incl = v0 + v1;
 #pragma unroll
-			for (int o = 1; o < 32; o <<= 1) {
-				uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-				if (lane >= o)
-					incl += y;
+				for (int o = 1; o < 32; o <<= 1) {
+					uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+					if (lane >= o)
+						incl += y;
+				}
 			}
 			if (lane == 31)
 				wsum[warp] = incl;
@@ -243,6 +245,7 @@ __global__ void __launch_bounds__(THREADS, sort_ctas_per_sm(THREADS)) bin_kernel
 			// ---- D: copy out (the next round's phase A only touches hist, so no barrier is needed after this)
 			total = wsum[NW];
 			const bool overflow = wsum[NW + 1] != 0;
+#pragma unroll 4
 			for (uint32_t pos = tid; pos < total; pos += kSortThreads) {
 				const uint2 item = sorted[pos];
 				const uint32_t off = item.x, aux = item.y;

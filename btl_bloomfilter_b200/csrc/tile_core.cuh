@@ -127,6 +127,8 @@ struct TileSmem
 	uint32_t* badw;    // invalid-bit plane, 32 bases per word
 	uint32_t* startw;  // sequence-start plane, 32 bases per word
 	uint64_t* gtab;    // g_f[16] g_fk[16] g_r[16] g_rk[16]
+	uint4* seedtab;    // [seed_rows(k)][4]: base i of a window with code c adds (x,y) = R^(k-2-i)(g_f[c]) to the forward hash
+	                   // of the window's first k-1 bases and (z,w) = R^(i+1)(g_r[c]) to the reverse one (see seed_packed)
 	uint64_t* sttab;   // spaced: TF[k][8], TR[k][8]
 	uint8_t* lut;      // byte -> class
 	uint64_t* scratch; // [0] first sequence index of the tile, [1] exotic flag, [2..] reductions
@@ -134,6 +136,13 @@ struct TileSmem
 	uint32_t writer;   // binned build: index of this CTA's private sub-buckets
 	uint32_t nb;       // staged bytes (multiple of 32)
 };
+
+// rows of the seeding table: one per base of the k-1 bases that precede a thread's first rolled-in base, when those
+// fit the thread's aligned 32-base register stream (k <= 33); larger k seed step by step
+BTL_HD uint32_t seed_rows(uint32_t k)
+{
+	return k >= 2u && k <= 33u ? k - 1u : 0u;
+}
 
 BTL_HD uint32_t tile_bytes(uint32_t k, uint32_t tile = (uint32_t)kTile)
 {
@@ -148,6 +157,7 @@ BTL_HD size_t tile_smem_bytes(uint32_t k, bool spaced, uint32_t nbins = 0, uint3
 	s += (nb / 16 + 4) * 4;              // codes
 	s += (nb / 32 + 4) * 4 * 2;          // badw, startw
 	s += 64 * 8;                         // gtab
+	s += (size_t)seed_rows(k) * 64;      // seedtab
 	s += spaced ? (size_t)k * 16 * 8 : 0; // sttab
 	s += 256;                            // lut
 	s += 16 * 8;                         // scratch
@@ -161,6 +171,7 @@ BTL_HD TileSmem carve_smem(uint8_t* raw, uint32_t k, bool spaced, uint32_t nbins
 	sm.nb = tile_bytes(k, tile);
 	uint8_t* p = raw;
 	sm.gtab = (uint64_t*)p;    p += 64 * 8;
+	sm.seedtab = (uint4*)p;    p += (size_t)seed_rows(k) * 64;
 	sm.scratch = (uint64_t*)p; p += 16 * 8;
 	sm.sttab = (uint64_t*)p;   p += spaced ? (size_t)k * 16 * 8 : 0;
 	sm.cursors = (uint32_t*)p; p += ((size_t)nbins * 4 + 15) / 16 * 16;
@@ -181,6 +192,11 @@ BTL_HD void tile_phase_a(const SeqParams& P, const TileSmem& sm, uint64_t t0, in
 		sm.gtab[i] = i < 16 ? P.g_f[i] : i < 32 ? P.g_fk[i - 16] : i < 48 ? P.g_r[i - 32] : P.g_rk[i - 48];
 	for (int i = tid; i < 256; i += ntid)
 		sm.lut[i] = base_class((unsigned)i);
+	for (uint32_t i = tid; i < seed_rows(P.k) * 4u; i += ntid) {
+		const uint32_t j = i >> 2, c = i & 3u;
+		const uint64_t f = srol_n(P.g_f[c], P.k - 2u - j), r = srol_n(P.g_r[c], j + 1u);
+		sm.seedtab[i] = make_uint4((uint32_t)f, (uint32_t)(f >> 32), (uint32_t)r, (uint32_t)(r >> 32));
+	}
 	if (P.n_seeds)
 		for (uint32_t i = tid; i < P.k * 16; i += ntid)
 			sm.sttab[i] = P.st_tab[i];
@@ -607,6 +623,44 @@ BTL_HD void window_op(const SeqParams& P, const TileSmem& sm, uint64_t t0, uint3
 	}
 }
 
+// ---------------------------------------------------------------- seeding
+// State of the rolling hash after the k-1 bases p0 .. p0+k-2 of the thread's first window (2-bit path): what the
+// step-by-step loop  F = R(F) ^ g_f[c_i],  RC = R(RC) ^ g_r[c_(k-2-i)],  ... RC = R(RC)  leaves, computed as
+// F = XOR_i R^(k-2-i)(g_f[c_i]),  RC = XOR_i R^(i+1)(g_r[c_i])  (R is linear over XOR) from the per-position table
+// tile_phase_a builds: one 16-byte shared-memory load and four XORs per base instead of two split rotations and four
+// dependent loads.  g (hashable bases ending at the newest one, restarting at sequence starts) comes from the
+// invalid / start planes with one count-leading-zeros.  p0 is a multiple of 32, k <= 33: the bases sit in one aligned
+// 64-bit code word pair and one word of each plane.  NTMC64 base, vendor/nthash.hpp:667-692.
+BTL_HD uint32_t clz32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+	return (uint32_t)__clz((int)x);
+#else
+	return x ? (uint32_t)__builtin_clz(x) : 32u;
+#endif
+}
+
+BTL_HD void seed_packed(const TileSmem& sm, uint32_t p0, uint32_t k, uint64_t codes, uint64_t& F, uint64_t& RC, uint32_t& g)
+{
+	uint32_t fl = 0, fh = 0, rl = 0, rh = 0;
+	const uint4* T = sm.seedtab;
+	for (uint32_t i = 0; i + 1 < k; i++) {
+		const uint4 e = T[i * 4u + ((uint32_t)codes & 3u)];
+		codes >>= 2;
+		fl ^= e.x; fh ^= e.y; rl ^= e.z; rh ^= e.w;
+	}
+	F = ((uint64_t)fh << 32) | fl;
+	RC = ((uint64_t)rh << 32) | rl;
+	const uint32_t m = k - 1u >= 32u ? 0xffffffffu : (1u << (k - 1u)) - 1u;
+	const uint32_t bad = sm.badw[p0 >> 5] & m, ev = bad | (sm.startw[p0 >> 5] & m);
+	if (ev == 0) {
+		g = k - 1u;
+	} else {
+		const uint32_t t = 31u - clz32(ev); // the last base that restarts the count
+		g = ((bad >> t) & 1u) ? k - 2u - t : k - 1u - t;
+	}
+}
+
 // ---------------------------------------------------------------- phase C: roll + operate
 // Rolls the canonical ntHash over the thread's kWPT consecutive windows and calls fn(s, ok, F, RC) for
 // every s in [0, kWPT) -- for every thread, in the same order, so that fn may contain warp-synchronous
@@ -658,17 +712,22 @@ BTL_HD void roll_windows(const SeqParams& P, const TileSmem& sm, uint64_t t0, in
 	}
 
 	// 2-bit packed path
-	for (uint32_t i = 0; i + 1 < k; i++) {
-		uint32_t qa = p0 + i, qb = p0 + k - 2 - i;
-		uint32_t ca = (sm.codes[qa >> 4] >> (2 * (qa & 15))) & 3u;
-		uint32_t cb = (sm.codes[qb >> 4] >> (2 * (qb & 15))) & 3u;
-		F = srol(F) ^ Gf[ca];
-		RC = srol(RC) ^ Gr[cb];
-		bool bad = (sm.badw[qa >> 5] >> (qa & 31)) & 1u;
-		bool st = (sm.startw[qa >> 5] >> (qa & 31)) & 1u;
-		g = bad ? 0u : (st ? 1u : g + 1u);
+	uint64_t out_codes = ((uint64_t)sm.codes[(p0 >> 4) + 1] << 32) | sm.codes[p0 >> 4];
+	if (seed_rows(k)) {
+		seed_packed(sm, p0, k, out_codes, F, RC, g);
+	} else {
+		for (uint32_t i = 0; i + 1 < k; i++) {
+			uint32_t qa = p0 + i, qb = p0 + k - 2 - i;
+			uint32_t ca = (sm.codes[qa >> 4] >> (2 * (qa & 15))) & 3u;
+			uint32_t cb = (sm.codes[qb >> 4] >> (2 * (qb & 15))) & 3u;
+			F = srol(F) ^ Gf[ca];
+			RC = srol(RC) ^ Gr[cb];
+			bool bad = (sm.badw[qa >> 5] >> (qa & 31)) & 1u;
+			bool st = (sm.startw[qa >> 5] >> (qa & 31)) & 1u;
+			g = bad ? 0u : (st ? 1u : g + 1u);
+		}
+		RC = srol(RC);
 	}
-	RC = srol(RC);
 	// register streams: 32 incoming bases from q1 (unaligned), 32 outgoing bases from p0 (aligned)
 	uint32_t a = q1 >> 4, sh2 = 2 * (q1 & 15);
 	uint32_t in_lo = funnel_r(sm.codes[a], sm.codes[a + 1], sh2);
@@ -677,7 +736,6 @@ BTL_HD void roll_windows(const SeqParams& P, const TileSmem& sm, uint64_t t0, in
 	uint32_t in_bad = funnel_r(sm.badw[bw], sm.badw[bw + 1], sh1);
 	uint32_t in_start = funnel_r(sm.startw[bw], sm.startw[bw + 1], sh1);
 	uint64_t in_codes = ((uint64_t)in_hi << 32) | in_lo;
-	uint64_t out_codes = ((uint64_t)sm.codes[(p0 >> 4) + 1] << 32) | sm.codes[p0 >> 4];
 #pragma unroll 4
 	for (uint32_t s = 0; s < (uint32_t)kWPT; s++) {
 		uint32_t cin = (uint32_t)in_codes & 3u;
@@ -733,17 +791,22 @@ struct Roller
 			RC = srol(RC);
 			return;
 		}
-		for (uint32_t i = 0; i + 1 < k; i++) {
-			uint32_t qa = p0 + i, qb = p0 + k - 2 - i;
-			uint32_t ca = (sm.codes[qa >> 4] >> (2 * (qa & 15))) & 3u;
-			uint32_t cb = (sm.codes[qb >> 4] >> (2 * (qb & 15))) & 3u;
-			F = srol(F) ^ Gf[ca];
-			RC = srol(RC) ^ Gr[cb];
-			bool bad = (sm.badw[qa >> 5] >> (qa & 31)) & 1u;
-			bool st = (sm.startw[qa >> 5] >> (qa & 31)) & 1u;
-			g = bad ? 0u : (st ? 1u : g + 1u);
+		out_codes = ((uint64_t)sm.codes[(p0 >> 4) + 1] << 32) | sm.codes[p0 >> 4];
+		if (seed_rows(k)) {
+			seed_packed(sm, p0, k, out_codes, F, RC, g);
+		} else {
+			for (uint32_t i = 0; i + 1 < k; i++) {
+				uint32_t qa = p0 + i, qb = p0 + k - 2 - i;
+				uint32_t ca = (sm.codes[qa >> 4] >> (2 * (qa & 15))) & 3u;
+				uint32_t cb = (sm.codes[qb >> 4] >> (2 * (qb & 15))) & 3u;
+				F = srol(F) ^ Gf[ca];
+				RC = srol(RC) ^ Gr[cb];
+				bool bad = (sm.badw[qa >> 5] >> (qa & 31)) & 1u;
+				bool st = (sm.startw[qa >> 5] >> (qa & 31)) & 1u;
+				g = bad ? 0u : (st ? 1u : g + 1u);
+			}
+			RC = srol(RC);
 		}
-		RC = srol(RC);
 		// register streams: 32 incoming bases from q1 (unaligned), 32 outgoing bases from p0 (aligned)
 		uint32_t a = q1 >> 4, sh2 = 2 * (q1 & 15);
 		uint32_t in_lo = funnel_r(sm.codes[a], sm.codes[a + 1], sh2);
@@ -752,7 +815,6 @@ struct Roller
 		in_bad = funnel_r(sm.badw[bw], sm.badw[bw + 1], sh1);
 		in_start = funnel_r(sm.startw[bw], sm.startw[bw + 1], sh1);
 		in_codes = ((uint64_t)in_hi << 32) | in_lo;
-		out_codes = ((uint64_t)sm.codes[(p0 >> 4) + 1] << 32) | sm.codes[p0 >> 4];
 	}
 
 	// advances to window p0+s (s = 0, 1, 2, ... in order); true when it is a k-mer the reference's
