@@ -61,34 +61,49 @@ def static_hist(obj, needle):
 
 
 def dynamic_hist(path):
+    """rows of an `ncu --page source --csv` export: (address, opcode, executed warp-instructions, stall samples)"""
+    allrows = list(csv.reader(open(path, newline="")))
+    hi = [i for i, r in enumerate(allrows) if r and r[0] == "Address"][0]
+    name = allrows[hi - 1][1] if hi > 0 and len(allrows[hi - 1]) > 1 else "(ncu source page)"
+    idx = {h: i for i, h in enumerate(allrows[hi])}
+    src, cnt, smp = idx["Source"], idx["Instructions Executed"], idx.get("Warp Stall Sampling (All Samples)")
     rows = []
-    with open(path, newline="") as fh:
-        rd = csv.reader(fh)
-        hdr = next(rd)
-        idx = {h: i for i, h in enumerate(hdr)}
-        src = idx.get("Source")
-        cnt = idx.get("# Instructions Executed", idx.get("Instructions Executed"))
-        adr = idx.get("Address")
-        for r in rd:
-            if len(r) <= max(src, cnt):
-                continue
-            ins = re.sub(r"^@!?U?P\d+\s+", "", r[src].strip())
-            if not ins:
-                continue
-            try:
-                n = int(float(r[cnt]))
-            except ValueError:
-                continue
-            a = int(r[adr], 16) if adr is not None and r[adr] else len(rows)
-            rows.append((a, ins.split()[0], n))
-    return "(ncu source page)", rows
+    for r in allrows[hi + 1:]:
+        try:
+            a, n = int(r[0], 16), int(float(r[cnt]))
+        except (ValueError, IndexError):
+            continue
+        ins = re.sub(r"^@!?U?P\d+\s+", "", r[src].strip())
+        if ins:
+            rows.append((a, ins.split()[0], n, int(r[smp] or 0) if smp is not None else 0))
+    return name, rows
+
+
+def sections(rows):
+    """executed instructions between consecutive CTA barriers (the kernel's phases)"""
+    base = rows[0][0]
+    tot = sum(r[2] for r in rows)
+    out, cur, start = [], 0, rows[0][0]
+    smp = 0
+    for r in rows:
+        cur += r[2]
+        smp += r[3] if len(r) > 3 else 0
+        if r[1].startswith("BAR"):
+            out.append((start - base, r[0] - base, cur, smp))
+            cur, smp, start = 0, 0, r[0] + 16
+    out.append((start - base, rows[-1][0] - base, cur, smp))
+    lines = ["| code range (hex offset) | executed warp-instructions | share | stall samples |", "|---|---|---|---|"]
+    for a, b, n, sp in out:
+        lines.append("| %x - %x | %d | %.1f %% | %d |" % (a, b, n, 100.0 * n / max(1, tot), sp))
+    return "\n".join(lines)
 
 
 def report(func, rows, unit, per=None):
-    tot = sum(n for _, _, n in rows)
+    tot = sum(r[2] for r in rows)
     by = collections.Counter()
     ops = collections.Counter()
-    for _, op, n in rows:
+    for r in rows:
+        op, n = r[1], r[2]
         by[classify(op)] += n
         ops[op.split(".")[0]] += n
     lines = ["kernel: %s" % func, "%s: %d" % (unit, tot), ""]
@@ -118,7 +133,7 @@ def main():
         a = a[:i] + a[i + 2:]
     if a[0] == "--source-csv":
         func, rows = dynamic_hist(a[1])
-        txt = report(func, rows, "executed warp-instructions", per)
+        txt = report(func, rows, "executed warp-instructions", per) + "\n\nbetween CTA barriers:\n\n" + sections(rows)
     else:
         func, rows = static_hist(a[0], a[1])
         txt = report(func, rows, "static instructions")
