@@ -427,6 +427,8 @@ MERGE_HOW = {
     "multimem": "btlbf_merge_multimem: one kernel per GPU, multimem.ld_reduce.or + multimem.st over an NVLS multicast mapping "
                 "of the partial filters (symmetric memory); the OR happens inside NVSwitch",
     "peer": "btlbf_merge_peers: one kernel per GPU over NVLink peer memory (reduce-scatter + all-gather in one pass)",
+    "hybrid": "btlbf_merge_hybrid: one kernel per GPU, part of its byte range reduced inside NVSwitch (multimem), the rest over "
+              "NVLink peer memory, side by side",
 }
 
 
@@ -732,9 +734,10 @@ def run_config(env, name, cfg, S, W, headline):
     if world > 1:
         # what the ranks do when nothing connects them: the same phases without the merge
         out["per_gpu_rate"] = (k_ins + k_qry) / ((ms_build + ms_query) * 1e-3) / 1e9
-        per_dir = filter_bytes(cfg) * (1.0 if merge_how == "multimem" else 2.0 * (world - 1) / world)
+        mm_share = 1.0 if merge_how == "multimem" else int(merge_how[6:]) / 100.0 if merge_how.startswith("hybrid") else 0.0
+        per_dir = filter_bytes(cfg) * (mm_share * (1.0 + 1.0 / world) + (1.0 - mm_share) * 2.0 * (world - 1) / world)
         out["merge"] = {"ms": ms_merge, "filter_bytes": filter_bytes(cfg), "kind": merge_how,
-                        "how": MERGE_HOW[merge_how] + ", two stream-ordered barriers",
+                        "how": MERGE_HOW["hybrid" if merge_how.startswith("hybrid") else merge_how] + ", two stream-ordered barriers",
                         "link_bytes_per_gpu_per_direction": per_dir,
                         "link_GBps_per_gpu_per_direction": per_dir / (ms_merge * 1e-3) / 1e9}
         if getattr(pm, "calibration", None):
@@ -886,7 +889,7 @@ def main():
     ap.add_argument("--no-job", action="store_true", help="skip the strong-scaled full cfg2 job")
     ap.add_argument("--cpu-sample", type=int, default=8 << 20, help="bases per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--merge", default="auto", choices=["auto", "multimem", "peer", "ipc"],
+    ap.add_argument("--merge", default="auto", choices=["auto", "multimem", "peer", "hybrid30", "hybrid50", "hybrid70", "ipc"],
                     help="N > 1 merge kernel: auto = the faster of the in-switch OR (multimem) and the peer-memory kernel, timed "
                          "once on this box; ipc = own allocations + CUDA IPC + the peer-memory kernel")
     ap.add_argument("--no-e2e", action="store_true")

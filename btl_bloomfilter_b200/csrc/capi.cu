@@ -1134,6 +1134,38 @@ extern "C" int btlbf_merge_multimem(btlbf_ctx* ctx, int kind, void* mc_base, int
 	return BTLBF_OK;
 }
 
+// Both at once (BLOOM, world 2 / 4 / 8): mm_pct per cent of this rank's byte range through the multicast mapping, the
+// rest through the peer pointers, in one kernel.
+extern "C" int btlbf_merge_hybrid(btlbf_ctx* ctx, int kind, void* mc_base, void* const* bases, int world, int rank,
+                                  uint64_t nbytes, unsigned mm_pct)
+{
+	if (kind != BTLBF_BLOOM)
+		return fail(BTLBF_ERR_ARG, "the in-switch merge is an OR: counting filters (saturating add) use btlbf_merge_peers");
+	if (!mc_base || ((uintptr_t)mc_base & 15u) || !bases || (world != 2 && world != 4 && world != 8) || rank < 0 || rank >= world ||
+	    mm_pct > 100)
+		return fail(BTLBF_ERR_ARG, "bad multicast base / peer list / world (2, 4 or 8) / rank / percentage");
+	TRY(use(ctx));
+	LOCKED(ctx);
+	PeerMergeParams M;
+	memset(&M, 0, sizeof M);
+	for (int i = 0; i < world; i++) {
+		void* b = bases[(rank + i) % world];
+		if (!b || ((uintptr_t)b & 15u))
+			return fail(BTLBF_ERR_ARG, "peer base %d is null or not 16-byte aligned", (rank + i) % world);
+		M.base[i] = (uint8_t*)b;
+	}
+	M.world = (uint32_t)world;
+	M.grid = (uint32_t)ctx->peer_grid;
+	TRY(btlbf_merge_slice(nbytes, world, rank, &M.lo, &M.hi));
+	cudaStream_t s;
+	TRY(join(ctx, &s));
+	cudaError_t e = launch_hybrid_merge(M, mc_base, mm_pct, s);
+	if (e != cudaSuccess)
+		return fail(BTLBF_ERR_CUDA, "hybrid merge launch failed: %s", cudaGetErrorString(e));
+	ctx->launches++;
+	return BTLBF_OK;
+}
+
 // ---------------------------------------------------------------- ordered (exact) updates
 static int ordered_state(btlbf_filter* f, uint32_t batch)
 {

@@ -852,10 +852,10 @@ cudaError_t launch_peer_merge(const PeerMergeParams& M, cudaStream_t stream)
 // only (vector forms are floating point), so a thread moves UNROLL independent 8-byte words per iteration.
 // Saturating add has no multimem form: counting filters stay on peer_merge_kernel.
 template<int UNROLL>
-__global__ void __launch_bounds__(512) multimem_or_kernel(uint64_t* __restrict__ mc, uint64_t n_words)
+__device__ __forceinline__ void multimem_or_range(uint64_t* __restrict__ mc, uint64_t n_words, uint32_t cta, uint32_t n_ctas)
 {
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * UNROLL;
-	for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x * UNROLL + threadIdx.x; i0 < n_words; i0 += stride) {
+	const uint64_t stride = (uint64_t)n_ctas * blockDim.x * UNROLL;
+	for (uint64_t i0 = (uint64_t)cta * blockDim.x * UNROLL + threadIdx.x; i0 < n_words; i0 += stride) {
 		uint64_t v[UNROLL];
 #pragma unroll
 		for (int u = 0; u < UNROLL; u++) {
@@ -871,6 +871,70 @@ __global__ void __launch_bounds__(512) multimem_or_kernel(uint64_t* __restrict__
 				asm volatile("multimem.st.relaxed.sys.global.b64 [%0], %1;" ::"l"(mc + i), "l"(v[u]) : "memory");
 		}
 	}
+}
+
+template<int UNROLL>
+__global__ void __launch_bounds__(512) multimem_or_kernel(uint64_t* __restrict__ mc, uint64_t n_words)
+{
+	multimem_or_range<UNROLL>(mc, n_words, blockIdx.x, gridDim.x);
+}
+
+// Both mechanisms at once: the first mm_ctas CTAs reduce bytes [lo, mid) inside the switch (multimem), the others
+// bytes [mid, hi) with peer loads and stores.  The two paths stress different parts of the fabric (the switch's
+// reduction / multicast engines against plain link bandwidth), so running them side by side can finish sooner than
+// either alone.  OR only.
+template<int WORLD>
+__global__ void __launch_bounds__(256) hybrid_merge_kernel(const __grid_constant__ PeerMergeParams M, uint64_t* __restrict__ mc,
+                                                            uint64_t mid, uint32_t mm_ctas)
+{
+	if (blockIdx.x < mm_ctas) {
+		multimem_or_range<4>(mc + M.lo / 8, (mid - M.lo) / 8, blockIdx.x, mm_ctas);
+		return;
+	}
+	const uint32_t cta = blockIdx.x - mm_ctas, n_ctas = gridDim.x - mm_ctas;
+	const uint64_t nvec = (M.hi - mid) / 16;
+	const uint64_t stride = (uint64_t)n_ctas * blockDim.x;
+	for (uint64_t i = (uint64_t)cta * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+		const uint64_t o = mid + i * 16;
+		uint4 v[WORLD];
+#pragma unroll
+		for (int p = 0; p < WORLD; p++)
+			v[p] = *reinterpret_cast<const uint4*>(M.base[p] + o);
+		uint4 acc = v[0];
+#pragma unroll
+		for (int p = 1; p < WORLD; p++) {
+			acc.x |= v[p].x; acc.y |= v[p].y; acc.z |= v[p].z; acc.w |= v[p].w;
+		}
+#pragma unroll
+		for (int p = 0; p < WORLD; p++)
+			*reinterpret_cast<uint4*>(M.base[p] + o) = acc;
+	}
+}
+
+cudaError_t launch_hybrid_merge(const PeerMergeParams& M, void* mc_base, unsigned mm_pct, cudaStream_t stream)
+{
+	if (M.world < 2 || M.world > (uint32_t)kMaxPeers || M.lo > M.hi || ((M.lo | M.hi) & 15u) || !mc_base || mm_pct > 100)
+		return cudaErrorInvalidValue;
+	if (M.hi == M.lo)
+		return cudaSuccess;
+	uint64_t mid = M.lo + (M.hi - M.lo) / 100 * mm_pct / 16 * 16;
+	if (mm_pct == 100)
+		mid = M.hi;
+	const unsigned total = M.grid ? M.grid : sm_count() * 8;
+	unsigned mm_ctas = (unsigned)((uint64_t)total * mm_pct / 100);
+	if (mid > M.lo && mm_ctas == 0)
+		mm_ctas = 1;
+	if (mid == M.lo)
+		mm_ctas = 0;
+	unsigned grid = mid < M.hi ? (total > mm_ctas ? total : mm_ctas + 1) : mm_ctas;
+	uint64_t* mc = reinterpret_cast<uint64_t*>(mc_base);
+	switch (M.world) {
+	case 2: hybrid_merge_kernel<2><<<grid, 256, 0, stream>>>(M, mc, mid, mm_ctas); break;
+	case 4: hybrid_merge_kernel<4><<<grid, 256, 0, stream>>>(M, mc, mid, mm_ctas); break;
+	case 8: hybrid_merge_kernel<8><<<grid, 256, 0, stream>>>(M, mc, mid, mm_ctas); break;
+	default: return cudaErrorInvalidValue;
+	}
+	return cudaGetLastError();
 }
 
 cudaError_t launch_multimem_or(void* mc_base, uint64_t lo, uint64_t hi, unsigned unroll, unsigned grid_ctas, cudaStream_t stream)

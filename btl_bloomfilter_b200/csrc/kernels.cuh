@@ -191,6 +191,8 @@ struct PeerMergeParams
 cudaError_t launch_peer_merge(const PeerMergeParams& M, cudaStream_t stream);
 // OR of all replicas of bytes [lo, hi) of an NVLS multicast mapping, written back to all replicas
 cudaError_t launch_multimem_or(void* mc_base, uint64_t lo, uint64_t hi, unsigned unroll, unsigned grid_ctas, cudaStream_t stream);
+// the first mm_pct per cent of [M.lo, M.hi) through the multicast mapping, the rest through the peer pointers, in one kernel
+cudaError_t launch_hybrid_merge(const PeerMergeParams& M, void* mc_base, unsigned mm_pct, cudaStream_t stream);
 cudaError_t launch_synth_genome(uint8_t* out, uint64_t start, uint64_t n, uint64_t seed,
                                 cudaStream_t stream);
 cudaError_t launch_synth_reads(uint8_t* out, uint64_t first_read, uint64_t n_reads,

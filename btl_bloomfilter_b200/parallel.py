@@ -278,6 +278,8 @@ class MultimemMerge:
                   NVLink direction
       "peer"      the peer-memory kernel (btlbf_merge_peers) over the handle's peer pointers (no CUDA IPC plumbing
                   needed); 2 (N-1)/N of the filter per direction; also the saturating-add merge of counting filters
+      "hybridP"   P per cent of the byte range inside the switch and the rest over peer memory, in one kernel
+                  (btlbf_merge_hybrid)
     Which one is faster depends on N (measured on B200 at N = 2: peer 6.5 ms, multimem 12.2 ms for a 3.95 GB filter,
     because multimem pulls the local replica through the switch too); calibrate() times both once on the box and keeps
     the faster.  Collective: every rank of the group constructs it and calls its methods together."""
@@ -291,6 +293,8 @@ class MultimemMerge:
         assert len(ptrs) == self.world
         self._bases = (C.c_void_p * self.world)(*ptrs)
         self.modes = (["multimem"] if self.mc else []) + ["peer"]
+        if self.mc and self.world in (2, 4, 8):  # both at once, 30 / 50 / 70 % of the range inside the switch
+            self.modes += ["hybrid30", "hybrid50", "hybrid70"]
         if mode is not None and mode not in self.modes:
             raise RuntimeError("merge mode %r is not available here (have %s)" % (mode, self.modes))
         self.mode = mode or self.modes[0]
@@ -304,8 +308,12 @@ class MultimemMerge:
         """The kernel alone; the caller brackets it (ctx.flush() before the first barrier, see PeerMerge.launch)."""
         from ._capi import check
         L, ctx = self.ctx.L, self.ctx
-        if (mode or self.mode) == "multimem":
+        mode = mode or self.mode
+        if mode == "multimem":
             check(L.btlbf_merge_multimem(ctx.handle, 0, C.c_void_p(self.mc), self.world, self.rank, self.nbytes))
+        elif mode.startswith("hybrid"):
+            check(L.btlbf_merge_hybrid(ctx.handle, 0, C.c_void_p(self.mc), self._bases, self.world, self.rank, self.nbytes,
+                                       int(mode[6:])))
         else:
             check(L.btlbf_merge_peers(ctx.handle, self.kind, self._bases, self.world, self.rank, self.nbytes))
 

@@ -180,6 +180,11 @@ int btlbf_merge_peers(btlbf_ctx *ctx, int kind, void *const *bases, int world, i
  * "wrap_accumulate" = 1 lets wrapped filters defer pass 2 of the partitioned build like owned ones (the caller
  * then calls btlbf_ctx_flush before the merge, as PeerMerge / MultimemMerge in parallel.py do). */
 int btlbf_merge_multimem(btlbf_ctx *ctx, int kind, void *mc_base, int world, int rank, uint64_t nbytes);
+/* Both mechanisms in ONE kernel (BLOOM; world 2, 4 or 8): the first mm_pct per cent of this rank's byte range is
+ * reduced inside the switch through mc_base, the rest with peer loads / stores through bases[] (as btlbf_merge_peers).
+ * The two paths load different parts of the fabric; parallel.py times the split once per box (MultimemMerge.calibrate). */
+int btlbf_merge_hybrid(btlbf_ctx *ctx, int kind, void *mc_base, void *const *bases, int world, int rank,
+                       uint64_t nbytes, unsigned mm_pct);
 /* order-dependent updates (counting insert, insert_and_check): number of k-mers that had to wait for
  * the index-ordered residual rounds, and the number of such rounds, since the filter was created */
 int btlbf_filter_ordered_stats(btlbf_filter *f, uint64_t *deferred, uint64_t *rounds);

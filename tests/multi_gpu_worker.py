@@ -99,6 +99,13 @@ def main():
     m7 = parallel.MultimemMerge(ctx2, hdl7, nbytes, mode="peer")
     m7.merge()
     assert np.array_equal(f7.to_numpy(), filt), "rank %d: peer merge over symmetric memory differs" % rank
+    if mm_ok:  # both mechanisms side by side in one kernel
+        f8, hdl8 = parallel.symmetric_filter(B.BloomFilter, bits, h, k, ctx2)
+        f8.insertSeqs(my)
+        m8 = parallel.MultimemMerge(ctx2, hdl8, nbytes, mode="hybrid50")
+        m8.merge()
+        assert np.array_equal(f8.to_numpy(), filt), "rank %d: hybrid merge differs from the oracle" % rank
+        m8.close()
     assert m7.calibrate() in m7.modes
     m7.merge()
     assert np.array_equal(f7.to_numpy(), filt)
