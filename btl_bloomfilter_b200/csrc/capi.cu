@@ -151,7 +151,7 @@ struct btlbf_ctx
 	int64_t query_p1_ctas = 0;      // pass-1 CTAs per SM while overlapping (0 auto: one fewer than fit)
 	int64_t query_probe_unroll = 0; // item vectors in flight per thread of pass 2 (0 auto)
 	int64_t probe_ld = 0, probe_carveout = -1; // experiment knobs of the probe kernel (load flavour; L1 split: -1 auto, 0 large L1, 1 small)
-	int64_t bin_prefetch = -1;      // pass 2 pulls the next partition into L2: -1 auto (partitions up to 16 MiB), 0, 1
+	int64_t bin_prefetch = -1;      // pass 2 prefetch into L2: -1 auto (see bin_setup), 0 none, 1 the next partition, 2 the CTA's share of its own
 	DevBuf ibin2_items, ibin2_counts; // level-2 buckets of the two-level pass 2 (apply2.cu)
 	int64_t bin_two_level = 0;        // 1: two-level pass 2 (apply2.cu); measured slower than the L2-atomics pass on B200
 	int64_t bin_two_level_min = (int64_t)1 << 26; // items below which the one-level pass is used
@@ -673,8 +673,8 @@ extern "C" int btlbf_ctx_set_option(btlbf_ctx* ctx, const char* key, int64_t val
 	} else if (k == "probe_carveout") {
 		ctx->probe_carveout = value < -1 || value > 1 ? -1 : value;
 	} else if (k == "bin_prefetch") {
-		if (value < -1 || value > 1)
-			return fail(BTLBF_ERR_ARG, "bin_prefetch must be -1, 0 or 1");
+		if (value < -1 || value > 2)
+			return fail(BTLBF_ERR_ARG, "bin_prefetch must be -1, 0, 1 or 2");
 		ctx->bin_prefetch = value;
 	} else if (k == "bin_two_level") {
 		ctx->bin_two_level = value != 0;
@@ -1402,11 +1402,15 @@ static int bin_setup(btlbf_filter* f, SeqParams& P, bool query, uint64_t capacit
 	P.bin_mask = (uint32_t)(((uint64_t)1 << shift) - 1);
 	P.bin_counting = f->kind == BTLBF_COUNTING8;
 	{
-		// Prefetching the next partition: always for the build (16 GiB filter, 32 MiB partitions: 16.9 against 15.7
-		// Gk-mer/s); for the query only while two partitions plus the item stream stay resident in L2 (32 MiB
-		// partitions: 21.3 with, 24.2 without; counting filter 20.6 / 24.7).
+		// Prefetch rules of pass 2, measured on B200 (profiles/r2_prefetch_sweep.txt).  Partitions up to 16 MiB: pull the
+		// NEXT partition into L2 while this one is processed (cfg2 build 27.9 against 23.8 Gk-mer/s without).  Larger
+		// partitions (the 16 GB filters: 512 x 32 MiB): two of them plus the item stream do not stay resident, so the
+		// build prefetches the CTA's share of its OWN partition in full lines (19.1 against 17.1 with the next one and
+		// 16.7 with none) and the query none at all (16 GiB BloomFilter 24.7 against 22.4 / 21.3; counting filter 24.5
+		// against 23.4 / 20.5).  1024 partitions of 16 MiB instead: slower in every case (pass 1 runs get too short).
 		const uint64_t part_bytes = f->kind == BTLBF_COUNTING8 ? (uint64_t)1 << shift : ((uint64_t)1 << shift) >> 3;
-		P.bin_prefetch = ctx->bin_prefetch < 0 ? (!query || part_bytes <= ((uint64_t)16 << 20)) : ctx->bin_prefetch != 0;
+		const bool small = part_bytes <= ((uint64_t)16 << 20);
+		P.bin_prefetch = ctx->bin_prefetch < 0 ? (small ? 1u : query ? 0u : 2u) : (uint32_t)ctx->bin_prefetch;
 	}
 	uint32_t writers = 0;
 	cudaError_t e = bin_plan(P, P.n_bins, query, &writers, grid, mode);

@@ -29,8 +29,11 @@ __global__ void __launch_bounds__(kApplyThreads) apply_bins_kernel(const __grid_
 	uint32_t* region = (uint32_t*)P.filter + ((uint64_t)part << (P.bin_shift - 5));
 	// Software pipeline: while partition `part` is being updated, pull the next partition's lines into L2
 	// with full-line prefetches, so that its atomics hit in L2 instead of waiting on one HBM sector each.
-	if (P.bin_prefetch && part + 1 < P.n_bins) {
-		const uint64_t next_bit0 = (uint64_t)(part + 1) << P.bin_shift;
+	// (bin_prefetch == 2: this CTA's share of its OWN partition instead -- full 128-byte lines ahead of the demand
+	// misses, without a second partition in L2; for partitions too large to keep two of them resident)
+	const uint32_t pf_part = part + (P.bin_prefetch == 2 ? 0u : 1u);
+	if (P.bin_prefetch && pf_part < P.n_bins) {
+		const uint64_t next_bit0 = (uint64_t)pf_part << P.bin_shift;
 		uint64_t bits = P.fm.m - next_bit0;
 		if (bits > ((uint64_t)1 << P.bin_shift))
 			bits = (uint64_t)1 << P.bin_shift;
@@ -119,8 +122,9 @@ __global__ void __launch_bounds__(kApplyThreads) probe_bins_kernel(const __grid_
 	const uint32_t part = blockIdx.x / blocks_per_part, sub = blockIdx.x % blocks_per_part;
 	const void* region = COUNTING ? (const void*)((const uint8_t*)P.filter + ((uint64_t)part << P.bin_shift))
 	                              : (const void*)((const uint32_t*)P.filter + ((uint64_t)part << (P.bin_shift - 5)));
-	if (P.bin_prefetch && part + 1 < P.n_bins) {
-		const uint64_t next0 = (uint64_t)(part + 1) << P.bin_shift; // bits, or counters
+	const uint32_t pf_part = part + (P.bin_prefetch == 2 ? 0u : 1u); // 2: the CTA's share of its own partition (see apply_bins_kernel)
+	if (P.bin_prefetch && pf_part < P.n_bins) {
+		const uint64_t next0 = (uint64_t)pf_part << P.bin_shift; // bits, or counters
 		uint64_t units = P.fm.m - next0;
 		if (units > ((uint64_t)1 << P.bin_shift))
 			units = (uint64_t)1 << P.bin_shift;
