@@ -292,11 +292,12 @@ class MultimemMerge:
         ptrs = [int(p) for p in hdl.buffer_ptrs]
         assert len(ptrs) == self.world
         self._bases = (C.c_void_p * self.world)(*ptrs)
-        self.modes = (["multimem"] if self.mc else []) + ["peer"]
-        if self.mc and self.world in (2, 4, 8):  # both at once, 30 / 50 / 70 % of the range inside the switch
-            self.modes += ["hybrid30", "hybrid50", "hybrid70"]
-        if mode is not None and mode not in self.modes:
-            raise RuntimeError("merge mode %r is not available here (have %s)" % (mode, self.modes))
+        self.modes = (["multimem"] if self.mc else []) + ["peer"]  # what calibrate() times
+        # both at once, P per cent of the range inside the switch: on request only (measured at N = 2: 8.8 / 9.5 / 10.7 ms
+        # for P = 30 / 50 / 70 between peer 6.5 and multimem 12.1 -- the two paths share the links, their times add)
+        hybrid = ["hybrid%d" % p for p in (30, 50, 70)] if self.mc and self.world in (2, 4, 8) else []
+        if mode is not None and mode not in self.modes + hybrid:
+            raise RuntimeError("merge mode %r is not available here (have %s)" % (mode, self.modes + hybrid))
         self.mode = mode or self.modes[0]
         self.calibration = None
 
