@@ -85,7 +85,28 @@ def test_partitioned_query_full_size_equals_oracle(oracle, bits, k, h):
     ctx.set_option("bin_query_mode", -1)
     r = f.containsSeqs((qb, qoff))
     assert np.array_equal(O.bits_to_bool(r.hit_bits, qb.size), present)
-    del f
+    # the same batch as 2 bits per base + invalid plane (btlbf_pack_seqs, btlbf_contains_seqs_packed), partitioned path
+    pk = B.pack_seqs((qb, qoff))
+    assert pk.invalid is not None and pk.n_invalid > 0
+    ctx.set_option("bin_query_mode", 1)
+    ctx.set_option("query_adaptive", 0)
+    b0 = ctx.counter("binned_launches")
+    r = f.containsSeqsPacked(pk)
+    assert ctx.counter("binned_launches") > b0
+    assert (r.n_kmers, r.n_hits) == (nv, n_hit) and np.array_equal(r.valid_bits, valid)
+    assert np.array_equal(O.bits_to_bool(r.hit_bits, qb.size), present), "packed query"
+    # ... and the packed build of the same genome gives the ASCII build's bytes
+    from btl_bloomfilter_b200 import parallel
+    f2 = B.BloomFilter(bits, h, k, ctx=ctx)
+    b0 = ctx.counter("binned_launches")
+    assert f2.insertSeqsPacked(B.pack_seqs((host_g, np.array([0, n_ins], np.uint64)))) == n_ins - k + 1
+    assert ctx.counter("binned_launches") > b0, "the packed build did not take the partitioned path"
+    va = parallel.device_tensor_from_ptr(*f.device_ptr(), dev)
+    vb = parallel.device_tensor_from_ptr(*f2.device_ptr(), dev)
+    assert torch.equal(va, vb), "packed build differs from the ASCII build"
+    for key, v in (("bin_query_mode", 0), ("query_adaptive", 1)):
+        ctx.set_option(key, v)
+    del f, f2, va, vb
     ctx.close()
 
 
