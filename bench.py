@@ -807,7 +807,7 @@ def run_config(env, name, cfg, S, W, headline):
         out.update({"roofline": roof_q, "roofline_build": roof_b, "roofline_step": roof_s, "clocks": clocks})
         if miss:
             out["query_miss_set"] = miss
-        if name == "cfg2":
+        if name == "cfg2" and not env.args.no_job:
             out["job"] = run_job(env, cfg, filt, pm)
     if pm is not None:
         pm.close()
