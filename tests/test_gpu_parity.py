@@ -625,3 +625,59 @@ def test_two_level_pass2_equals_oracle(oracle, golden, shift):
     filt = np.zeros((1 << 22) // 8, np.uint8)
     assert f.insert(seqs) == oracle.bf_insert_seqs(filt, 1 << 22, 4, 11, b, off)
     assert np.array_equal(f.bytes(), filt)
+
+
+def test_per_kmer_updates_from_threads_and_in_order(gpu, oracle):
+    """The legacy per-k-mer interface (`bloom.insert(*itr)`, README.md:30-43): (a) eight host threads insert into one
+    shared BloomFilter concurrently (the reference's OpenMP pattern, Tests/AdHoc/ParallelFilter.cpp:104-122) -- same bytes
+    as the batched build; (b) one thread feeds a CountingBloomFilter k-mer by k-mer, across the boundaries of the
+    per-thread (512) and per-filter (65,536) queues, interleaved with reads -- the order-dependent incrementMin result
+    of the sequential reference loop (CountingBloomFilter.hpp:134-162), and reads see everything queued before them."""
+    import threading
+    B = gpu.B
+    k, h, bits = 25, 4, 1 << 22
+    g = oracle.synth_genome(0, 90_000, 42)
+    off = np.array([0, g.size], np.uint64)
+    n, hs, valid = oracle.hash_seqs(h, k, g, off)
+    hs = np.ascontiguousarray(hs[: g.size - k + 1])
+    filt = np.zeros(bits // 8, np.uint8)
+    assert oracle.bf_insert_seqs(filt, bits, h, k, g, off) == n
+    f = B.BloomFilter(bits, h, k, ctx=gpu.ctx)
+    nthreads = 8
+    per = (hs.shape[0] + nthreads - 1) // nthreads
+
+    def work(t):
+        for row in hs[t * per:(t + 1) * per]:
+            f.insert(row)
+
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert f.getPop() == int(np.unpackbits(filt).sum())  # a read drains every thread's queue
+    assert np.array_equal(f.to_numpy(), filt)
+    # (b) counting filter, one thread, 70k k-mers with heavy repetition
+    m = 50_000
+    reps = np.concatenate([g[:30_000], g[:30_000], g[10_000:25_000]])
+    roff = np.array([0, 30_000, 60_000, 75_000], np.uint64)
+    n2, hs2, valid2 = oracle.hash_seqs(h, k, reps, roff)
+    vmask = O.bits_to_bool(valid2, reps.size)
+    rows = np.ascontiguousarray(hs2[vmask])
+    cnt = np.zeros(m, np.uint8)
+    assert oracle.cbf_insert_seqs(cnt, m, h, k, reps, roff) == rows.shape[0]
+    c = B.CountingBloomFilter(m, h, k, 2, ctx=gpu.ctx)
+    half = rows.shape[0] // 2
+    for row in rows[:half]:
+        c.insert(row)
+    mid = c.minCount(rows[half - 1])  # a read in the middle of the stream sees the first half, all of it
+    part = np.zeros(m, np.uint8)      # the sequential loop of CountingBloomFilter.hpp:134-162 over the first half
+    for row in rows[:half]:
+        slots = (row % np.uint64(m)).astype(np.int64)
+        mn = part[slots].min()
+        if mn < 255:
+            part[slots[part[slots] == mn]] += 1
+    assert mid == int(part[(rows[half - 1] % np.uint64(m)).astype(np.int64)].min())
+    for row in rows[half:]:
+        c.insert(row)
+    assert np.array_equal(c.to_numpy(), cnt)
