@@ -415,7 +415,7 @@ def make_sharded_filter(env, cfg):
                     f.clear()
                 pm.mode, pm.calibration = env.merge_choice[key]
             return f, pm, pm.mode
-        except RuntimeError as e:  # symmetric memory unavailable: every rank takes the same branch
+        except Exception as e:  # noqa: BLE001  symmetric memory unavailable: every rank takes the same branch
             if want in ("multimem", "peer"):
                 raise SystemExit("--merge %s: %s" % (want, str(e)[:200]))
             env.no_symm = "%s: %s" % (type(e).__name__, str(e)[:120])
