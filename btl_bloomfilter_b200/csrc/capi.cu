@@ -13,6 +13,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace btl;
@@ -86,6 +87,7 @@ struct TlQueue
 	uint32_t n = 0;
 	int op = -1;
 	uint64_t* data = nullptr; // kTlCap x h hash values, in call order
+	std::thread::id owner;    // the host thread that appends to it
 };
 constexpr uint32_t kTlCap = 512;
 
@@ -2505,19 +2507,29 @@ static TlQueue* tl_queue(btlbf_filter* f)
 	for (const Entry& e : cache)
 		if (e.uid == f->uid)
 			return e.q;
-	TlQueue* q = new (std::nothrow) TlQueue;
-	if (!q)
-		return nullptr;
-	q->data = (uint64_t*)malloc((size_t)kTlCap * f->hc.h * 8);
-	if (!q->data) {
-		delete q;
-		return nullptr;
-	}
+	const std::thread::id me = std::this_thread::get_id();
+	TlQueue* q = nullptr;
 	{
 		LOCKED(f->ctx);
-		if (f->tlq.empty())
-			f->ctx->tl_filters.push_back(f);
-		f->tlq.push_back(q);
+		for (TlQueue* t : f->tlq) // a thread that works on more filters than its cache holds finds its queue again
+			if (t->owner == me) {
+				q = t;
+				break;
+			}
+		if (!q) {
+			q = new (std::nothrow) TlQueue;
+			if (!q)
+				return nullptr;
+			q->data = (uint64_t*)malloc((size_t)kTlCap * f->hc.h * 8);
+			if (!q->data) {
+				delete q;
+				return nullptr;
+			}
+			q->owner = me;
+			if (f->tlq.empty())
+				f->ctx->tl_filters.push_back(f);
+			f->tlq.push_back(q);
+		}
 	}
 	cache[next++ & 3u] = { f->uid, q };
 	return q;

@@ -681,3 +681,12 @@ def test_per_kmer_updates_from_threads_and_in_order(gpu, oracle):
     for row in rows[half:]:
         c.insert(row)
     assert np.array_equal(c.to_numpy(), cnt)
+    # (c) one thread alternating between more filters than its queue cache holds: every filter gets exactly its k-mers
+    small = [B.BloomFilter(1 << 16, h, k, ctx=gpu.ctx) for _ in range(6)]
+    for i, row in enumerate(hs[:3000]):
+        small[i % 6].insert(row)
+    for j, sf in enumerate(small):
+        exp = np.zeros((1 << 16) // 8, np.uint8)
+        idx = (hs[j:3000:6].reshape(-1) % np.uint64(1 << 16)).astype(np.int64)
+        np.bitwise_or.at(exp, idx >> 3, (1 << (idx & 7)).astype(np.uint8))
+        assert np.array_equal(sf.to_numpy(), exp), "filter %d" % j
