@@ -279,6 +279,8 @@ class Env:
         self.n_reads = self.chunk * args.query_factor // READ_LEN
         self.read_bases = self.n_reads * READ_LEN
         self.token = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.token2 = torch.zeros(1, dtype=torch.int32, device=self.dev)  # barrier word of the side stream
+        self.side = torch.cuda.Stream(device=self.dev) if self.world > 1 else None  # merges pipelined behind pass 2
         self.host = None
         self.no_symm = None      # why symmetric memory is not used (set on first failure)
         self.merge_choice = {}   # (kind, size) -> (kernel, calibration) of the N > 1 merge
@@ -504,10 +506,21 @@ def run_config(env, name, cfg, S, W, headline):
         filt.containsSeqsDevice(env.r[j].data_ptr(), env.read_bases, env.d_roff.data_ptr(), env.n_reads,
                                 env.d_hits.data_ptr(), 0, d_stats[2:].data_ptr())
 
-    def merge_dev():
+    chunks = env.args.merge_chunks if (pm is not None and hasattr(pm, "launch_range") and kind == "bloom") else 0
+
+    def settle_and_merge(ev_applied=None):
+        """pass 2 of whatever the build has parked, then (N > 1) the merge: one after the other, or -- merge_chunks > 0
+        -- pipelined: the merge of a chunk of partitions runs over NVLink while the next chunk is applied"""
+        if chunks > 0:
+            from btl_bloomfilter_b200 import parallel
+            parallel.pipelined_flush_merge(filt, pm, chunks, env.side, env.token2, ev_applied)
+            return
+        ctx.flush()  # every k-mer parked in the partition buckets reaches the filter (pass 2)
+        if ev_applied is not None:
+            ev_applied.record(env.stream)
         if pm is None:
             return
-        env.stream_barrier()  # every rank's partial build (pass 2 included: ctx.flush) is complete
+        env.stream_barrier()  # every rank's partial build is complete
         pm.launch()
         env.stream_barrier()  # every rank's byte range has been written into every filter
 
@@ -515,9 +528,10 @@ def run_config(env, name, cfg, S, W, headline):
     # timed region (2x coverage), so that every queried k-mer reaches the threshold (a hit set, like the BloomFilter's)
     for i in range(n_q if counting else W):
         build_dev(i)
-    ctx.flush()
-    if not counting:
-        merge_dev()  # (counting: one merge only, the timed one -- a second saturating add would count every k-mer N times over)
+    if counting:
+        ctx.flush()  # (counting: one merge only, the timed one -- a second saturating add would count every k-mer N times over)
+    else:
+        settle_and_merge()
     for i in range(W):
         query_dev(i)
     torch.cuda.synchronize()
@@ -537,9 +551,7 @@ def run_config(env, name, cfg, S, W, headline):
     for i in range(S):
         build_dev(i)
         ev_b[i].record(env.stream)
-    ctx.flush()  # every k-mer parked in the partition buckets reaches the filter (pass 2)
-    t_built.record(env.stream)
-    merge_dev()
+    settle_and_merge(t_built)
     t_mid.record(env.stream)
     for i in range(S):
         query_dev(i)
@@ -740,6 +752,10 @@ def run_config(env, name, cfg, S, W, headline):
                         "how": MERGE_HOW["hybrid" if merge_how.startswith("hybrid") else merge_how] + ", two stream-ordered barriers",
                         "link_bytes_per_gpu_per_direction": per_dir,
                         "link_GBps_per_gpu_per_direction": per_dir / (ms_merge * 1e-3) / 1e9}
+        if chunks > 0:
+            out["merge"]["pipelined_chunks"] = chunks
+            out["merge"]["how"] = ("pass 2 of the build and btlbf_merge_peers_range pipelined in %d chunks of partitions "
+                                   "(btlbf_filter_flush_parts): `ms` is what the merge adds behind the last chunk of pass 2" % chunks)
         if getattr(pm, "calibration", None):
             out["merge"]["calibration_ms"] = pm.calibration
         if env.no_symm:
@@ -838,12 +854,16 @@ def run_job(env, cfg, filt, pm):
         for i in range(n_mine):
             n = env.insert_len(i, k)
             filt.insertSeqsDevice(env.g[i].data_ptr(), n, env.goff(n).data_ptr(), 1, d_stats.data_ptr())
-        ctx.flush()
-        ev[1].record(env.stream)
-        if pm is not None:
-            env.stream_barrier()
-            pm.launch()
-            env.stream_barrier()
+        if pm is not None and env.args.merge_chunks > 0 and hasattr(pm, "launch_range"):
+            from btl_bloomfilter_b200 import parallel
+            parallel.pipelined_flush_merge(filt, pm, env.args.merge_chunks, env.side, env.token2, ev[1])
+        else:
+            ctx.flush()
+            ev[1].record(env.stream)
+            if pm is not None:
+                env.stream_barrier()
+                pm.launch()
+                env.stream_barrier()
         ev[2].record(env.stream)
         for i in range(q_mine):
             filt.containsSeqsDevice(env.r[i % len(env.r)].data_ptr(), env.read_bases, env.d_roff.data_ptr(), env.n_reads,
@@ -893,6 +913,9 @@ def main():
     ap.add_argument("--merge", default="auto", choices=["auto", "multimem", "peer", "hybrid30", "hybrid50", "hybrid70", "ipc"],
                     help="N > 1 merge kernel: auto = the faster of the in-switch OR (multimem) and the peer-memory kernel, timed "
                          "once on this box; ipc = own allocations + CUDA IPC + the peer-memory kernel")
+    ap.add_argument("--merge-chunks", type=int, default=0,
+                    help="N > 1 BloomFilter builds: pipeline the merge behind pass 2 of the build in this many chunks of "
+                         "partitions (0: pass 2, then the merge)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-packed", action="store_true", help="skip the 2-bit packed host-buffer leg (e2e_packed)")
     ap.add_argument("--chunk", type=int, default=CHUNK)

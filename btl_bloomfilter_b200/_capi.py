@@ -52,6 +52,8 @@ SIGNATURES = {
     "btlbf_merge_peers": [vp, C.c_int, C.POINTER(vp), C.c_int, C.c_int, u64],
     "btlbf_merge_multimem": [vp, C.c_int, vp, C.c_int, C.c_int, u64],
     "btlbf_merge_hybrid": [vp, C.c_int, vp, C.POINTER(vp), C.c_int, C.c_int, u64, C.c_uint],
+    "btlbf_filter_flush_parts": [vp, C.c_uint, C.c_uint, u64p, u64p],
+    "btlbf_merge_peers_range": [vp, C.c_int, C.POINTER(vp), C.c_int, C.c_int, u64, u64, vp],
     "btlbf_filter_ordered_stats": [vp, u64p, u64p],
     "btlbf_insert_file": [vp, C.c_char_p, C.c_int, u64p, u64p],
     "btlbf_query_file": [vp, C.c_char_p, C.c_int, u64p, u64p, u64p],

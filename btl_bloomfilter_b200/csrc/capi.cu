@@ -168,6 +168,13 @@ struct btlbf_ctx
 		uint64_t windows = 0, capacity = 0, tiles = 0;
 		int slot = 0;
 	} acc;
+	// btlbf_filter_flush_parts in progress: the filter, its partition geometry and the number of chunks (n_bins 0: the
+	// parked work could not be applied in parts and chunk 0 applied all of it)
+	struct
+	{
+		btlbf_filter* f = nullptr;
+		uint32_t n_bins = 0, shift = 0, n_chunks = 0;
+	} parts;
 	int64_t bin_accum_bytes = (int64_t)8 << 30; // sub-bucket storage one accumulation may use
 	int64_t bin_kernel = 0;                     // 0 auto (sort-bin kernel when the shape allows), 1 legacy kernels only
 	int64_t bin_max_parts = 512;                // the sort-bin path widens the partitions until there are at most this many
@@ -1164,6 +1171,104 @@ extern "C" int btlbf_merge_hybrid(btlbf_ctx* ctx, int kind, void* mc_base, void*
 	cudaError_t e = launch_hybrid_merge(M, mc_base, mm_pct, s);
 	if (e != cudaSuccess)
 		return fail(BTLBF_ERR_CUDA, "hybrid merge launch failed: %s", cudaGetErrorString(e));
+	ctx->launches++;
+	return BTLBF_OK;
+}
+
+// Pass 2 of the parked build in parts, so that a multi-GPU merge can follow the partitions as they are finished
+// (pass 2 is partition-major).  Chunk `chunk` of `n_chunks` applies the parked k-mers of its share of the partitions on
+// the active stream and reports the byte range [lo, hi) of the filter array those partitions cover (multiples of 16).
+// Call with chunk = 0, 1, ..., n_chunks-1; after the last one nothing is parked.  When the parked work cannot be
+// split (nothing parked for f, two-level or background pass 2, queued per-k-mer updates), chunk 0 applies everything
+// and reports the whole array, the other chunks report empty ranges.  Any other call in between settles all of it
+// (harmless: OR is idempotent); the remaining chunks then only report their ranges.
+extern "C" int btlbf_filter_flush_parts(btlbf_filter* f, unsigned chunk, unsigned n_chunks, uint64_t* byte_lo, uint64_t* byte_hi)
+{
+	if (!f || !byte_lo || !byte_hi || n_chunks == 0 || chunk >= n_chunks)
+		return fail(BTLBF_ERR_ARG, "bad filter / chunk");
+	btlbf_ctx* ctx = f->ctx;
+	TRY(use(ctx));
+	LOCKED(ctx);
+	*byte_lo = *byte_hi = 0;
+	const uint64_t whole = (f->bytes + 15) / 16 * 16;
+	if (chunk == 0) {
+		const bool ok = ctx->acc.f == f && f->kind == BTLBF_BLOOM && !ctx->overlap && !ctx->bin_two_level && !ctx->hq_owner &&
+		                ctx->tl_pending.load() == 0 && !ctx->aux_pending && ctx->acc.P.n_bins >= n_chunks && ctx->acc.P.bin_shift >= 7;
+		ctx->parts.f = f;
+		ctx->parts.n_chunks = n_chunks;
+		ctx->parts.n_bins = ok ? ctx->acc.P.n_bins : 0;
+		ctx->parts.shift = ok ? ctx->acc.P.bin_shift : 0;
+		if (!ok) {
+			cudaStream_t s;
+			TRY(join(ctx, &s));
+			*byte_hi = whole;
+			return BTLBF_OK;
+		}
+	} else if (ctx->parts.f != f || ctx->parts.n_chunks != n_chunks) {
+		return fail(BTLBF_ERR_STATE, "flush_parts: chunk %u without chunk 0 of the same sequence", chunk);
+	}
+	if (ctx->parts.n_bins == 0)
+		return BTLBF_OK; // chunk 0 reported the whole array
+	const uint32_t nb = ctx->parts.n_bins;
+	const uint32_t p0 = (uint32_t)((uint64_t)nb * chunk / n_chunks), p1 = (uint32_t)((uint64_t)nb * (chunk + 1) / n_chunks);
+	if (ctx->acc.f == f && p1 > p0) { // still parked: apply this chunk's partitions
+		SeqParams P = ctx->acc.P;
+		P.bin_part0 = p0;
+		P.bin_part_count = p1 - p0;
+		cudaError_t e = launch_apply_bins(P, ctx->active);
+		if (e != cudaSuccess)
+			return fail(BTLBF_ERR_CUDA, "partitioned build (pass 2, partitions %u..%u) launch failed: %s", p0, p1, cudaGetErrorString(e));
+		ctx->launches++;
+	}
+	const uint64_t part_bytes = ((uint64_t)1 << ctx->parts.shift) >> 3;
+	uint64_t lo = (uint64_t)p0 * part_bytes, hi = (uint64_t)p1 * part_bytes;
+	if (chunk + 1 == n_chunks) {
+		hi = whole;
+		if (ctx->acc.f == f) { // the accumulation is closed, as settle() would have done
+			CU(cudaEventRecord(ctx->ev_apply_done[ctx->acc.slot], ctx->active));
+			ctx->slot_used[ctx->acc.slot] = true;
+			ctx->acc.f = nullptr;
+		}
+		ctx->parts.f = nullptr;
+	}
+	*byte_lo = lo < whole ? lo : whole;
+	*byte_hi = hi < whole ? hi : whole;
+	return BTLBF_OK;
+}
+
+// btlbf_merge_peers for bytes [lo, hi) of the arrays only (multiples of 16), on the given stream, WITHOUT applying
+// deferred work first: the caller has just flushed exactly that range (btlbf_filter_flush_parts) and the rest of the
+// parked k-mers must stay parked.  This rank reduces its 1/world share of the range.
+extern "C" int btlbf_merge_peers_range(btlbf_ctx* ctx, int kind, void* const* bases, int world, int rank, uint64_t lo,
+                                       uint64_t hi, void* cuda_stream)
+{
+	if (!bases || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || lo > hi || ((lo | hi) & 15u))
+		return fail(BTLBF_ERR_ARG, "bad peer list / byte range");
+	if (kind != BTLBF_BLOOM && kind != BTLBF_COUNTING8)
+		return fail(BTLBF_ERR_ARG, "bad filter kind");
+	TRY(use(ctx));
+	LOCKED(ctx);
+	PeerMergeParams M;
+	memset(&M, 0, sizeof M);
+	for (int i = 0; i < world; i++) {
+		void* b = bases[(rank + i) % world];
+		if (!b || ((uintptr_t)b & 15u))
+			return fail(BTLBF_ERR_ARG, "peer base %d is null or not 16-byte aligned", (rank + i) % world);
+		M.base[i] = (uint8_t*)b;
+	}
+	M.world = (uint32_t)world;
+	M.sat_add = kind == BTLBF_COUNTING8;
+	M.unroll = (uint32_t)ctx->peer_unroll;
+	M.grid = (uint32_t)ctx->peer_grid;
+	uint64_t a = 0, b = 0;
+	TRY(btlbf_merge_slice(hi - lo, world, rank, &a, &b));
+	M.lo = lo + a;
+	M.hi = lo + (b < hi - lo ? b : hi - lo);
+	if (M.lo > M.hi)
+		M.lo = M.hi;
+	cudaError_t e = launch_peer_merge(M, cuda_stream ? (cudaStream_t)cuda_stream : ctx->active);
+	if (e != cudaSuccess)
+		return fail(BTLBF_ERR_CUDA, "peer merge launch failed: %s", cudaGetErrorString(e));
 	ctx->launches++;
 	return BTLBF_OK;
 }

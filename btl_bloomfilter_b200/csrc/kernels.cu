@@ -25,7 +25,7 @@ namespace btl {
 constexpr int kApplyThreads = BTL_APPLY_THREADS;
 __global__ void __launch_bounds__(kApplyThreads) apply_bins_kernel(const __grid_constant__ SeqParams P, uint32_t blocks_per_part)
 {
-	const uint32_t part = blockIdx.x / blocks_per_part, sub = blockIdx.x % blocks_per_part;
+	const uint32_t part = P.bin_part0 + blockIdx.x / blocks_per_part, sub = blockIdx.x % blocks_per_part;
 	uint32_t* region = (uint32_t*)P.filter + ((uint64_t)part << (P.bin_shift - 5));
 	// Software pipeline: while partition `part` is being updated, pull the next partition's lines into L2
 	// with full-line prefetches, so that its atomics hit in L2 instead of waiting on one HBM sector each.
@@ -393,7 +393,7 @@ cudaError_t launch_finalize_hits(uint32_t* hit, const uint32_t* valid, uint64_t 
 cudaError_t launch_apply_bins(const SeqParams& P, cudaStream_t stream)
 {
 	uint32_t bpp = blocks_per_partition(P);
-	uint64_t grid = (uint64_t)P.n_bins * bpp;
+	uint64_t grid = (uint64_t)(P.bin_part_count ? P.bin_part_count : P.n_bins) * bpp;
 	if (grid == 0)
 		return cudaSuccess;
 	if (grid > 0x7fffffffULL)

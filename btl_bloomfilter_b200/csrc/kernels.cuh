@@ -76,6 +76,8 @@ struct SeqParams
 	uint32_t bin_counting;    // partitioned query of a counting filter: an item is a counter index, the test is >= threshold
 	uint32_t probe_ld;        // pass 2 of the query, experiment knob: 0 ld.global.nc, 1 ld.global.cg, 2 L1::no_allocate
 	uint32_t bin_prefetch;    // pass 2: pull the next partition into L2 while this one is processed
+	uint32_t bin_part0, bin_part_count; // pass 2 of the build over partitions [bin_part0, bin_part0 + bin_part_count) only
+	                                    // (count 0: all of them) -- btlbf_filter_flush_parts
 	uint32_t bin_ctas_per_sm; // pass 1 (query): persistent CTAs per SM (0 = as many as fit); fewer leave room for a
 	                          // concurrent pass 2
 	// outputs (chunk-local indexing by window)

@@ -402,6 +402,12 @@ class _DeviceFilter:
                                               C.c_void_p(d_hit_bits or 0), C.c_void_p(d_valid_bits or 0),
                                               C.c_void_p(d_stats or 0)))
 
+    def flushParts(self, chunk, n_chunks):
+        """btlbf_filter_flush_parts: pass 2 of the parked build for chunk `chunk` of `n_chunks`; the byte range it covers."""
+        lo, hi = C.c_uint64(), C.c_uint64()
+        check(self._L.btlbf_filter_flush_parts(self._h, int(chunk), int(n_chunks), C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
     def orderedStats(self):
         d, r = C.c_uint64(), C.c_uint64()
         check(self._L.btlbf_filter_ordered_stats(self._h, C.byref(d), C.byref(r)))

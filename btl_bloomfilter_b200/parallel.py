@@ -318,6 +318,13 @@ class MultimemMerge:
         else:
             check(L.btlbf_merge_peers(ctx.handle, self.kind, self._bases, self.world, self.rank, self.nbytes))
 
+    def launch_range(self, lo, hi, cuda_stream=0):
+        """The peer-memory kernel for bytes [lo, hi) of the arrays only, on `cuda_stream` (0: the context's active
+        stream), without applying deferred work (btlbf_merge_peers_range)."""
+        from ._capi import check
+        check(self.ctx.L.btlbf_merge_peers_range(self.ctx.handle, self.kind, self._bases, self.world, self.rank, int(lo), int(hi),
+                                                 C.c_void_p(cuda_stream or 0)))
+
     def calibrate(self, repeats=2):
         """Times every available kernel on this box (max over ranks) and keeps the fastest.  BloomFilter only: OR is
         idempotent, so the trial merges leave a filter that is still correct -- merged -- for whatever was inserted
@@ -358,3 +365,30 @@ class MultimemMerge:
     def close(self):
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
+
+
+def pipelined_flush_merge(filt, merger, n_chunks, side, token, applied_event=None):
+    """Pass 2 of the parked build and the multi-GPU merge, pipelined: the build's pass 2 is partition-major, so chunk j
+    of the partitions is merged over NVLink (on the stream `side`) while chunk j+1 is still being applied (on the
+    current stream).  Per chunk: btlbf_filter_flush_parts -> event -> cross-rank barrier in stream order (a one-word
+    all-reduce of `token`, a tensor used for nothing else) -> btlbf_merge_peers_range of exactly that byte range.
+    On return the current stream is ordered after the last merge of every rank; applied_event (optional) is recorded on
+    the current stream behind the last chunk of pass 2.  The context's kernels must run on the current torch stream
+    (Context.set_stream(torch.cuda.current_stream().cuda_stream)).  Collective.  BloomFilter or counting filter held in symmetric
+    memory (merger = MultimemMerge); the result is the one of merger.merge()."""
+    main = torch.cuda.current_stream()
+    for j in range(n_chunks):
+        lo, hi = filt.flushParts(j, n_chunks)
+        if hi <= lo:
+            continue
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            dist.all_reduce(token, group=merger.group)  # every rank has applied this chunk
+            merger.launch_range(lo, hi, side.cuda_stream)
+    if applied_event is not None:
+        applied_event.record(main)
+    with torch.cuda.stream(side):
+        dist.all_reduce(token, group=merger.group)      # every rank has written its share of every chunk everywhere
+    main.wait_stream(side)

@@ -185,6 +185,16 @@ int btlbf_merge_multimem(btlbf_ctx *ctx, int kind, void *mc_base, int world, int
  * The two paths load different parts of the fabric; parallel.py times the split once per box (MultimemMerge.calibrate). */
 int btlbf_merge_hybrid(btlbf_ctx *ctx, int kind, void *mc_base, void *const *bases, int world, int rank,
                        uint64_t nbytes, unsigned mm_pct);
+/* Merge pipelined behind pass 2 of the build.  Pass 2 of the partitioned BloomFilter build is partition-major, so the
+ * partitions of a partial filter are final one after the other.  btlbf_filter_flush_parts applies the parked k-mers of
+ * chunk `chunk` of `n_chunks` (chunk = 0 .. n_chunks-1, in order) on the active stream and reports the byte range of
+ * the array those partitions cover; btlbf_merge_peers_range merges exactly that range (this rank's 1/world share of it)
+ * on a stream of the caller's choice and does NOT apply deferred work.  The caller orders the two with an event and a
+ * cross-rank barrier per chunk (parallel.py: pipelined_flush_merge), so that the merge of chunk j runs over NVLink while
+ * chunk j+1 is applied.  When the parked work cannot be split, chunk 0 applies all of it and reports the whole array. */
+int btlbf_filter_flush_parts(btlbf_filter *f, unsigned chunk, unsigned n_chunks, uint64_t *byte_lo, uint64_t *byte_hi);
+int btlbf_merge_peers_range(btlbf_ctx *ctx, int kind, void *const *bases, int world, int rank, uint64_t lo,
+                            uint64_t hi, void *cuda_stream);
 /* order-dependent updates (counting insert, insert_and_check): number of k-mers that had to wait for
  * the index-ordered residual rounds, and the number of such rounds, since the filter was created */
 int btlbf_filter_ordered_stats(btlbf_filter *f, uint64_t *deferred, uint64_t *rounds);

@@ -111,6 +111,26 @@ def main():
     assert np.array_equal(f7.to_numpy(), filt)
     m7.close()
 
+    # ---- pass 2 of the build and the merge pipelined in chunks of partitions (btlbf_filter_flush_parts +
+    # btlbf_merge_peers_range): k-mers parked by two insert calls, 1 / 3 / 5 chunks
+    ctx2.set_stream(torch.cuda.current_stream().cuda_stream)
+    side = torch.cuda.Stream(device=dev)
+    tok = torch.zeros(1, dtype=torch.int32, device=dev)
+    half = (my[1].size - 1) // 2
+    for n_chunks in (1, 3, 5):
+        f9, hdl9 = parallel.symmetric_filter(B.BloomFilter, bits, h, k, ctx2)
+        b0 = ctx2.counter("binned_launches")
+        f9.insertSeqs((my[0][: int(my[1][half])], my[1][: half + 1]))
+        f9.insertSeqs((my[0][int(my[1][half]):], my[1][half:] - my[1][half]))
+        assert ctx2.counter("binned_launches") >= b0 + 2
+        m9 = parallel.MultimemMerge(ctx2, hdl9, nbytes, mode="peer")
+        parallel.pipelined_flush_merge(f9, m9, n_chunks, side, tok)
+        torch.cuda.synchronize()
+        dist.barrier()
+        assert np.array_equal(f9.to_numpy(), filt), "rank %d: pipelined merge in %d chunks differs" % (rank, n_chunks)
+        m9.close()
+    ctx2.set_stream(None)
+
     # ---- query: filter replicated (after the merge), reads sharded, no collective
     r = f.containsSeqs(my)
     nq, nh, hits, valid = orc.bf_contains_seqs(filt, bits, h, k, my[0], my[1])
