@@ -82,11 +82,12 @@ def measured_peak():
 
 
 def source_sha():
-    """Hash of the kernel sources: profiles carry it so that a stale ncu figure is never attached to a new binary."""
+    """Hash of the kernel sources: profiles carry it so that a stale ncu figure is never attached to a new binary.
+    (pack.cu and ingest.cu are host-only translation units -- the 2-bit packer and the FASTA/FASTQ parser -- and are left out.)"""
     h = hashlib.sha256()
     d = os.path.join(ROOT, "btl_bloomfilter_b200", "csrc")
     for name in sorted(os.listdir(d)):
-        if name.endswith((".cu", ".cuh", ".hpp")):
+        if name.endswith((".cu", ".cuh", ".hpp")) and name not in ("pack.cu", "ingest.cu"):
             with open(os.path.join(d, name), "rb") as fh:
                 h.update(fh.read())
     return h.hexdigest()[:16]
