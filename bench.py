@@ -698,6 +698,43 @@ def run_config(env, name, cfg, S, W, headline):
                 assert np.array_equal(counts[:S2, 2], counts[:S2, 3]), "packed e2e: a queried k-mer was not found"
             e2e.update({"kmers_packed": kp, "seconds_packed": dtp,
                         "h2d_packed": (int(goffs[0][1]) + 3) // 4 + (env.read_bases + 3) // 4 + (env.n_reads + 1) * 8 + 16})
+        if not env.args.no_packed and not counting:
+            # the ASCII calls again with the library packing every chunk on host threads before the H2D copy (context
+            # option host_pack): same API and buffers as `e2e`, a quarter of the PCIe bytes, host cores spent on packing
+            try:
+                ctx.set_option("host_pack", 1)
+                ctx.set_option("host_pack_threads", max(2, min(16, HOST_THREADS // max(1, world))))
+                filt.clear()
+                for i in range(min(2, S2)):
+                    build_host_async(i, 60 + (i & 1))
+                ctx.sync()
+                merge_host()
+                for i in range(min(2, S2)):
+                    query_host_async(i, 60 + (i & 1))
+                ctx.sync()
+                filt.clear()
+                counts[:] = 0
+                env.barrier()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for i in range(S2):
+                    build_host_async(i, i)
+                if pm is not None:
+                    ctx.sync()
+                    merge_host()
+                for i in range(S2):
+                    query_host_async(i, i)
+                ctx.sync()
+                dth = time.perf_counter() - t0
+                env.barrier()
+                kh = int(counts[:S2, 0].sum() + counts[:S2, 2].sum())
+                assert kh == ke and np.array_equal(counts[:S2, 2], counts[:S2, 3]), "host_pack e2e: results differ"
+                e2e.update({"kmers_hostpack": kh, "seconds_hostpack": dth,
+                            "threads_hostpack": max(2, min(16, HOST_THREADS // max(1, world)))})
+            except Exception as ex:  # noqa: BLE001  (an optional leg must not take the line with it)
+                e2e["hostpack_error"] = "%s: %s" % (type(ex).__name__, str(ex)[:200])
+            finally:
+                ctx.set_option("host_pack", 0)
         if headline:
             def step_host_sync(i):
                 j = i % n_host
@@ -716,20 +753,23 @@ def run_config(env, name, cfg, S, W, headline):
     # ---- reductions over ranks (max time, summed work)
     if world > 1:
         t = torch.tensor([ms_total, ms_build, ms_merge, ms_query, e2e["seconds"] if e2e else 0.0,
-                          e2e.get("seconds_sync", 0.0) if e2e else 0.0, e2e.get("seconds_packed", 0.0) if e2e else 0.0],
-                         dtype=torch.float64, device=env.dev)
+                          e2e.get("seconds_sync", 0.0) if e2e else 0.0, e2e.get("seconds_packed", 0.0) if e2e else 0.0,
+                          e2e.get("seconds_hostpack", 0.0) if e2e else 0.0], dtype=torch.float64, device=env.dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, ms_build, ms_merge, ms_query = (float(x) for x in t[:4])
         w = torch.tensor([k_ins, k_qry, e2e["kmers"] if e2e else 0, launches, e2e.get("kmers_sync", 0) if e2e else 0,
-                          e2e.get("kmers_packed", 0) if e2e else 0], dtype=torch.int64, device=env.dev)
+                          e2e.get("kmers_packed", 0) if e2e else 0, e2e.get("kmers_hostpack", 0) if e2e else 0],
+                         dtype=torch.int64, device=env.dev)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        k_ins_all, k_qry_all, ke_all, launches_all, ks_all, kp_all = [int(x) for x in w]
+        k_ins_all, k_qry_all, ke_all, launches_all, ks_all, kp_all, kh_all = [int(x) for x in w]
         if e2e:
             e2e["seconds"], e2e["kmers"] = float(t[4]), ke_all
             if "seconds_sync" in e2e:
                 e2e["seconds_sync"], e2e["kmers_sync"] = float(t[5]), ks_all
             if "seconds_packed" in e2e:
                 e2e["seconds_packed"], e2e["kmers_packed"] = float(t[6]), kp_all
+            if "seconds_hostpack" in e2e:
+                e2e["seconds_hostpack"], e2e["kmers_hostpack"] = float(t[7]), kh_all
     else:
         k_ins_all, k_qry_all, launches_all = k_ins, k_qry, launches
 
@@ -774,6 +814,15 @@ def run_config(env, name, cfg, S, W, headline):
                                  "api": "btlbf_insert_seqs_packed_async + btlbf_contains_seqs_packed_async: the same batches "
                                         "held by the caller as 2 bits per base (packed once, outside the timed region, by "
                                         "btlbf_pack_seqs at %.2f Gbase/s on this host)" % env.host.get("pack_reads_gbases_s", 0.0)}
+        if "seconds_hostpack" in e2e:
+            out["e2e_hostpack"] = {"value": e2e["kmers_hostpack"] / e2e["seconds_hostpack"] / 1e9, "unit": "Gk-mer/s",
+                                   "steps": e2e["steps"], "h2d_bytes_per_step": e2e.get("h2d_packed", 0),
+                                   "d2h_bytes_per_step": e2e["d2h"], "host_threads_per_gpu": e2e["threads_hostpack"],
+                                   "api": "the calls and ASCII host buffers of `e2e`, with context option host_pack = 1: the "
+                                          "library packs every chunk to 2 bits per base on host threads before the H2D copy "
+                                          "(packing inside the timed region)"}
+        elif "hostpack_error" in e2e:
+            out["e2e_hostpack"] = {"error": e2e["hostpack_error"]}
         if "seconds_sync" in e2e:
             out["e2e_sync"] = {"value": e2e["kmers_sync"] / e2e["seconds_sync"] / 1e9, "unit": "Gk-mer/s",
                                "steps": e2e["steps_sync"], "api": "btlbf_insert_seqs + btlbf_contains_seqs (blocking)"}

@@ -18,6 +18,10 @@
 
 using namespace btl;
 
+// pack.cu: ASCII -> 2-bit codes + invalid plane on host threads
+void btl_pack_bases(const char* bases, uint64_t n_bases, uint8_t* codes, uint8_t* invalid, int threads, uint64_t* n_invalid,
+                    uint64_t* first_raw);
+
 // ---------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
 
@@ -58,6 +62,10 @@ struct Slot // one stage of the host-buffer pipeline (H2D copy | kernel | D2H co
 	DevBuf bases, invalid, hit, valid, counts, hashes, strands;
 	cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_d2h = nullptr;
 	bool used = false;
+	// pinned staging of the host-side packing ("host_pack"): the chunk as 2-bit codes + invalid plane
+	uint8_t* pk_codes = nullptr;
+	uint8_t* pk_inv = nullptr;
+	size_t pk_cap = 0; // bases the staging buffers hold
 };
 
 struct Ticket // per-call state of the host-buffer pipeline (several calls may be in flight)
@@ -182,6 +190,9 @@ struct btlbf_ctx
 	int64_t peer_unroll = 1, peer_grid = 0, peer_mode = 0; // fused multi-GPU merge: vectors in flight per thread and peer, CTAs
 	int64_t mm_unroll = 4, mm_grid = 0;                    // in-switch (multimem) merge: 8-byte words in flight per thread, CTAs
 	int64_t wrap_accumulate = 0; // 1: filters over caller-owned memory may park k-mers too (the caller flushes before reading)
+	// 1: the ASCII host-buffer calls (insert / contains) pack every chunk to 2 bits per base on host threads before the
+	// H2D copy (a quarter of the PCIe bytes; the CPU packs chunk i+1 while the GPU works on chunk i)
+	int64_t host_pack = 0, host_pack_threads = 8;
 	int64_t query_adaptive = 1;      // partitioned query: sample the batch, fall back to the early-exit kernel when few k-mers hit
 	int64_t query_adaptive_pct = 20; // ... fewer than this percentage of the sampled k-mers
 	int64_t query_adaptive_min_tiles = 256; // batches below this many 4096-window tiles are not sampled
@@ -499,6 +510,10 @@ extern "C" int btlbf_ctx_destroy(btlbf_ctx* ctx)
 	release(ctx->q_valid);
 	if (ctx->d_scalars) cudaFree(ctx->d_scalars);
 	if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+	for (int i = 0; i < 2; i++) {
+		if (ctx->slot[i].pk_codes) cudaFreeHost(ctx->slot[i].pk_codes);
+		if (ctx->slot[i].pk_inv) cudaFreeHost(ctx->slot[i].pk_inv);
+	}
 	if (ctx->own) cudaStreamDestroy(ctx->own);
 	if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
 	if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
@@ -651,6 +666,12 @@ extern "C" int btlbf_ctx_set_option(btlbf_ctx* ctx, const char* key, int64_t val
 		ctx->mm_grid = value < 0 ? 0 : value;
 	} else if (k == "wrap_accumulate") {
 		ctx->wrap_accumulate = value != 0;
+	} else if (k == "host_pack") {
+		ctx->host_pack = value != 0;
+	} else if (k == "host_pack_threads") {
+		if (value < 1 || value > 64)
+			return fail(BTLBF_ERR_ARG, "host_pack_threads out of range [1,64]");
+		ctx->host_pack_threads = value;
 	} else if (k == "query_adaptive") {
 		ctx->query_adaptive = value != 0;
 	} else if (k == "query_adaptive_min_tiles") {
@@ -2127,6 +2148,7 @@ static int host_pipeline(btlbf_ctx* ctx, btlbf_filter* f, const HashCfg* hash_on
 		tk.in_use = false;
 	}
 	const bool want_hit = h.hit_bits != nullptr, want_valid = h.valid_bits != nullptr;
+	const bool host_pack = ctx->host_pack && !h.packed && f && (op == PUB_INSERT || op == PUB_CONTAINS);
 	const bool need_hit_dev = want_hit || op == PUB_INSERT_CHECK; // list rounds OR into hit words
 	auto run_chunks = [&]() -> int {
 		TRY(ensure_idle(ctx, tk.offsets, (h.n_seqs + 1) * 8));
@@ -2146,11 +2168,38 @@ static int host_pipeline(btlbf_ctx* ctx, btlbf_filter* f, const HashCfg* hash_on
 			// the slot is free once its previous results have left the device
 			if (sl.used)
 				CU(cudaStreamWaitEvent(ctx->copy_in, sl.ev_d2h, 0));
-			if (h.packed) { // c0 is a multiple of the tile size: the chunk starts on a byte of both planes
-				CU(cudaMemcpyAsync(sl.bases.p, h.bases + (c0 >> 2), (cb + 3) >> 2, cudaMemcpyHostToDevice, ctx->copy_in));
-				if (h.invalid) {
+			// the chunk as the device will see it: 2-bit planes (the caller's, or packed here on host threads) or ASCII
+			bool c_packed = h.packed;
+			const uint8_t* c_codes = h.packed ? (const uint8_t*)h.bases + (c0 >> 2) : nullptr; // c0 is a multiple of the tile
+			const uint8_t* c_inv = h.packed && h.invalid ? h.invalid + (c0 >> 3) : nullptr;    // size: whole bytes of both planes
+			if (host_pack) {
+				if (sl.pk_cap < cb) {
+					if (sl.used)
+						CU(cudaEventSynchronize(sl.ev_h2d));
+					if (sl.pk_codes) cudaFreeHost(sl.pk_codes);
+					if (sl.pk_inv) cudaFreeHost(sl.pk_inv);
+					sl.pk_codes = sl.pk_inv = nullptr;
+					sl.pk_cap = 0;
+					const size_t want = (size_t)chunk + k + 64;
+					CU(cudaHostAlloc((void**)&sl.pk_codes, want / 4 + 64, cudaHostAllocDefault));
+					CU(cudaHostAlloc((void**)&sl.pk_inv, want / 8 + 64, cudaHostAllocDefault));
+					sl.pk_cap = want;
+				} else if (sl.used) {
+					CU(cudaEventSynchronize(sl.ev_h2d)); // the copy that last read this staging buffer has finished
+				}
+				uint64_t n_bad = 0, raw = ~0ull;
+				btl_pack_bases(h.bases + c0, cb, sl.pk_codes, sl.pk_inv, (int)ctx->host_pack_threads, &n_bad, &raw);
+				if (raw == ~0ull) { // (a raw byte 1 3 4 5 7 has no packed form: such a chunk travels as ASCII)
+					c_packed = true;
+					c_codes = sl.pk_codes;
+					c_inv = n_bad ? sl.pk_inv : nullptr;
+				}
+			}
+			if (c_packed) {
+				CU(cudaMemcpyAsync(sl.bases.p, c_codes, (cb + 3) >> 2, cudaMemcpyHostToDevice, ctx->copy_in));
+				if (c_inv) {
 					TRY(ensure_idle(ctx, sl.invalid, (size_t)chunk / 8 + k + 64));
-					CU(cudaMemcpyAsync(sl.invalid.p, h.invalid + (c0 >> 3), (cb + 7) >> 3, cudaMemcpyHostToDevice, ctx->copy_in));
+					CU(cudaMemcpyAsync(sl.invalid.p, c_inv, (cb + 7) >> 3, cudaMemcpyHostToDevice, ctx->copy_in));
 				}
 			} else
 				CU(cudaMemcpyAsync(sl.bases.p, h.bases + c0, cb, cudaMemcpyHostToDevice, ctx->copy_in));
@@ -2160,8 +2209,8 @@ static int host_pipeline(btlbf_ctx* ctx, btlbf_filter* f, const HashCfg* hash_on
 				CU(cudaStreamWaitEvent(s, sl.ev_d2h, 0));
 			ChunkIO io;
 			io.d_bases = (const uint8_t*)sl.bases.p;
-			io.packed = h.packed;
-			io.d_invalid = h.packed && h.invalid ? (const uint8_t*)sl.invalid.p : nullptr;
+			io.packed = c_packed;
+			io.d_invalid = c_packed && c_inv ? (const uint8_t*)sl.invalid.p : nullptr;
 			io.n_bases = cb;
 			io.base0 = c0;
 			io.n_windows = cw;

@@ -132,15 +132,16 @@ void pack_range(const uint8_t* bases, uint64_t lo, uint64_t hi, uint8_t* codes, 
 
 } // namespace
 
-extern "C" int btlbf_pack_seqs(const char* bases, uint64_t n_bases, uint8_t* codes, uint8_t* invalid, int threads,
-                               uint64_t* n_invalid)
+// The packer without the error convention: n_invalid = bytes that are not bases, first_raw = position of the first raw
+// byte 1 3 4 5 7 (which has no packed form) or ~0.  Used by btlbf_pack_seqs and by capi.cu's host-side packing of the
+// ASCII entry points (context option "host_pack").
+void btl_pack_bases(const char* bases, uint64_t n_bases, uint8_t* codes, uint8_t* invalid, int threads, uint64_t* n_invalid,
+                    uint64_t* first_raw)
 {
-	if (n_invalid)
-		*n_invalid = 0;
+	*n_invalid = 0;
+	*first_raw = ~0ull;
 	if (n_bases == 0)
-		return BTLBF_OK;
-	if (!bases || !codes)
-		return btlbf_set_error(BTLBF_ERR_ARG, "null argument");
+		return;
 	unsigned nt = threads > 0 ? (unsigned)threads : std::thread::hardware_concurrency();
 	if (nt < 1)
 		nt = 1;
@@ -163,12 +164,24 @@ extern "C" int btlbf_pack_seqs(const char* bases, uint64_t n_bases, uint8_t* cod
 	}
 	for (auto& th : pool)
 		th.join();
-	uint64_t total = 0, first = ~0ull;
 	for (unsigned t = 0; t < nt; t++) {
-		total += bad[t];
-		if (raw[t] < first)
-			first = raw[t];
+		*n_invalid += bad[t];
+		if (raw[t] < *first_raw)
+			*first_raw = raw[t];
 	}
+}
+
+extern "C" int btlbf_pack_seqs(const char* bases, uint64_t n_bases, uint8_t* codes, uint8_t* invalid, int threads,
+                               uint64_t* n_invalid)
+{
+	if (n_invalid)
+		*n_invalid = 0;
+	if (n_bases == 0)
+		return BTLBF_OK;
+	if (!bases || !codes)
+		return btlbf_set_error(BTLBF_ERR_ARG, "null argument");
+	uint64_t total = 0, first = ~0ull;
+	btl_pack_bases(bases, n_bases, codes, invalid, threads, &total, &first);
 	if (n_invalid)
 		*n_invalid = total;
 	if (first != ~0ull) {

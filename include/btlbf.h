@@ -225,6 +225,10 @@ int btlbf_contains_seqs_async(btlbf_filter *f, const char *bases, const uint64_t
  * refuses them).  offsets, outputs and the window convention are those of the ASCII calls and keep counting BASES.
  * Host buffers: ceil(n_bases / 4) and ceil(n_bases / 8) bytes.  Device buffers (_dev): 16-byte aligned and padded to
  * a multiple of 16 bytes.  A quarter to three eighths of the host->device bytes of the ASCII calls. ---- */
+/* Context option "host_pack" = 1 makes the ASCII host-buffer calls (btlbf_insert_seqs / btlbf_contains_seqs and their _async
+ * forms) do this packing themselves, chunk by chunk on "host_pack_threads" (default 8) host threads into pinned staging
+ * buffers, while the GPU works on the previous chunk: same results, a quarter of the PCIe bytes (a chunk that holds one of the
+ * raw bytes 1 3 4 5 7 travels as ASCII).  Off by default: at one GPU the ASCII path is not PCIe-bound. */
 int btlbf_pack_seqs(const char *bases, uint64_t n_bases, uint8_t *codes, uint8_t *invalid, int threads,
                     uint64_t *n_invalid); /* host packer (threads = 0: all cores); invalid may be NULL if the input has none */
 int btlbf_insert_seqs_packed(btlbf_filter *f, const uint8_t *codes, const uint8_t *invalid, const uint64_t *offsets,

@@ -165,3 +165,32 @@ def test_gpu_packed_device_and_async_entry_points(oracle):
     ctx.sync()
     assert int(counts[0, 0]) == n_ref and (int(counts[1, 0]), int(counts[1, 1])) == e[:2]
     assert np.array_equal(f2.to_numpy(), filt) and np.array_equal(hits, e[2]) and np.array_equal(valid, e[3])
+
+
+@pytest.mark.gpu
+def test_gpu_host_side_packing_of_the_ascii_calls(oracle, golden):
+    """Context option host_pack: the ASCII host-buffer calls pack every chunk on host threads before the H2D copy.  Same
+    results as without it, including chunks that fall back to ASCII because they hold a raw byte 1 3 4 5 7."""
+    from _backends import GpuBackend
+    be = GpuBackend(host_pack=1, host_pack_threads=3)
+    S.check_golden_bf(be, golden)
+    S.check_golden_cbf(be, golden)
+    S.check_cfg1(be, oracle, golden)
+    small = GpuBackend(host_pack=1, chunk=4096, batch=4096, resv_log2=10, list_log2=6, drain_threshold=16)
+    S.check_random_bf(small, oracle, 25, 4, 8 * 3001, seed=11, n_seqs=100, max_len=300)
+    S.check_random_cbf(small, oracle, 9, 4, 256, seed=1, n_seqs=80, max_len=200)
+    S.check_edge_cases(GpuBackend(host_pack=1), oracle)
+    # exotic bytes: some chunks travel packed, some as ASCII
+    rng = np.random.default_rng(9)
+    b, off = S.rand_batch(rng, 60, 3000, exotic=0.0005)
+    k, h, bits = 21, 3, 1 << 18
+    f = small.filter(0, bits, h, k)
+    filt = np.zeros(bits // 8, np.uint8)
+    assert f.insert((b, off)) == oracle.bf_insert_seqs(filt, bits, h, k, b, off)
+    assert np.array_equal(f.bytes(), filt)
+    e = oracle.bf_contains_seqs(filt, bits, h, k, b, off)
+    g = f.contains((b, off))
+    assert e[:2] == g[:2] and np.array_equal(e[2], g[2]) and np.array_equal(e[3], g[3])
+    # the partitioned paths on a larger batch (1 Mi-base chunks: the multi-threaded packer)
+    big = GpuBackend(host_pack=1, bin_shift=16, query_adaptive=0, chunk=1 << 20)
+    S.check_random_bf(big, oracle, 25, 4, 1 << 24, seed=5, n_seqs=600, max_len=8000, p_n=0.003)
