@@ -194,3 +194,34 @@ def test_gpu_host_side_packing_of_the_ascii_calls(oracle, golden):
     # the partitioned paths on a larger batch (1 Mi-base chunks: the multi-threaded packer)
     big = GpuBackend(host_pack=1, bin_shift=16, query_adaptive=0, chunk=1 << 20)
     S.check_random_bf(big, oracle, 25, 4, 1 << 24, seed=5, n_seqs=600, max_len=8000, p_n=0.003)
+
+
+def test_packer_property_arbitrary_bytes():
+    """Any byte string: the packer either refuses it (exactly when it holds one of the raw bytes 1 3 4 5 7 that seedTab hashes
+    but that have no 2-bit form) or produces the planes of the numpy restatement; the vector and the scalar code agree
+    whatever the alignment of the input."""
+    import btl_bloomfilter_b200 as B
+    rng = np.random.default_rng(2026)
+    raw = np.array([1, 3, 4, 5, 7], np.uint8)
+    for trial in range(300):
+        n = int(rng.integers(1, 700))
+        kind = trial % 3
+        if kind == 0:    # arbitrary bytes
+            b = rng.integers(0, 256, n).astype(np.uint8)
+        elif kind == 1:  # mostly bases, a few other bytes at or above 8
+            b = rng.choice(np.frombuffer(b"ACGTacgtuUNn*-", np.uint8), size=n)
+            b[rng.integers(0, n, max(1, n // 50))] = rng.integers(8, 256)
+        else:            # bases with bytes 0 2 6 (below 8, but not raw bases: plain invalid)
+            b = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=n)
+            b[rng.integers(0, n, max(1, n // 40))] = rng.choice(np.array([0, 2, 6], np.uint8))
+        lead = int(rng.integers(0, 9))  # misalign the input pointer
+        buf = np.concatenate([np.zeros(lead, np.uint8), b])
+        view = buf[lead:]
+        off = np.array([0, n], np.uint64)
+        if np.isin(b, raw).any():
+            with pytest.raises(B.BtlbfError, match="no 2-bit form"):
+                B.pack_seqs((view, off))
+            continue
+        pk = B.pack_seqs((view, off), keep_invalid=True)
+        codes, invalid, bad = np_pack(b)
+        assert pk.n_invalid == bad and np.array_equal(pk.codes, codes) and np.array_equal(pk.invalid, invalid), trial
